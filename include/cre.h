@@ -1,0 +1,162 @@
+/*
+ * cre.h — C-ABI of libcre_b200.so: the clip-embedding + re-ID hot path on B200 (sm_100a).
+ *
+ * The reference (UBC-AWP/vision-sam3-yolo-lameless) has no FFI: its hot path is Python that calls
+ * HuggingFace transformers / torch / a remote Qdrant server.  Each entry point below replaces the
+ * arithmetic behind one reference call site (file:line relative to the reference tree; "HF:" =
+ * transformers 5.5.0, models/dinov3_vit/):
+ *
+ *   cre_preprocess_patchify  <- services/dinov3-pipeline/app/main.py:98-107 (BGR->RGB, PIL, HF processor)
+ *                               HF:image_processing_dinov3_vit.py:45-86 (rescale, antialiased bilinear
+ *                               resize, normalise) + the im2col half of HF:modeling_dinov3_vit.py:71-81
+ *   cre_vit_forward          <- services/dinov3-pipeline/app/main.py:110-113 (model(**inputs),
+ *                               last_hidden_state.mean(dim=1)); HF:modeling_dinov3_vit.py:60-92,153-200,
+ *                               238-343,381-386,424-450,530-555
+ *   cre_pool_clips           <- services/dinov3-pipeline/app/main.py:204-208 (np.mean over frames) and
+ *                               services/tracking-service/app/reid/matcher.py:124 (e / (||e|| + 1e-8))
+ *   cre_gallery_topk         <- services/tracking-service/app/reid/matcher.py:127-132 and
+ *     + cre_merge_topk          services/dinov3-pipeline/app/main.py:168-172 (Qdrant COSINE search, limit=k)
+ *
+ * Conventions: every function returns 0 on success, a negative code on failure (-1 bad argument,
+ * -2 CUDA error, -3 unsupported shape); cre_last_error() returns the thread-local message.  Hot calls
+ * are asynchronous on the given stream (a cudaStream_t passed as void*), never allocate and never
+ * synchronise; the caller owns every buffer.  All pointers named *_dev are device pointers.
+ * A cre_ctx is bound to one device and must not be shared between host threads.
+ */
+#ifndef CRE_H_
+#define CRE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRE_ABI_VERSION 1
+#define CRE_TOPK_MAX 8
+
+typedef struct cre_ctx cre_ctx;
+
+/* HF DINOv3ViTConfig fields the forward pass needs (HF:configuration_dinov3_vit.py:74-101). */
+typedef struct cre_model_cfg {
+    int32_t hidden;       /* 768 (ViT-B/16) | 1024 (ViT-L/16); multiple of 64 */
+    int32_t layers;       /* 12 | 24 */
+    int32_t heads;        /* 12 | 16; hidden / heads must be 64 */
+    int32_t mlp;          /* 3072 | 4096 */
+    int32_t patch;        /* 16 */
+    int32_t registers;    /* 4 register tokens; prefix = 1 + registers */
+    float rope_theta;     /* 100.0 */
+    float ln_eps;         /* 1e-5 */
+} cre_model_cfg;
+
+/* Tensor kinds inside the packed weight blob.  Per-layer kinds take layer in [0, layers); global kinds
+ * take layer = -1.  Matrices are bf16 row-major [out, in] (= nn.Linear.weight); vectors are fp32. */
+enum cre_weight_kind {
+    CRE_W_PATCH = 0,      /* bf16 [hidden, 3*patch*patch]  conv weight .view(hidden, -1)            */
+    CRE_B_PATCH = 1,      /* f32  [hidden]                                                          */
+    CRE_PREFIX = 2,       /* f32  [1 + registers, hidden]  cls token then register tokens            */
+    CRE_LN_F_G = 3,       /* f32  [hidden] final norm weight                                         */
+    CRE_LN_F_B = 4,       /* f32  [hidden] final norm bias                                           */
+    CRE_LN1_G = 5, CRE_LN1_B = 6,
+    CRE_W_QKV = 7,        /* bf16 [3*hidden, hidden]  rows: q_proj, k_proj, v_proj                   */
+    CRE_B_QKV = 8,        /* f32  [3*hidden]  (k part is zero: key_bias = False)                     */
+    CRE_W_O = 9, CRE_B_O = 10,
+    CRE_LS1 = 11,         /* f32  [hidden] layer_scale1.lambda1                                      */
+    CRE_LN2_G = 12, CRE_LN2_B = 13,
+    CRE_W_UP = 14, CRE_B_UP = 15,     /* bf16 [mlp, hidden], f32 [mlp]                               */
+    CRE_W_DOWN = 16, CRE_B_DOWN = 17, /* bf16 [hidden, mlp], f32 [hidden]                            */
+    CRE_LS2 = 18,
+    CRE_WEIGHT_KINDS = 19
+};
+
+const char* cre_last_error(void);
+int32_t cre_abi_version(void);
+
+/* Packed weight blob layout: byte size, and byte offset / element count of one tensor. */
+int64_t cre_packed_weights_bytes(const cre_model_cfg* cfg);
+int64_t cre_weight_offset(const cre_model_cfg* cfg, int32_t layer, int32_t kind);
+int64_t cre_weight_elems(const cre_model_cfg* cfg, int32_t layer, int32_t kind);
+
+/* Context: keeps the device weight pointer, cached TMA descriptors, RoPE and resize-weight tables. */
+int32_t cre_create(const cre_model_cfg* cfg, const void* packed_weights_dev, int32_t device, cre_ctx** out);
+int32_t cre_destroy(cre_ctx* ctx);
+
+/* Bytes of scratch cre_vit_forward needs for `frames` frames of grid_h x grid_w patches. */
+int64_t cre_workspace_bytes(const cre_model_cfg* cfg, int32_t frames, int32_t grid_h, int32_t grid_w);
+
+/* K1. uint8 NHWC frames -> antialiased bilinear resize to (resize_h, resize_w) -> (x/255 - mean)/std
+ * -> 16x16 patchify of the top-left (resize_h/16)*(resize_w/16) patches -> bf16
+ * out[n * P, 3*256], K index = c*256 + ky*16 + kx with c in RGB order.
+ * frames_dev: n frames, each h rows of row_pitch bytes (>= 3*w), frame_pitch bytes apart.
+ * bgr != 0: channel order in memory is B,G,R (cv2), swapped on the fly. */
+int32_t cre_preprocess_patchify(cre_ctx* ctx, const uint8_t* frames_dev, int32_t n, int32_t h, int32_t w,
+                                int64_t row_pitch, int64_t frame_pitch, int32_t bgr, int32_t resize_h,
+                                int32_t resize_w, const float mean[3], const float std_[3],
+                                void* out_patches_dev, void* stream);
+
+/* K2 + K3a. bf16 patch rows [n * grid_h * grid_w, 3*256] -> ViT forward -> final LayerNorm ->
+ * mean over ALL tokens (cls + registers + patches) -> out_frame_emb_dev f32 [n, hidden].
+ * If out_tokens_dev != NULL the final-normed hidden state f32 [n, T, hidden] is also written. */
+int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_t grid_h, int32_t grid_w,
+                        void* workspace_dev, int64_t workspace_bytes, float* out_frame_emb_dev,
+                        float* out_tokens_dev, void* stream);
+
+/* K3b. Per-clip mean of frame embeddings + L2 normalisation.  clip_offsets_dev: int32 [clips + 1],
+ * frames of clip c are rows [off[c], off[c+1]).  out_mean_dev f32 [clips, dim] (raw mean, what the
+ * reference upserts), out_unit_dev f32 [clips, dim] = mean / (||mean||_2 + 1e-8). Either may be NULL. */
+int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_dev, int32_t clips,
+                       int32_t dim, float* out_mean_dev, float* out_unit_dev, void* stream);
+
+/* K4. Cosine re-ID against one gallery shard.  queries_dev f32 [q, dim] (L2-normalised by the caller via
+ * cre_pool_clips), gallery_dev bf16 [rows, dim] row-major, L2-normalised rows.  Scores are
+ * fp32-query x bf16-gallery dot products accumulated in fp32 (queries are split hi+lo bf16 internally).
+ * Writes the k best (score desc, index asc) per query: out_scores_dev f32 [q, k], out_idx_dev i32 [q, k]
+ * with idx = row_base + local row; missing entries (rows < k) are (-inf, INT32_MAX).
+ * scratch_dev: cre_gallery_scratch_bytes(q, dim, k) bytes.  dump_scores_dev (optional, may be NULL):
+ * f32 [q, rows] full score matrix for parity tests. */
+int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k);
+int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int32_t dim,
+                         const void* gallery_dev, int32_t rows, int32_t row_base, int32_t k,
+                         void* scratch_dev, int64_t scratch_bytes, float* out_scores_dev,
+                         int32_t* out_idx_dev, float* dump_scores_dev, void* stream);
+
+/* Merge `lists` candidate lists per query (e.g. one per gallery shard after the all-gather):
+ * scores_dev f32 [lists, q, k], idx_dev i32 [lists, q, k] -> best k by (score desc, index asc). */
+int32_t cre_merge_topk(const float* scores_dev, const int32_t* idx_dev, int32_t lists, int32_t q, int32_t k,
+                       float* out_scores_dev, int32_t* out_idx_dev, void* stream);
+
+/* Gallery maintenance (matcher.py:203-255 create_identity, :257-301 momentum update):
+ * row <- bf16( normalise( momentum * row + (1 - momentum) * unit_query ) ); momentum = 0 writes the query. */
+int32_t cre_gallery_update_row(void* gallery_dev, int32_t dim, int32_t row, const float* unit_query_dev,
+                               float momentum, void* stream);
+
+/* ---- building blocks exported for the parity tests (same kernels the calls above launch) ---------- */
+enum cre_gemm_epilogue {
+    CRE_EPI_BF16 = 0,  /* out_bf16 = acc + bias                         */
+    CRE_EPI_F32 = 1,   /* out_f32  = acc + bias                         */
+    CRE_EPI_GELU = 3,  /* out_bf16 = gelu_erf(acc + bias)               */
+    CRE_EPI_RESID = 4  /* out_f32 += scale * (acc + bias)   (in place)  */
+};
+/* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0, n % 32 == 0.
+ * cta_group = 1 or 2 (CTA pair, cta_group::2). bias/scale may be NULL where unused. */
+int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k,
+                      int32_t epilogue, const float* bias_dev, const float* scale_dev, void* out_dev,
+                      int32_t cta_group, void* stream);
+/* out bf16 [rows, dim] = LayerNorm(x f32 [rows, dim]) * gamma + beta */
+int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const float* beta_dev, int32_t rows,
+                           int32_t dim, float eps, void* out_dev, void* stream);
+/* Non-causal attention over frames: q/k bf16 rows [n*t, ld_qk] (q at column head*64, k at column
+ * k_col0 + head*64; q pre-scaled by 1/8, rotary already applied), vt bf16 [n*heads*64, t_pad]
+ * (v transposed), out bf16 [n*t, heads*64]. */
+int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k_col0, const void* vt_dev,
+                      int32_t t_pad, int32_t n, int32_t t, int32_t heads, void* out_dev, void* stream);
+
+/* Process-wide tuning knob: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs on
+ * 256x256 tiles (cta_group::2) for the ViT GEMMs.  Results are identical either way. */
+int32_t cre_set_cta_group(int32_t cta_group);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRE_H_ */

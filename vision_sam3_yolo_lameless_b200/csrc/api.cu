@@ -1,0 +1,596 @@
+// extern "C" surface of libcre_b200.so (include/cre.h): context, packed-weight layout, workspace
+// carving and the launch sequence of the ViT forward pass.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "gemm_tcgen05.cuh"
+#include "internal.h"
+
+using namespace cre;
+
+namespace {
+
+constexpr int64_t kAlign = 256;
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct DevTable {
+    int32_t* lo = nullptr;
+    int32_t* cnt = nullptr;
+    float* w = nullptr;
+    int kmax = 0, in = 0, out = 0;
+};
+struct RopeTable {
+    float* cos = nullptr;
+    float* sin = nullptr;
+};
+
+bool cfg_ok(const cre_model_cfg* c) {
+    if (c == nullptr) {
+        set_error("cfg is NULL");
+        return false;
+    }
+    if (c->hidden <= 0 || c->hidden % 64 != 0 || c->heads <= 0 || c->hidden != c->heads * 64) {
+        set_error("cfg: hidden=%d heads=%d (need hidden == 64*heads)", c->hidden, c->heads);
+        return false;
+    }
+    if (c->hidden != 768 && c->hidden != 1024) {
+        set_error("cfg: hidden=%d unsupported (768 | 1024)", c->hidden);
+        return false;
+    }
+    if (c->layers <= 0 || c->mlp <= 0 || c->mlp % 64 != 0 || c->patch != 16 || c->registers < 0) {
+        set_error("cfg: layers=%d mlp=%d patch=%d registers=%d unsupported", c->layers, c->mlp, c->patch, c->registers);
+        return false;
+    }
+    return true;
+}
+
+// elements and element size of one tensor kind
+void kind_shape(const cre_model_cfg* c, int kind, int64_t* elems, int* esize) {
+    const int64_t D = c->hidden, F = c->mlp, PK = 3LL * c->patch * c->patch;
+    switch (kind) {
+        case CRE_W_PATCH: *elems = D * PK; *esize = 2; break;
+        case CRE_B_PATCH: *elems = D; *esize = 4; break;
+        case CRE_PREFIX: *elems = (1 + c->registers) * D; *esize = 4; break;
+        case CRE_LN_F_G: case CRE_LN_F_B: case CRE_LN1_G: case CRE_LN1_B: case CRE_LN2_G: case CRE_LN2_B:
+        case CRE_B_O: case CRE_LS1: case CRE_LS2: case CRE_B_DOWN: *elems = D; *esize = 4; break;
+        case CRE_W_QKV: *elems = 3 * D * D; *esize = 2; break;
+        case CRE_B_QKV: *elems = 3 * D; *esize = 4; break;
+        case CRE_W_O: *elems = D * D; *esize = 2; break;
+        case CRE_W_UP: *elems = F * D; *esize = 2; break;
+        case CRE_B_UP: *elems = F; *esize = 4; break;
+        case CRE_W_DOWN: *elems = D * F; *esize = 2; break;
+        default: *elems = 0; *esize = 0; break;
+    }
+}
+inline bool kind_is_global(int kind) { return kind <= CRE_LN_F_B; }
+
+int64_t globals_bytes(const cre_model_cfg* c) {
+    int64_t off = 0;
+    for (int k = 0; k <= CRE_LN_F_B; ++k) {
+        int64_t e; int s;
+        kind_shape(c, k, &e, &s);
+        off += align_up(e * s, kAlign);
+    }
+    return off;
+}
+int64_t layer_bytes(const cre_model_cfg* c) {
+    int64_t off = 0;
+    for (int k = CRE_LN1_G; k < CRE_WEIGHT_KINDS; ++k) {
+        int64_t e; int s;
+        kind_shape(c, k, &e, &s);
+        off += align_up(e * s, kAlign);
+    }
+    return off;
+}
+int64_t weight_offset(const cre_model_cfg* c, int layer, int kind) {
+    if (kind < 0 || kind >= CRE_WEIGHT_KINDS) return -1;
+    int64_t off = 0;
+    int first = 0;
+    if (kind_is_global(kind)) {
+        if (layer != -1) return -1;
+    } else {
+        if (layer < 0 || layer >= c->layers) return -1;
+        off = globals_bytes(c) + layer * layer_bytes(c);
+        first = CRE_LN1_G;
+    }
+    for (int k = first; k < kind; ++k) {
+        int64_t e; int s;
+        kind_shape(c, k, &e, &s);
+        off += align_up(e * s, kAlign);
+    }
+    return off;
+}
+
+struct Workspace {
+    float* x;            // [M, D] residual stream, fp32
+    __nv_bfloat16* h;    // [M, D] LayerNorm output / attention output
+    __nv_bfloat16* qk;   // [M, 2D] q (pre-scaled, rotated) | k (rotated)
+    __nv_bfloat16* vt;   // [n*heads*64, t_pad] v transposed
+    __nv_bfloat16* mlp;  // [M, F]
+    int64_t vt_bytes;
+    int64_t total;
+};
+Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) {
+    const int64_t T = static_cast<int64_t>(gh) * gw + 1 + c->registers;
+    const int64_t M = frames * T, D = c->hidden, F = c->mlp;
+    const int64_t tpad = align_up(T, 8);
+    uint8_t* p = static_cast<uint8_t*>(base);
+    int64_t off = 0;
+    Workspace w;
+    auto take = [&](int64_t bytes) { uint8_t* r = p + off; off += align_up(bytes, 1024); return r; };
+    w.x = reinterpret_cast<float*>(take(M * D * 4));
+    w.h = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+    w.qk = reinterpret_cast<__nv_bfloat16*>(take(M * 2 * D * 2));
+    w.vt_bytes = static_cast<int64_t>(frames) * D * tpad * 2;
+    w.vt = reinterpret_cast<__nv_bfloat16*>(take(w.vt_bytes));
+    w.mlp = reinterpret_cast<__nv_bfloat16*>(take(M * F * 2));
+    w.total = off;
+    return w;
+}
+
+// aten _upsample_bilinear2d_aa weights for one axis (ATen/native/cpu/UpSampleKernel.cpp,
+// HelperInterpBase::_compute_indices_min_size_weights_aa with the bilinear (triangle) filter), float math.
+void build_resize_table(int in, int out, std::vector<int32_t>& lo, std::vector<int32_t>& cnt, std::vector<float>& w,
+                        int* kmax_out) {
+    const float scale = static_cast<float>(in) / static_cast<float>(out);
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const int kmax = static_cast<int>(ceilf(support)) * 2 + 1;
+    lo.assign(out, 0);
+    cnt.assign(out, 0);
+    w.assign(static_cast<size_t>(out) * kmax, 0.0f);
+    for (int i = 0; i < out; ++i) {
+        const float center = scale * (static_cast<float>(i) + 0.5f);
+        int xmin = static_cast<int>(center - support + 0.5f);
+        if (xmin < 0) xmin = 0;
+        int xmax = static_cast<int>(center + support + 0.5f);
+        if (xmax > in) xmax = in;
+        const int xsize = xmax - xmin;
+        float total = 0.0f;
+        float* wi = w.data() + static_cast<size_t>(i) * kmax;
+        for (int j = 0; j < xsize && j < kmax; ++j) {
+            float x = (static_cast<float>(j + xmin) - center + 0.5f) * invscale;
+            x = fabsf(x);
+            const float v = x < 1.0f ? 1.0f - x : 0.0f;
+            wi[j] = v;
+            total += v;
+        }
+        if (total != 0.0f)
+            for (int j = 0; j < xsize && j < kmax; ++j) wi[j] /= total;
+        lo[i] = xmin;
+        cnt[i] = xsize < kmax ? xsize : kmax;
+    }
+    *kmax_out = kmax;
+}
+
+}  // namespace
+
+struct cre_ctx {
+    cre_model_cfg cfg;
+    const uint8_t* weights;
+    int device;
+    int num_sms;
+    std::map<std::pair<int, int>, DevTable> resize_tables;
+    std::map<std::pair<int, int>, RopeTable> rope_tables;
+
+    template <typename T>
+    const T* w(int layer, int kind) const {
+        return reinterpret_cast<const T*>(weights + weight_offset(&cfg, layer, kind));
+    }
+};
+
+namespace {
+
+int get_resize_table(cre_ctx* ctx, int in, int out, DevTable* t) {
+    auto key = std::make_pair(in, out);
+    auto it = ctx->resize_tables.find(key);
+    if (it != ctx->resize_tables.end()) {
+        *t = it->second;
+        return 0;
+    }
+    std::vector<int32_t> lo, cnt;
+    std::vector<float> w;
+    int kmax = 0;
+    build_resize_table(in, out, lo, cnt, w, &kmax);
+    DevTable d;
+    d.kmax = kmax;
+    d.in = in;
+    d.out = out;
+    CRE_CUDA_OK(cudaMalloc(&d.lo, lo.size() * 4));
+    CRE_CUDA_OK(cudaMalloc(&d.cnt, cnt.size() * 4));
+    CRE_CUDA_OK(cudaMalloc(&d.w, w.size() * 4));
+    CRE_CUDA_OK(cudaMemcpy(d.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMemcpy(d.cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMemcpy(d.w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    ctx->resize_tables[key] = d;
+    *t = d;
+    return 0;
+}
+
+// HF:modeling_dinov3_vit.py:95-121,153-200: patch-centre coordinates in [-1, 1], 16 inverse frequencies,
+// angles = 2*pi*coord*inv_freq laid out [y*f0..f15, x*f0..f15] and tiled twice; fp32 cos / sin.
+int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
+    auto key = std::make_pair(gh, gw);
+    auto it = ctx->rope_tables.find(key);
+    if (it != ctx->rope_tables.end()) {
+        *t = it->second;
+        return 0;
+    }
+    const int P = gh * gw;
+    std::vector<float> c(static_cast<size_t>(P) * 64), s(static_cast<size_t>(P) * 64);
+    float inv_freq[16];
+    for (int k = 0; k < 16; ++k) inv_freq[k] = 1.0f / powf(ctx->cfg.rope_theta, static_cast<float>(k) * (4.0f / 64.0f));
+    const float two_pi = static_cast<float>(2.0 * M_PI);
+    for (int py = 0; py < gh; ++py)
+        for (int px = 0; px < gw; ++px) {
+            const float cy = 2.0f * ((static_cast<float>(py) + 0.5f) / static_cast<float>(gh)) - 1.0f;
+            const float cx = 2.0f * ((static_cast<float>(px) + 0.5f) / static_cast<float>(gw)) - 1.0f;
+            float* cr = c.data() + static_cast<size_t>(py * gw + px) * 64;
+            float* sr = s.data() + static_cast<size_t>(py * gw + px) * 64;
+            for (int k = 0; k < 16; ++k) {
+                const float ay = two_pi * cy * inv_freq[k];
+                const float ax = two_pi * cx * inv_freq[k];
+                cr[k] = cr[32 + k] = cosf(ay);
+                sr[k] = sr[32 + k] = sinf(ay);
+                cr[16 + k] = cr[48 + k] = cosf(ax);
+                sr[16 + k] = sr[48 + k] = sinf(ax);
+            }
+        }
+    RopeTable r;
+    CRE_CUDA_OK(cudaMalloc(&r.cos, c.size() * 4));
+    CRE_CUDA_OK(cudaMalloc(&r.sin, s.size() * 4));
+    CRE_CUDA_OK(cudaMemcpy(r.cos, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMemcpy(r.sin, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
+    ctx->rope_tables[key] = r;
+    *t = r;
+    return 0;
+}
+
+GemmParams base_params(int M, int N, int K) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.b_k_extent = K;
+    p.ldo = N;
+    return p;
+}
+
+int g_default_cg = 1;
+
+}  // namespace
+
+extern "C" {
+
+const char* cre_last_error(void) { return last_error(); }
+int32_t cre_abi_version(void) { return CRE_ABI_VERSION; }
+
+int64_t cre_packed_weights_bytes(const cre_model_cfg* cfg) {
+    if (!cfg_ok(cfg)) return -1;
+    return globals_bytes(cfg) + static_cast<int64_t>(cfg->layers) * layer_bytes(cfg);
+}
+int64_t cre_weight_offset(const cre_model_cfg* cfg, int32_t layer, int32_t kind) {
+    if (!cfg_ok(cfg)) return -1;
+    const int64_t off = weight_offset(cfg, layer, kind);
+    if (off < 0) set_error("weight_offset: bad (layer=%d, kind=%d)", layer, kind);
+    return off;
+}
+int64_t cre_weight_elems(const cre_model_cfg* cfg, int32_t layer, int32_t kind) {
+    if (!cfg_ok(cfg)) return -1;
+    if (weight_offset(cfg, layer, kind) < 0) {
+        set_error("weight_elems: bad (layer=%d, kind=%d)", layer, kind);
+        return -1;
+    }
+    int64_t e; int s;
+    kind_shape(cfg, kind, &e, &s);
+    return e;
+}
+
+int32_t cre_create(const cre_model_cfg* cfg, const void* packed_weights_dev, int32_t device, cre_ctx** out) {
+    if (!cfg_ok(cfg)) return -1;
+    CRE_REQUIRE(out != nullptr, "cre_create: out is NULL");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(packed_weights_dev) & 255) == 0, "cre_create: weights must be 256-byte aligned");
+    cudaDeviceProp prop;
+    CRE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    CRE_REQUIRE(prop.major == 10, "cre_create: device %d is sm_%d%d; this library is sm_100a only (no fallback)", device,
+                prop.major, prop.minor);
+    CRE_CUDA_OK(cudaSetDevice(device));
+    cre_ctx* c = new (std::nothrow) cre_ctx();
+    CRE_REQUIRE(c != nullptr, "cre_create: out of host memory");
+    c->cfg = *cfg;
+    c->weights = static_cast<const uint8_t*>(packed_weights_dev);
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+int32_t cre_destroy(cre_ctx* ctx) {
+    if (ctx == nullptr) return 0;
+    for (auto& kv : ctx->resize_tables) {
+        cudaFree(kv.second.lo);
+        cudaFree(kv.second.cnt);
+        cudaFree(kv.second.w);
+    }
+    for (auto& kv : ctx->rope_tables) {
+        cudaFree(kv.second.cos);
+        cudaFree(kv.second.sin);
+    }
+    delete ctx;
+    return 0;
+}
+
+int64_t cre_workspace_bytes(const cre_model_cfg* cfg, int32_t frames, int32_t grid_h, int32_t grid_w) {
+    if (!cfg_ok(cfg)) return -1;
+    if (frames <= 0 || grid_h <= 0 || grid_w <= 0) {
+        set_error("workspace_bytes: frames=%d grid=%dx%d", frames, grid_h, grid_w);
+        return -1;
+    }
+    return carve(cfg, frames, grid_h, grid_w, nullptr).total;
+}
+
+int32_t cre_preprocess_patchify(cre_ctx* ctx, const uint8_t* frames_dev, int32_t n, int32_t h, int32_t w,
+                                int64_t row_pitch, int64_t frame_pitch, int32_t bgr, int32_t resize_h,
+                                int32_t resize_w, const float mean[3], const float std_[3], void* out_patches_dev,
+                                void* stream) {
+    CRE_REQUIRE(ctx != nullptr && frames_dev != nullptr && out_patches_dev != nullptr, "preprocess: NULL argument");
+    CRE_REQUIRE(n > 0 && h > 0 && w > 0 && resize_h >= 16 && resize_w >= 16, "preprocess: bad sizes n=%d %dx%d -> %dx%d", n, h,
+                w, resize_h, resize_w);
+    CRE_REQUIRE(ctx->cfg.patch == 16, "preprocess: patch size must be 16");
+    PreprocArgs a;
+    a.frames = frames_dev;
+    a.n = n;
+    a.h = h;
+    a.w = w;
+    a.row_pitch = row_pitch;
+    a.frame_pitch = frame_pitch;
+    a.bgr = bgr;
+    a.gh = resize_h / 16;
+    a.gw = resize_w / 16;
+    for (int i = 0; i < 3; ++i) {
+        a.mean[i] = mean[i];
+        a.inv_std[i] = 1.0f / std_[i];
+    }
+    a.out = static_cast<__nv_bfloat16*>(out_patches_dev);
+    DevTable ty, tx;
+    int rc = get_resize_table(ctx, h, resize_h, &ty);
+    if (rc) return rc;
+    rc = get_resize_table(ctx, w, resize_w, &tx);
+    if (rc) return rc;
+    a.ty = {ty.lo, ty.cnt, ty.w, ty.kmax, ty.in, ty.out};
+    a.tx = {tx.lo, tx.cnt, tx.w, tx.kmax, tx.in, tx.out};
+    return launch_preprocess(a, static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_t grid_h, int32_t grid_w,
+                        void* workspace_dev, int64_t workspace_bytes, float* out_frame_emb_dev, float* out_tokens_dev,
+                        void* stream_) {
+    CRE_REQUIRE(ctx != nullptr && patches_dev != nullptr && workspace_dev != nullptr && out_frame_emb_dev != nullptr,
+                "vit_forward: NULL argument");
+    CRE_REQUIRE(n > 0 && grid_h > 0 && grid_w > 0, "vit_forward: bad sizes n=%d grid=%dx%d", n, grid_h, grid_w);
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "vit_forward: workspace must be 1024-byte aligned");
+    const cre_model_cfg& c = ctx->cfg;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws = carve(&c, n, grid_h, grid_w, workspace_dev);
+    CRE_REQUIRE(workspace_bytes >= ws.total, "vit_forward: workspace %lld < required %lld bytes", (long long)workspace_bytes,
+                (long long)ws.total);
+    const int P = grid_h * grid_w, prefix = 1 + c.registers, T = P + prefix;
+    const int64_t M64 = static_cast<int64_t>(n) * T;
+    CRE_REQUIRE(M64 < (1LL << 31) / 4, "vit_forward: too many token rows (%lld); split the batch", (long long)M64);
+    const int M = static_cast<int>(M64), D = c.hidden, F = c.mlp, PK = 3 * c.patch * c.patch;
+    const int tpad = static_cast<int>(align_up(T, 8));
+    const int cg = g_default_cg;
+    RopeTable rope;
+    int rc = get_rope_table(ctx, grid_h, grid_w, &rope);
+    if (rc) return rc;
+
+    // pad columns of vt must be finite zeros: P is zero there, but 0 * NaN would poison the PV product
+    CRE_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, stream));
+    rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
+    if (rc) return rc;
+    {   // patch embedding: [n*P, 768] x [D, 768]^T + bias -> token rows prefix.. of x
+        GemmParams p = base_params(n * P, D, PK);
+        p.bias = ctx->w<float>(-1, CRE_B_PATCH);
+        p.out_f32 = ws.x;
+        p.ldo = D;
+        p.tokens_per_frame = T;
+        p.prefix_tokens = prefix;
+        p.patches_per_frame = P;
+        rc = launch_gemm(EPI_PATCH, cg, patches_dev, PK, ctx->w<void>(-1, CRE_W_PATCH), PK, p, ctx->num_sms, stream);
+        if (rc) return rc;
+    }
+    for (int l = 0; l < c.layers; ++l) {
+        rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN1_G), ctx->w<float>(l, CRE_LN1_B), M, D, c.ln_eps, ws.h, stream);
+        if (rc) return rc;
+        {
+            GemmParams p = base_params(M, 3 * D, D);
+            p.bias = ctx->w<float>(l, CRE_B_QKV);
+            p.out_bf16 = ws.qk;
+            p.ldo = 2 * D;
+            p.rope_cos = rope.cos;
+            p.rope_sin = rope.sin;
+            p.tokens_per_frame = T;
+            p.prefix_tokens = prefix;
+            p.hidden = D;
+            p.q_scale = 0.125f;  // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284)
+            p.vt = ws.vt;
+            p.t_pad = tpad;
+            rc = launch_gemm(EPI_QKV, cg, ws.h, D, ctx->w<void>(l, CRE_W_QKV), D, p, ctx->num_sms, stream);
+            if (rc) return rc;
+        }
+        {
+            AttnArgs a;
+            a.qk = ws.qk;
+            a.ld_qk = 2 * D;
+            a.k_col0 = D;
+            a.vt = ws.vt;
+            a.t_pad = tpad;
+            a.n = n;
+            a.t = T;
+            a.heads = c.heads;
+            a.out = ws.h;
+            rc = launch_attention(a, stream);
+            if (rc) return rc;
+        }
+        {
+            GemmParams p = base_params(M, D, D);
+            p.bias = ctx->w<float>(l, CRE_B_O);
+            p.scale = ctx->w<float>(l, CRE_LS1);
+            p.out_f32 = ws.x;
+            p.ldo = D;
+            rc = launch_gemm(EPI_RESID, cg, ws.h, D, ctx->w<void>(l, CRE_W_O), D, p, ctx->num_sms, stream);
+            if (rc) return rc;
+        }
+        rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN2_G), ctx->w<float>(l, CRE_LN2_B), M, D, c.ln_eps, ws.h, stream);
+        if (rc) return rc;
+        {
+            GemmParams p = base_params(M, F, D);
+            p.bias = ctx->w<float>(l, CRE_B_UP);
+            p.out_bf16 = ws.mlp;
+            p.ldo = F;
+            rc = launch_gemm(EPI_GELU, cg, ws.h, D, ctx->w<void>(l, CRE_W_UP), D, p, ctx->num_sms, stream);
+            if (rc) return rc;
+        }
+        {
+            GemmParams p = base_params(M, D, F);
+            p.bias = ctx->w<float>(l, CRE_B_DOWN);
+            p.scale = ctx->w<float>(l, CRE_LS2);
+            p.out_f32 = ws.x;
+            p.ldo = D;
+            rc = launch_gemm(EPI_RESID, cg, ws.mlp, F, ctx->w<void>(l, CRE_W_DOWN), F, p, ctx->num_sms, stream);
+            if (rc) return rc;
+        }
+    }
+    return launch_final_norm_mean(ws.x, ctx->w<float>(-1, CRE_LN_F_G), ctx->w<float>(-1, CRE_LN_F_B), n, T, D, c.ln_eps,
+                                  out_frame_emb_dev, out_tokens_dev, stream);
+}
+
+int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_dev, int32_t clips, int32_t dim,
+                       float* out_mean_dev, float* out_unit_dev, void* stream) {
+    CRE_REQUIRE(frame_emb_dev != nullptr && clip_offsets_dev != nullptr, "pool_clips: NULL argument");
+    return launch_pool_clips(frame_emb_dev, clip_offsets_dev, clips, dim, out_mean_dev, out_unit_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+static const int kMaxSlots = 512;
+
+int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k) {
+    if (q <= 0 || dim <= 0 || k <= 0 || k > CRE_TOPK_MAX) {
+        set_error("gallery_scratch_bytes: q=%d dim=%d k=%d", q, dim, k);
+        return -1;
+    }
+    const int64_t a = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
+    const int64_t part = align_up(static_cast<int64_t>(q) * kMaxSlots * k * 4, 1024);
+    return a + 2 * part;
+}
+
+int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int32_t dim, const void* gallery_dev,
+                         int32_t rows, int32_t row_base, int32_t k, void* scratch_dev, int64_t scratch_bytes,
+                         float* out_scores_dev, int32_t* out_idx_dev, float* dump_scores_dev, void* stream_) {
+    CRE_REQUIRE(ctx != nullptr && queries_dev != nullptr && scratch_dev != nullptr && out_scores_dev != nullptr &&
+                    out_idx_dev != nullptr, "gallery_topk: NULL argument");
+    CRE_REQUIRE(q > 0 && dim > 0 && dim % 64 == 0 && rows >= 0, "gallery_topk: q=%d dim=%d rows=%d", q, dim, rows);
+    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX, "gallery_topk: k=%d out of range (1..%d)", k, CRE_TOPK_MAX);
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 1023) == 0, "gallery_topk: scratch must be 1024-byte aligned");
+    const int64_t need = cre_gallery_scratch_bytes(q, dim, k);
+    CRE_REQUIRE(scratch_bytes >= need, "gallery_topk: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)need);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows == 0) return launch_fill_topk(out_scores_dev, out_idx_dev, static_cast<int64_t>(q) * k, stream);
+    CRE_REQUIRE(gallery_dev != nullptr, "gallery_topk: NULL gallery");
+
+    uint8_t* sp = static_cast<uint8_t*>(scratch_dev);
+    __nv_bfloat16* a_hilo = reinterpret_cast<__nv_bfloat16*>(sp);
+    const int64_t a_bytes = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
+    const int64_t part_bytes = align_up(static_cast<int64_t>(q) * kMaxSlots * k * 4, 1024);
+    float* part_s = reinterpret_cast<float*>(sp + a_bytes);
+    int32_t* part_i = reinterpret_cast<int32_t*>(sp + a_bytes + part_bytes);
+
+    const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
+    const int slots = 2 * workers;
+    CRE_REQUIRE(slots <= kMaxSlots, "gallery_topk: %d partial slots exceed %d", slots, kMaxSlots);
+    int rc = launch_split_hi_lo(queries_dev, q, dim, a_hilo, stream);
+    if (rc) return rc;
+    rc = launch_fill_topk(part_s, part_i, static_cast<int64_t>(q) * slots * k, stream);
+    if (rc) return rc;
+    GemmParams p = base_params(q, rows, 2 * dim);
+    p.b_k_extent = dim;
+    p.topk = k;
+    p.col_base = row_base;
+    p.part_scores = part_s;
+    p.part_idx = part_i;
+    p.part_slots = slots;
+    p.dump_scores = dump_scores_dev;
+    rc = launch_gemm(EPI_TOPK, 1, a_hilo, 2 * dim, gallery_dev, dim, p, ctx->num_sms, stream);
+    if (rc) return rc;
+    return launch_merge_topk(part_s, part_i, k, static_cast<int64_t>(slots) * k, slots, k, q, k, out_scores_dev, out_idx_dev,
+                             stream);
+}
+
+int32_t cre_merge_topk(const float* scores_dev, const int32_t* idx_dev, int32_t lists, int32_t q, int32_t k,
+                       float* out_scores_dev, int32_t* out_idx_dev, void* stream) {
+    CRE_REQUIRE(scores_dev != nullptr && idx_dev != nullptr && out_scores_dev != nullptr && out_idx_dev != nullptr,
+                "merge_topk: NULL argument");
+    return launch_merge_topk(scores_dev, idx_dev, static_cast<int64_t>(q) * k, k, lists, k, q, k, out_scores_dev, out_idx_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_gallery_update_row(void* gallery_dev, int32_t dim, int32_t row, const float* unit_query_dev, float momentum,
+                               void* stream) {
+    CRE_REQUIRE(gallery_dev != nullptr && unit_query_dev != nullptr, "gallery_update_row: NULL argument");
+    return launch_gallery_update_row(static_cast<__nv_bfloat16*>(gallery_dev), dim, row, unit_query_dev, momentum,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k,
+                      int32_t epilogue, const float* bias_dev, const float* scale_dev, void* out_dev, int32_t cta_group,
+                      void* stream) {
+    CRE_REQUIRE(ctx != nullptr && a_dev != nullptr && b_dev != nullptr && out_dev != nullptr, "gemm: NULL argument");
+    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_F32 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID,
+                "gemm: epilogue %d is not exposed", epilogue);
+    CRE_REQUIRE(epilogue != CRE_EPI_RESID || scale_dev != nullptr, "gemm: RESID epilogue needs scale");
+    GemmParams p = base_params(m, n, k);
+    p.bias = bias_dev;
+    p.scale = scale_dev;
+    p.out_f32 = static_cast<float*>(out_dev);
+    p.out_bf16 = static_cast<__nv_bfloat16*>(out_dev);
+    p.ldo = n;
+    return launch_gemm(epilogue, cta_group, a_dev, k, b_dev, k, p, ctx->num_sms, static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const float* beta_dev, int32_t rows, int32_t dim,
+                           float eps, void* out_dev, void* stream) {
+    CRE_REQUIRE(x_dev != nullptr && gamma_dev != nullptr && beta_dev != nullptr && out_dev != nullptr, "layernorm: NULL argument");
+    return launch_layernorm_bf16(x_dev, gamma_dev, beta_dev, rows, dim, eps, static_cast<__nv_bfloat16*>(out_dev),
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k_col0, const void* vt_dev, int32_t t_pad,
+                      int32_t n, int32_t t, int32_t heads, void* out_dev, void* stream) {
+    CRE_REQUIRE(ctx != nullptr && qk_dev != nullptr && vt_dev != nullptr && out_dev != nullptr, "attention: NULL argument");
+    AttnArgs a;
+    a.qk = qk_dev;
+    a.ld_qk = ld_qk;
+    a.k_col0 = k_col0;
+    a.vt = vt_dev;
+    a.t_pad = t_pad;
+    a.n = n;
+    a.t = t;
+    a.heads = heads;
+    a.out = out_dev;
+    return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+// 1 = one CTA per tile (cta_group::1), 2 = CTA pairs (cta_group::2) for the ViT GEMMs
+int32_t cre_set_cta_group(int32_t cg) {
+    CRE_REQUIRE(cg == 1 || cg == 2, "set_cta_group: %d", cg);
+    g_default_cg = cg;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+// Memory-bound row kernels around the GEMMs: LayerNorm, prefix-token fill, final norm + token mean,
+// clip pooling + L2 normalisation, query hi/lo split, top-k list merge, gallery row update.
+// All are one-warp-per-row (or one-CTA-per-row) with 16-byte loads and shuffle reductions.
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace cre {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (HF:modeling_dinov3_vit.py:411,416 nn.LayerNorm, eps 1e-5): fp32 in, bf16 out.
+// One warp per row, the row lives in registers (DIM/128 float4 per lane), exact two-pass variance.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                             const float* __restrict__ b, int rows, float eps,
+                                                             __nv_bfloat16* __restrict__ out) {
+    constexpr int V = DIM / 128;  // float4 per lane
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * DIM);
+    float4 v[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i] = xr[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / DIM);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + c * c) + (d * d + e * e);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+    uint2* o = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * DIM);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+        o[lane + 32 * i] = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+                                      pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
+    }
+}
+
+int launch_layernorm_bf16(const float* x, const float* g, const float* b, int rows, int dim, float eps,
+                          __nv_bfloat16* out, cudaStream_t stream) {
+    CRE_REQUIRE(rows > 0, "layernorm: no rows");
+    const int grid = (rows + 7) / 8;
+    if (dim == 768) layernorm_bf16_kernel<768><<<grid, 256, 0, stream>>>(x, g, b, rows, eps, out);
+    else if (dim == 1024) layernorm_bf16_kernel<1024><<<grid, 256, 0, stream>>>(x, g, b, rows, eps, out);
+    else {
+        set_error("layernorm: unsupported dim %d (768 or 1024)", dim);
+        return -3;
+    }
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final LayerNorm + mean over all tokens of a frame (HF:modeling_dinov3_vit.py:547 self.norm, then
+// services/dinov3-pipeline/app/main.py:113 last_hidden_state.mean(dim=1)).  One CTA per frame,
+// warps stride over the frame's tokens and keep a per-warp partial sum in registers.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                              const float* __restrict__ b, int t, float eps,
+                                                              float* __restrict__ frame_emb,
+                                                              float* __restrict__ tokens_out) {
+    constexpr int V = DIM / 128;
+    __shared__ float4 part[8][DIM / 4];
+    const int frame = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tok = warp; tok < t; tok += 8) {
+        const size_t row = static_cast<size_t>(frame) * t + tok;
+        const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+        float4 v[V];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            v[i] = xr[lane + 32 * i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / DIM);
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + c * c) + (d * d + e * e);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+            y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+            y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+            y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+            if (tokens_out != nullptr) reinterpret_cast<float4*>(tokens_out + row * DIM)[lane + 32 * i] = y;
+            acc[i].x += y.x; acc[i].y += y.y; acc[i].z += y.z; acc[i].w += y.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) part[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    const float inv_t = 1.0f / static_cast<float>(t);
+    for (int c = threadIdx.x; c < DIM / 4; c += blockDim.x) {
+        float4 s = part[0][c];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            const float4 o = part[w][c];
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        reinterpret_cast<float4*>(frame_emb + static_cast<size_t>(frame) * DIM)[c] =
+            make_float4(s.x * inv_t, s.y * inv_t, s.z * inv_t, s.w * inv_t);
+    }
+}
+
+int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
+                           float* frame_emb, float* tokens_out, cudaStream_t stream) {
+    CRE_REQUIRE(frames > 0 && t > 0, "final_norm_mean: empty input");
+    if (dim == 768) final_norm_mean_kernel<768><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
+    else if (dim == 1024) final_norm_mean_kernel<1024><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
+    else {
+        set_error("final_norm_mean: unsupported dim %d", dim);
+        return -3;
+    }
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// cls + register tokens copied into rows [0, prefix) of every frame (HF:modeling_dinov3_vit.py:88-90)
+__global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restrict__ prefix, int t, int prefix_tokens,
+                                   int dim4, int64_t total4) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c = static_cast<int>(i % dim4);
+    const int64_t r = i / dim4;
+    const int tok = static_cast<int>(r % prefix_tokens);
+    const int64_t frame = r / prefix_tokens;
+    reinterpret_cast<float4*>(x)[(frame * t + tok) * dim4 + c] = __ldg(reinterpret_cast<const float4*>(prefix) + tok * dim4 + c);
+}
+
+int launch_fill_prefix(float* x, const float* prefix, int frames, int t, int prefix_tokens, int dim,
+                       cudaStream_t stream) {
+    const int64_t total4 = static_cast<int64_t>(frames) * prefix_tokens * (dim / 4);
+    fill_prefix_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(x, prefix, t, prefix_tokens,
+                                                                                         dim / 4, total4);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Clip pooling (services/dinov3-pipeline/app/main.py:204-208 np.mean over the clip's frame
+// embeddings) + L2 normalisation (services/tracking-service/app/reid/matcher.py:124, +1e-8).
+// One CTA per clip; thread c owns columns c, c+256, ...
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_clips_kernel(const float* __restrict__ emb, const int32_t* __restrict__ offs,
+                                                         int dim, float* __restrict__ out_mean,
+                                                         float* __restrict__ out_unit) {
+    __shared__ float red[8];
+    const int clip = blockIdx.x;
+    const int f0 = offs[clip], f1 = offs[clip + 1];
+    const float inv = f1 > f0 ? 1.0f / static_cast<float>(f1 - f0) : 0.0f;
+    float m[4] = {0.f, 0.f, 0.f, 0.f};  // dim <= 1024
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < dim) {
+            float s = 0.0f;
+            for (int f = f0; f < f1; ++f) s += emb[static_cast<size_t>(f) * dim + c];
+            m[i] = s * inv;
+            ss += m[i] * m[i];
+        }
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float scale = 1.0f / (sqrtf(tot) + 1e-8f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < dim) {
+            if (out_mean != nullptr) out_mean[static_cast<size_t>(clip) * dim + c] = m[i];
+            if (out_unit != nullptr) out_unit[static_cast<size_t>(clip) * dim + c] = m[i] * scale;
+        }
+    }
+}
+
+int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, int dim, float* out_mean,
+                      float* out_unit, cudaStream_t stream) {
+    CRE_REQUIRE(clips > 0, "pool_clips: no clips");
+    CRE_REQUIRE(dim > 0 && dim <= 1024, "pool_clips: dim %d out of range (<= 1024)", dim);
+    pool_clips_kernel<<<clips, 256, 0, stream>>>(frame_emb, offs, dim, out_mean, out_unit);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// query f32 [rows, dim] -> bf16 [rows, 2*dim] = [hi | lo], hi = bf16(q), lo = bf16(q - hi): the gallery GEMM
+// then accumulates hi.g + lo.g in fp32, i.e. an (almost) fp32 query against the bf16 gallery.
+__global__ void split_hi_lo_kernel(const float* __restrict__ q, int dim, int64_t total, __nv_bfloat16* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t r = i / dim;
+    const int c = static_cast<int>(i % dim);
+    const float v = q[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    out[r * 2 * dim + c] = hi;
+    out[r * 2 * dim + dim + c] = lo;
+}
+
+int launch_split_hi_lo(const float* q, int rows, int dim, __nv_bfloat16* out, cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(rows) * dim;
+    split_hi_lo_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(q, dim, total, out);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void fill_topk_kernel(float* __restrict__ s, int32_t* __restrict__ idx, int64_t count) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) {
+        s[i] = -INFINITY;
+        idx[i] = 0x7fffffff;
+    }
+}
+
+int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t stream) {
+    fill_topk_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, stream>>>(scores, idx, count);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge candidate lists under the total order (score desc, index asc).  One warp per query: each
+// lane scans a strided share of the lists*per_list candidates into a private sorted top-k, then
+// k rounds of a warp arg-best over the lane heads pop the global winners.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
+
+__global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
+                                                         int64_t list_stride, int64_t query_stride, int lists,
+                                                         int per_list, int q, int k, float* __restrict__ out_scores,
+                                                         int32_t* __restrict__ out_idx) {
+    const int query = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (query >= q) return;
+    const int lane = threadIdx.x & 31;
+    float bs[CRE_TOPK_MAX];
+    int bi[CRE_TOPK_MAX];
+#pragma unroll
+    for (int j = 0; j < CRE_TOPK_MAX; ++j) { bs[j] = -INFINITY; bi[j] = 0x7fffffff; }
+    const int total = lists * per_list;
+    for (int c = lane; c < total; c += 32) {
+        const int l = c / per_list, e = c % per_list;
+        const int64_t o = l * list_stride + query * query_stride + e;
+        float cs = scores[o];
+        int ci = idx[o];
+        if (better(cs, ci, bs[CRE_TOPK_MAX - 1], bi[CRE_TOPK_MAX - 1])) {
+#pragma unroll
+            for (int j = 0; j < CRE_TOPK_MAX; ++j) {
+                if (better(cs, ci, bs[j], bi[j])) {
+                    const float ts = bs[j]; const int ti = bi[j];
+                    bs[j] = cs; bi[j] = ci;
+                    cs = ts; ci = ti;
+                }
+            }
+        }
+    }
+    for (int r = 0; r < k; ++r) {
+        float ws = bs[0];
+        int wi = bi[0];
+        int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+            if (better(os, oi, ws, wi) || (os == ws && oi == wi && ol < wl)) { ws = os; wi = oi; wl = ol; }
+        }
+        if (lane == 0) {
+            out_scores[static_cast<size_t>(query) * k + r] = ws;
+            out_idx[static_cast<size_t>(query) * k + r] = wi;
+        }
+        if (lane == wl) {  // pop the winner from its lane
+#pragma unroll
+            for (int j = 0; j < CRE_TOPK_MAX - 1; ++j) { bs[j] = bs[j + 1]; bi[j] = bi[j + 1]; }
+            bs[CRE_TOPK_MAX - 1] = -INFINITY;
+            bi[CRE_TOPK_MAX - 1] = 0x7fffffff;
+        }
+    }
+}
+
+int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stride, int64_t query_stride,
+                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx,
+                      cudaStream_t stream) {
+    CRE_REQUIRE(q > 0 && lists > 0, "merge_topk: empty input");
+    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX && per_list >= 1 && per_list <= CRE_TOPK_MAX, "merge_topk: k=%d per_list=%d out of range (1..%d)", k,
+                per_list, CRE_TOPK_MAX);
+    merge_topk_kernel<<<(q + 3) / 4, 128, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, q, k,
+                                                       out_scores, out_idx);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// gallery row <- bf16(normalise(momentum * row + (1 - momentum) * unit_q))   (matcher.py:281-285); one CTA
+__global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* __restrict__ row, int dim,
+                                                                 const float* __restrict__ uq, float momentum) {
+    __shared__ float red[8];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < dim) {
+            const float old = momentum != 0.0f ? __bfloat162float(row[c]) : 0.0f;
+            v[i] = momentum * old + (1.0f - momentum) * uq[c];
+            ss += v[i] * v[i];
+        }
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float scale = 1.0f / (sqrtf(tot) + 1e-8f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < dim) row[c] = __float2bfloat16_rn(v[i] * scale);
+    }
+}
+
+int launch_gallery_update_row(__nv_bfloat16* gallery, int dim, int row, const float* unit_q, float momentum,
+                              cudaStream_t stream) {
+    CRE_REQUIRE(dim > 0 && dim <= 1024 && row >= 0, "gallery_update_row: bad dim/row");
+    gallery_update_row_kernel<<<1, 256, 0, stream>>>(gallery + static_cast<size_t>(row) * dim, dim, unit_q, momentum);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cre

@@ -1,0 +1,129 @@
+// Launcher + TMA descriptor construction for the tcgen05 GEMM family (gemm_tcgen05.cuh).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "gemm_tcgen05.cuh"
+#include "internal.h"
+
+namespace cre {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time dependency
+// on libcuda.so (it must dlopen on a GPU-less build box for the symbol-export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    CRE_REQUIRE((ld * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
+    CRE_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range: %d", box_rows);
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
+                (int)r, (long long)rows, (long long)cols, (long long)ld);
+    return 0;
+}
+
+template <int EPI, int CG>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                      cudaStream_t stream) {
+    using Cfg = GemmCfg<CG>;
+    auto* kern = gemm_tn_kernel<EPI, CG>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CRE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int rows_per_tile = kBlockM * CG;
+    const int64_t tiles = static_cast<int64_t>((p.M + rows_per_tile - 1) / rows_per_tile) *
+                          ((p.N + kBlockN - 1) / kBlockN);
+    int workers = num_sms / CG;
+    if (tiles < workers) workers = static_cast<int>(tiles);
+    if (workers < 1) workers = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CG);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    return 0;
+}
+
+int gemm_workers(int m, int n, int cg, int num_sms) {
+    const int rows_per_tile = kBlockM * cg;
+    const int64_t tiles = static_cast<int64_t>((m + rows_per_tile - 1) / rows_per_tile) * ((n + kBlockN - 1) / kBlockN);
+    int workers = num_sms / cg;
+    if (tiles < workers) workers = static_cast<int>(tiles);
+    return workers < 1 ? 1 : workers;
+}
+
+int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int64_t ldb, const GemmParams& p,
+                int num_sms, cudaStream_t stream) {
+    CRE_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
+    CRE_REQUIRE(p.K % kBlockK == 0, "gemm: K=%d must be a multiple of %d", p.K, kBlockK);
+    CRE_REQUIRE(p.b_k_extent % kBlockK == 0 && p.b_k_extent > 0, "gemm: bad b_k_extent %d", p.b_k_extent);
+    CRE_REQUIRE(epi == EPI_TOPK || p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
+    CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16(&ta, a, p.M, p.K, lda, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tb, b, p.N, p.b_k_extent, ldb, kBlockN / cg);
+    if (rc) return rc;
+#define CRE_CASE(E)                                                        \
+    case E:                                                                \
+        return cg == 1 ? launch_one<E, 1>(ta, tb, p, num_sms, stream)      \
+                       : launch_one<E, 2>(ta, tb, p, num_sms, stream);
+    switch (epi) {
+        CRE_CASE(EPI_BF16)
+        CRE_CASE(EPI_F32)
+        CRE_CASE(EPI_QKV)
+        CRE_CASE(EPI_GELU)
+        CRE_CASE(EPI_RESID)
+        CRE_CASE(EPI_PATCH)
+        case EPI_TOPK:
+            return launch_one<EPI_TOPK, 1>(ta, tb, p, num_sms, stream);
+        default:
+            set_error("gemm: unknown epilogue %d", epi);
+            return -1;
+    }
+#undef CRE_CASE
+}
+
+}  // namespace cre

@@ -1,0 +1,73 @@
+// Host-side launcher declarations shared by the translation units of libcre_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cre.h"
+
+namespace cre {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int gemm_workers(int m, int n, int cg, int num_sms);
+
+// 2-D bf16 row-major tensor [rows, cols] (row stride ld elements) -> TMA descriptor with a
+// [box_rows x 64] box and 128-byte swizzle.  Returns 0 / negative error code.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+struct GemmParams;
+// epi is a cre::GemmEpi value; cg = 1 | 2
+int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int64_t ldb, const GemmParams& p,
+                int num_sms, cudaStream_t stream);
+
+struct AttnArgs {
+    const void* qk;   // bf16 [n*t, ld_qk]
+    int ld_qk;
+    int k_col0;
+    const void* vt;   // bf16 [n*heads*64, t_pad]
+    int t_pad;
+    int n, t, heads;
+    void* out;        // bf16 [n*t, heads*64]
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+int launch_layernorm_bf16(const float* x, const float* g, const float* b, int rows, int dim, float eps,
+                          __nv_bfloat16* out, cudaStream_t stream);
+// final LayerNorm + mean over the t tokens of each frame; tokens_out optional
+int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
+                           float* frame_emb, float* tokens_out, cudaStream_t stream);
+int launch_fill_prefix(float* x, const float* prefix, int frames, int t, int prefix_tokens, int dim,
+                       cudaStream_t stream);
+int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, int dim, float* out_mean,
+                      float* out_unit, cudaStream_t stream);
+int launch_split_hi_lo(const float* q, int rows, int dim, __nv_bfloat16* out, cudaStream_t stream);
+int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t stream);
+int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stride, int64_t query_stride,
+                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx,
+                      cudaStream_t stream);
+int launch_gallery_update_row(__nv_bfloat16* gallery, int dim, int row, const float* unit_q, float momentum,
+                              cudaStream_t stream);
+
+struct ResizeTable {   // device-resident separable antialias weights for one axis
+    const int32_t* lo;   // [out] first contributing input index
+    const int32_t* cnt;  // [out] number of taps
+    const float* w;      // [out, kmax] normalised weights (zero padded)
+    int kmax;
+    int in, out;
+};
+struct PreprocArgs {
+    const uint8_t* frames;
+    int n, h, w;
+    int64_t row_pitch, frame_pitch;
+    int bgr;
+    int gh, gw;          // patch grid written (top-left gh*16 x gw*16 pixels of the resized image)
+    float mean[3], inv_std[3];
+    __nv_bfloat16* out;
+    ResizeTable ty, tx;
+};
+int launch_preprocess(const PreprocArgs& a, cudaStream_t stream);
+
+}  // namespace cre

@@ -1,0 +1,313 @@
+"""Device-side engine: owns the packed weights, the workspace and the cre_ctx, and sequences the
+C-ABI calls for   uint8 frames -> patches -> ViT -> frame embeddings -> clip embeddings -> re-ID top-k.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only; every arithmetic
+step is a libcre_b200 kernel.  Reference call sites replaced (relative to the reference tree):
+services/dinov3-pipeline/app/main.py:95-115 (extract_embedding), :204-208 (clip mean),
+services/tracking-service/app/reid/matcher.py:124-132 (normalise + cosine top-k).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # HF DINOv3ViTImageProcessor defaults
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+@dataclass(frozen=True)
+class VitConfig:
+    """The DINOv3ViTConfig fields the forward pass depends on (HF:configuration_dinov3_vit.py:74-101)."""
+
+    hidden: int = 768
+    layers: int = 12
+    heads: int = 12
+    mlp: int = 3072
+    patch: int = 16
+    registers: int = 4
+    rope_theta: float = 100.0
+    ln_eps: float = 1e-5
+
+    @staticmethod
+    def vit_b16() -> "VitConfig":
+        return VitConfig()
+
+    @staticmethod
+    def vit_l16() -> "VitConfig":
+        return VitConfig(hidden=1024, layers=24, heads=16, mlp=4096)
+
+    @staticmethod
+    def from_hf(cfg) -> "VitConfig":
+        if getattr(cfg, "model_type", "dinov3_vit") != "dinov3_vit":
+            raise ValueError(f"only dinov3_vit checkpoints are supported, got model_type={cfg.model_type!r}")
+        if getattr(cfg, "use_gated_mlp", False):
+            raise ValueError("gated-MLP DINOv3 variants are not supported")
+        if cfg.hidden_act != "gelu":
+            raise ValueError(f"hidden_act={cfg.hidden_act!r} unsupported (exact-erf gelu only)")
+        if cfg.hidden_size // cfg.num_attention_heads != 64:
+            raise ValueError("head_dim must be 64")
+        return VitConfig(
+            hidden=cfg.hidden_size,
+            layers=cfg.num_hidden_layers,
+            heads=cfg.num_attention_heads,
+            mlp=cfg.intermediate_size,
+            patch=cfg.patch_size,
+            registers=cfg.num_register_tokens,
+            rope_theta=float(cfg.rope_theta),
+            ln_eps=float(cfg.layer_norm_eps),
+        )
+
+    def c_struct(self) -> _lib.ModelCfg:
+        return _lib.ModelCfg(self.hidden, self.layers, self.heads, self.mlp, self.patch, self.registers,
+                             self.rope_theta, self.ln_eps)
+
+    @property
+    def prefix(self) -> int:
+        return 1 + self.registers
+
+    def flops_per_frame(self, grid_h: int, grid_w: int) -> float:
+        """Algorithmic FLOPs (2MNK per GEMM, 4 T^2 D per layer of attention), SURVEY.md section 8(d)."""
+        p = grid_h * grid_w
+        t = p + self.prefix
+        d, f = self.hidden, self.mlp
+        return 2.0 * p * d * 3 * self.patch * self.patch + self.layers * (8.0 * t * d * d + 4.0 * t * d * f + 4.0 * t * t * d)
+
+
+def _get(sd: Mapping[str, torch.Tensor], *names: str) -> torch.Tensor:
+    for n in names:
+        if n in sd:
+            return sd[n]
+    raise KeyError(f"none of {names} in state_dict")
+
+
+def pack_weights(cfg: VitConfig, state_dict: Mapping[str, torch.Tensor]) -> torch.Tensor:
+    """HF DINOv3ViTModel.state_dict() -> one uint8 host blob in the layout cre_weight_offset() defines
+    (bf16 matrices [out, in], fp32 vectors; q/k/v fused into one [3D, D] matrix, zero k bias)."""
+    lib = _lib.load()
+    cs = cfg.c_struct()
+    total = _lib.check_size(lib.cre_packed_weights_bytes(C.byref(cs)), "cre_packed_weights_bytes")
+    blob = torch.zeros(total, dtype=torch.uint8)
+
+    def put(layer: int, kind: int, t: torch.Tensor) -> None:
+        off = _lib.check_size(lib.cre_weight_offset(C.byref(cs), layer, kind), "cre_weight_offset")
+        n = _lib.check_size(lib.cre_weight_elems(C.byref(cs), layer, kind), "cre_weight_elems")
+        t = t.detach().to("cpu").contiguous().reshape(-1)
+        if t.numel() != n:
+            raise ValueError(f"weight kind {kind} layer {layer}: {t.numel()} elements, expected {n}")
+        if kind in _lib.BF16_KINDS:
+            raw = t.to(torch.bfloat16).view(torch.uint8)
+        else:
+            raw = t.to(torch.float32).view(torch.uint8)
+        blob[off:off + raw.numel()] = raw
+
+    sd = state_dict
+    d = cfg.hidden
+    put(-1, _lib.W_PATCH, _get(sd, "embeddings.patch_embeddings.weight").reshape(d, -1))
+    put(-1, _lib.B_PATCH, _get(sd, "embeddings.patch_embeddings.bias"))
+    put(-1, _lib.PREFIX, torch.cat([_get(sd, "embeddings.cls_token").reshape(1, d),
+                                    _get(sd, "embeddings.register_tokens").reshape(-1, d)], dim=0))
+    put(-1, _lib.LN_F_G, _get(sd, "norm.weight"))
+    put(-1, _lib.LN_F_B, _get(sd, "norm.bias"))
+    for i in range(cfg.layers):
+        def g(name: str) -> torch.Tensor:
+            return _get(sd, f"model.layer.{i}.{name}", f"layer.{i}.{name}")
+
+        def gopt(name: str, n: int) -> torch.Tensor:
+            for k in (f"model.layer.{i}.{name}", f"layer.{i}.{name}"):
+                if k in sd:
+                    return sd[k]
+            return torch.zeros(n)
+
+        put(i, _lib.LN1_G, g("norm1.weight"))
+        put(i, _lib.LN1_B, g("norm1.bias"))
+        put(i, _lib.W_QKV, torch.cat([g("attention.q_proj.weight"), g("attention.k_proj.weight"),
+                                      g("attention.v_proj.weight")], dim=0))
+        put(i, _lib.B_QKV, torch.cat([gopt("attention.q_proj.bias", d), gopt("attention.k_proj.bias", d),
+                                      gopt("attention.v_proj.bias", d)], dim=0))
+        put(i, _lib.W_O, g("attention.o_proj.weight"))
+        put(i, _lib.B_O, gopt("attention.o_proj.bias", d))
+        put(i, _lib.LS1, g("layer_scale1.lambda1"))
+        put(i, _lib.LN2_G, g("norm2.weight"))
+        put(i, _lib.LN2_B, g("norm2.bias"))
+        put(i, _lib.W_UP, g("mlp.up_proj.weight"))
+        put(i, _lib.B_UP, gopt("mlp.up_proj.bias", cfg.mlp))
+        put(i, _lib.W_DOWN, g("mlp.down_proj.weight"))
+        put(i, _lib.B_DOWN, gopt("mlp.down_proj.bias", d))
+        put(i, _lib.LS2, g("layer_scale2.lambda1"))
+    return blob
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class ClipEmbedEngine:
+    """One engine per process / GPU.  Not thread-safe (one cre_ctx, one workspace)."""
+
+    def __init__(self, cfg: VitConfig, state_dict: Mapping[str, torch.Tensor], device: Optional[int] = None,
+                 max_frames: int = 256, resize: Tuple[int, int] = (224, 224),
+                 mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD):
+        if not torch.cuda.is_available():
+            raise _lib.CreError("ClipEmbedEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.resize = (int(resize[0]), int(resize[1]))
+        self.grid = (self.resize[0] // cfg.patch, self.resize[1] // cfg.patch)
+        self.tokens = self.grid[0] * self.grid[1] + cfg.prefix
+        self.max_frames = int(max_frames)
+        self._mean = (C.c_float * 3)(*mean)
+        self._std = (C.c_float * 3)(*std)
+        self._cs = cfg.c_struct()
+        blob = pack_weights(cfg, state_dict)
+        with torch.cuda.device(self.device):
+            self.weights = blob.to(self.device)
+            ctx = C.c_void_p()
+            _lib.check(self.lib.cre_create(C.byref(self._cs), self.weights.data_ptr(), self.device_index, C.byref(ctx)),
+                       "cre_create")
+            self._ctx = ctx
+            self._ws_bytes = _lib.check_size(
+                self.lib.cre_workspace_bytes(C.byref(self._cs), self.max_frames, self.grid[0], self.grid[1]),
+                "cre_workspace_bytes")
+            self.workspace = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+            self.patches = torch.empty((self.max_frames * self.grid[0] * self.grid[1], 3 * cfg.patch * cfg.patch),
+                                       dtype=torch.bfloat16, device=self.device)
+        self._gallery_scratch: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None:
+            self.lib.cre_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------------------------------
+    def preprocess(self, frames: torch.Tensor, bgr: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 [n, H, W, 3] on the device -> bf16 patch rows [n * P, 768] (K1)."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
+            raise ValueError("frames must be a CUDA uint8 tensor [n, H, W, 3]")
+        if frames.stride(3) != 1 or frames.stride(2) != 3:
+            frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        p = self.grid[0] * self.grid[1]
+        if out is None:
+            if n > self.max_frames:
+                raise ValueError(f"{n} frames > max_frames={self.max_frames}")
+            out = self.patches[: n * p]
+        _lib.check(self.lib.cre_preprocess_patchify(
+            self._ctx, frames.data_ptr(), n, h, w, frames.stride(1), frames.stride(0), 1 if bgr else 0,
+            self.resize[0], self.resize[1], self._mean, self._std, out.data_ptr(), self._stream()),
+            "cre_preprocess_patchify")
+        return out
+
+    def forward_patches(self, patches: torch.Tensor, n: int, want_tokens: bool = False):
+        """bf16 patch rows -> f32 frame embeddings [n, D] (final LayerNorm + mean over all tokens)."""
+        if n > self.max_frames:
+            raise ValueError(f"{n} frames > max_frames={self.max_frames}")
+        emb = torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        tokens = (torch.empty((n, self.tokens, self.cfg.hidden), dtype=torch.float32, device=self.device)
+                  if want_tokens else None)
+        _lib.check(self.lib.cre_vit_forward(
+            self._ctx, patches.data_ptr(), n, self.grid[0], self.grid[1], self.workspace.data_ptr(), self._ws_bytes,
+            emb.data_ptr(), _ptr(tokens), self._stream()), "cre_vit_forward")
+        return (emb, tokens) if want_tokens else emb
+
+    def embed_frames(self, frames: torch.Tensor, bgr: bool = True) -> torch.Tensor:
+        """uint8 [n, H, W, 3] (device) -> f32 [n, D]; processed in chunks of max_frames."""
+        outs = []
+        for s in range(0, frames.shape[0], self.max_frames):
+            chunk = frames[s:s + self.max_frames]
+            patches = self.preprocess(chunk, bgr=bgr)
+            outs.append(self.forward_patches(patches, chunk.shape[0]))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def pool_clips(self, frame_emb: torch.Tensor, clip_offsets: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """f32 [F, D] + int32 offsets [Q + 1] -> (raw clip mean [Q, D], unit-norm [Q, D])  (K3b)."""
+        q = clip_offsets.numel() - 1
+        d = frame_emb.shape[1]
+        offs = clip_offsets.to(device=self.device, dtype=torch.int32).contiguous()
+        mean = torch.empty((q, d), dtype=torch.float32, device=self.device)
+        unit = torch.empty((q, d), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cre_pool_clips(frame_emb.contiguous().data_ptr(), offs.data_ptr(), q, d, mean.data_ptr(),
+                                           unit.data_ptr(), self._stream()), "cre_pool_clips")
+        return mean, unit
+
+    def gallery_topk(self, queries: torch.Tensor, gallery: torch.Tensor, k: int = 5, row_base: int = 0,
+                     dump_scores: bool = False):
+        """f32 unit queries [Q, D] x bf16 unit gallery [N, D] -> (scores [Q, k], idx [Q, k]) (K4)."""
+        if gallery.dtype != torch.bfloat16 or not gallery.is_contiguous():
+            raise ValueError("gallery must be a contiguous bf16 tensor [N, D]")
+        queries = queries.to(torch.float32).contiguous()
+        q, d = queries.shape
+        rows = gallery.shape[0]
+        need = _lib.check_size(self.lib.cre_gallery_scratch_bytes(q, d, k), "cre_gallery_scratch_bytes")
+        if self._gallery_scratch is None or self._gallery_scratch.numel() < need:
+            self._gallery_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        scores = torch.empty((q, k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        dump = torch.empty((q, rows), dtype=torch.float32, device=self.device) if dump_scores else None
+        _lib.check(self.lib.cre_gallery_topk(
+            self._ctx, queries.data_ptr(), q, d, gallery.data_ptr() if rows else None, rows, row_base, k,
+            self._gallery_scratch.data_ptr(), self._gallery_scratch.numel(), scores.data_ptr(), idx.data_ptr(),
+            _ptr(dump), self._stream()), "cre_gallery_topk")
+        return (scores, idx, dump) if dump_scores else (scores, idx)
+
+    def merge_topk(self, scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """[lists, Q, k] candidate lists -> [Q, k] under (score desc, index asc)."""
+        lists, q, k = scores.shape
+        scores = scores.contiguous()
+        idx = idx.to(torch.int32).contiguous()
+        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.cre_merge_topk(scores.data_ptr(), idx.data_ptr(), lists, q, k, out_s.data_ptr(),
+                                           out_i.data_ptr(), self._stream()), "cre_merge_topk")
+        return out_s, out_i
+
+    def gallery_update_row(self, gallery: torch.Tensor, row: int, unit_query: torch.Tensor, momentum: float) -> None:
+        _lib.check(self.lib.cre_gallery_update_row(gallery.data_ptr(), gallery.shape[1], int(row),
+                                                   unit_query.to(torch.float32).contiguous().data_ptr(),
+                                                   float(momentum), self._stream()), "cre_gallery_update_row")
+
+    # ---- building blocks (parity tests) ------------------------------------------------------
+    def gemm(self, a: torch.Tensor, b: torch.Tensor, epilogue: int = _lib.EPI_F32, bias=None, scale=None,
+             out: Optional[torch.Tensor] = None, cta_group: int = 1) -> torch.Tensor:
+        m, k = a.shape
+        n = b.shape[0]
+        if out is None:
+            dt = torch.float32 if epilogue in (_lib.EPI_F32, _lib.EPI_RESID) else torch.bfloat16
+            out = torch.zeros((m, n), dtype=dt, device=self.device)
+        _lib.check(self.lib.cre_gemm_bf16(self._ctx, a.data_ptr(), b.data_ptr(), m, n, k, epilogue, _ptr(bias),
+                                          _ptr(scale), out.data_ptr(), cta_group, self._stream()), "cre_gemm_bf16")
+        return out
+
+    def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+        rows, dim = x.shape
+        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.cre_layernorm_bf16(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, dim, eps,
+                                               out.data_ptr(), self._stream()), "cre_layernorm_bf16")
+        return out
+
+    def attention(self, qk: torch.Tensor, vt: torch.Tensor, n: int, t: int, heads: int) -> torch.Tensor:
+        out = torch.empty((n * t, heads * 64), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.cre_attention(self._ctx, qk.data_ptr(), qk.shape[1], heads * 64, vt.data_ptr(), vt.shape[1],
+                                          n, t, heads, out.data_ptr(), self._stream()), "cre_attention")
+        return out
+
+
+def set_cta_group(cg: int) -> None:
+    _lib.check(_lib.load().cre_set_cta_group(int(cg)), "cre_set_cta_group")
