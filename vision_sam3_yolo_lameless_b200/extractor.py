@@ -1,0 +1,263 @@
+"""Drop-in replacement for the reference's embedding extractor
+(``services/dinov3-pipeline/app/main.py`` class ``DINOv3Pipeline``, lines 21-296).
+
+Same method names, argument meaning, return shapes, file / NATS / Qdrant outputs and error behaviour;
+the arithmetic (BGR->RGB, HF processor, ViT forward, token mean, clip mean, similarity search) runs in
+libcre_b200 kernels through :class:`ClipEmbedEngine`.  Differences, all deliberate and opt-in except (1):
+
+1. frames of one video are embedded as ONE batch (the reference runs batch-1 forwards with a host
+   sync per frame, main.py:107-113); per-frame results are identical up to bf16 tolerance.
+2. ``gallery_backend="gpu"`` serves ``search_similar`` from a device mirror of the collection
+   (GpuGallery) with write-through to Qdrant; default ``"qdrant"`` keeps the reference behaviour.
+3. ``emit_embedding=True`` adds an ``"embedding"`` key to the results JSON (the reference omits it, which
+   makes the tracking service fall back to canonical frames, tracking main.py:292-304).
+"""
+from __future__ import annotations
+
+import json
+import os
+from pathlib import Path
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import ClipEmbedEngine, VitConfig
+from .gallery import GpuGallery
+
+DEFAULT_CONFIG = {  # services/dinov3-pipeline/app/main.py:57-68 fallback config
+    "qdrant": {"url": os.getenv("QDRANT_URL", "http://localhost:6333"), "collection_name": "cow_embeddings"},
+    "nats": {"subjects": {"video_preprocessed": "video.preprocessed", "pipeline_dinov3": "pipeline.dinov3"}},
+}
+
+
+class _PointStruct:
+    """Stand-in with qdrant_client.models.PointStruct's attribute surface (id, vector, payload), used when
+    qdrant_client is not importable (tests, benchmarks).  The real class is used when available."""
+
+    def __init__(self, id, vector, payload):
+        self.id, self.vector, self.payload = id, vector, payload
+
+
+def _point_struct(**kw):
+    try:
+        from qdrant_client.models import PointStruct  # type: ignore
+        return PointStruct(**kw)
+    except Exception:
+        return _PointStruct(**kw)
+
+
+class DINOv3Pipeline:
+    """DINOv3 embedding extraction and VectorDB storage (B200-native)."""
+
+    def __init__(self, engine: ClipEmbedEngine, config: Optional[dict] = None, nats_client=None, qdrant_client=None,
+                 results_dir: Optional[Path] = None, gallery_backend: str = "qdrant", emit_embedding: bool = False,
+                 frame_interval: Optional[int] = None):
+        if gallery_backend not in ("qdrant", "gpu"):
+            raise ValueError("gallery_backend must be 'qdrant' or 'gpu'")
+        self.config = config if config is not None else DEFAULT_CONFIG
+        self.engine = engine
+        self.device = engine.device
+        self.model = engine       # attribute kept for callers that poke at .model / .processor
+        self.processor = None
+        self.nats_client = nats_client
+        self.qdrant_client = qdrant_client
+        self.collection_name = self.config.get("qdrant", {}).get("collection_name", "cow_embeddings")
+        self.gallery_backend = gallery_backend
+        self.emit_embedding = emit_embedding
+        self.frame_interval = frame_interval
+        self.gallery: Optional[GpuGallery] = GpuGallery(engine, engine.cfg.hidden) if gallery_backend == "gpu" else None
+        self.processed_dir = Path("/app/data/processed")
+        self.results_dir = Path(results_dir) if results_dir is not None else Path("/app/data/results/dinov3")
+        self.results_dir.mkdir(parents=True, exist_ok=True)
+        self._pinned: Optional[torch.Tensor] = None
+        self._ensure_collection()
+
+    # -- main.py:70-93 ---------------------------------------------------------------------------
+    def _ensure_collection(self):
+        if self.qdrant_client is None:
+            return
+        try:
+            names = [c.name for c in self.qdrant_client.get_collections().collections]
+            if self.collection_name not in names:
+                try:
+                    from qdrant_client.models import Distance, VectorParams  # type: ignore
+                    vc = VectorParams(size=self.engine.cfg.hidden, distance=Distance.COSINE)
+                except Exception:
+                    vc = {"size": self.engine.cfg.hidden, "distance": "Cosine"}
+                self.qdrant_client.create_collection(collection_name=self.collection_name, vectors_config=vc)
+                print(f"Created Qdrant collection: {self.collection_name}")
+        except Exception as e:
+            print(f"Error ensuring collection: {e}")
+
+    # -- host staging ------------------------------------------------------------------------------
+    def _to_device(self, frames: np.ndarray) -> torch.Tensor:
+        """uint8 [n, H, W, 3] host -> device through a reusable pinned buffer (async H2D on the current stream)."""
+        n = frames.size
+        if self._pinned is None or self._pinned.numel() < n:
+            self._pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host = self._pinned[:n].view(frames.shape)
+        host.numpy()[...] = frames
+        return host.to(self.device, non_blocking=True)
+
+    def embed_frames(self, frames: np.ndarray, bgr: bool = True) -> np.ndarray:
+        """uint8 [n, H, W, 3] (cv2 BGR by default) -> float32 [n, D] per-frame embeddings (token mean)."""
+        emb = self.engine.embed_frames(self._to_device(np.ascontiguousarray(frames)), bgr=bgr)
+        return emb.cpu().numpy()
+
+    # -- main.py:95-115 ---------------------------------------------------------------------------
+    def extract_embedding(self, image: np.ndarray) -> np.ndarray:
+        """Extract DINOv3 embedding from one image (H, W, 3) uint8 BGR -> (D,) float32."""
+        if image.ndim == 3 and image.shape[2] == 3:
+            return self.embed_frames(image[None], bgr=True)[0]
+        # the reference passes non-3-channel input through unconverted (main.py:98-101); PIL then turns a
+        # 2-D array into a grey image that the HF processor replicates to RGB
+        if image.ndim == 2:
+            return self.embed_frames(np.repeat(image[None, :, :, None], 3, axis=3), bgr=False)[0]
+        raise ValueError(f"unsupported image shape {image.shape}")
+
+    # -- main.py:117-163 --------------------------------------------------------------------------
+    def extract_video_embeddings(self, video_path: Path) -> Dict[str, Any]:
+        """Extract embeddings from video frames (1 frame per second, like the reference)."""
+        import cv2
+
+        cap = cv2.VideoCapture(str(video_path))
+        if not cap.isOpened():
+            raise Exception(f"Failed to open video: {video_path}")
+        fps = int(cap.get(cv2.CAP_PROP_FPS))
+        total_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        frame_interval = self.frame_interval if self.frame_interval is not None else max(1, fps)
+        picked: List[np.ndarray] = []
+        picked_idx: List[int] = []
+        frame_count = 0
+        while True:
+            ret, frame = cap.read()
+            if not ret:
+                break
+            if frame_count % frame_interval == 0:
+                picked.append(frame)
+                picked_idx.append(frame_count)
+            frame_count += 1
+        cap.release()
+
+        embeddings = []
+        if picked:
+            embs = self.embed_frames(np.stack(picked), bgr=True)
+            for idx, e in zip(picked_idx, embs):
+                embeddings.append({"frame": idx, "time": idx / fps if fps > 0 else 0, "embedding": e.tolist()})
+        canonical_frames = []
+        if embeddings:
+            canonical_frames = [embeddings[0], embeddings[len(embeddings) // 2], embeddings[-1]]
+        return {"embeddings": embeddings, "canonical_frames": canonical_frames, "total_frames": total_frames, "fps": fps}
+
+    # -- main.py:165-186 --------------------------------------------------------------------------
+    def search_similar(self, query_embedding: np.ndarray, top_k: int = 5) -> List[Dict]:
+        """Search for similar embeddings in the VectorDB; [] on any error."""
+        try:
+            if self.gallery is not None:
+                results = self.gallery.search(query_embedding, top_k)
+            else:
+                results = self.qdrant_client.search(collection_name=self.collection_name,
+                                                    query_vector=query_embedding.tolist(), limit=top_k)
+            similar_cases = []
+            for result in results:
+                similar_cases.append({
+                    "video_id": result.payload.get("video_id", "unknown"),
+                    "score": float(result.score),
+                    "label": result.payload.get("label", None),
+                    "metadata": result.payload.get("metadata", {}),
+                })
+            return similar_cases
+        except Exception as e:
+            print(f"Error searching similar: {e}")
+            return []
+
+    # -- main.py:188-282 --------------------------------------------------------------------------
+    async def process_video(self, video_data: dict):
+        """Process a preprocessed video (NATS `video.preprocessed` handler).  Never raises for a bad video."""
+        video_id = video_data["video_id"]
+        processed_path = Path(video_data["processed_path"])
+        print(f"DINOv3 pipeline processing video {video_id}")
+        if not processed_path.exists():
+            print(f"Processed video not found: {processed_path}")
+            return
+        try:
+            embedding_data = self.extract_video_embeddings(processed_path)
+            if embedding_data["embeddings"]:
+                avg_embedding = np.mean([np.array(e["embedding"]) for e in embedding_data["embeddings"]], axis=0)
+            else:
+                print(f"No embeddings extracted for {video_id}")
+                return
+            similar_cases = self.search_similar(avg_embedding, top_k=5)
+            if similar_cases:
+                labels = [case["label"] for case in similar_cases if case["label"] is not None]
+                if labels:
+                    lame_count = sum(1 for label in labels if label == 1)
+                    neighbor_evidence = lame_count / len(labels)
+                else:
+                    neighbor_evidence = 0.5
+            else:
+                neighbor_evidence = 0.5
+            payload = {
+                "video_id": video_id,
+                "filename": video_data.get("filename", ""),
+                "uploaded_at": video_data.get("uploaded_at", ""),
+                "label": None,
+                "metadata": video_data.get("metadata", {}),
+            }
+            try:
+                if self.gallery is not None:
+                    self.gallery.upsert(video_id, avg_embedding, payload)
+                if self.qdrant_client is not None:
+                    point = _point_struct(id=video_id, vector=avg_embedding.tolist(), payload=payload)
+                    self.qdrant_client.upsert(collection_name=self.collection_name, points=[point])
+                print(f"Stored embedding in VectorDB for {video_id}")
+            except Exception as e:
+                print(f"Error storing in VectorDB: {e}")
+            results = {
+                "video_id": video_id,
+                "embedding_dim": len(avg_embedding),
+                "num_embeddings": len(embedding_data["embeddings"]),
+                "similar_cases": similar_cases,
+                "neighbor_evidence": neighbor_evidence,
+                "canonical_frames": embedding_data["canonical_frames"],
+            }
+            if self.emit_embedding:
+                results["embedding"] = avg_embedding.tolist()
+            results_file = self.results_dir / f"{video_id}_dinov3.json"
+            with open(results_file, "w") as f:
+                json.dump(results, f, indent=2)
+            pipeline_result = {
+                "video_id": video_id,
+                "pipeline": "dinov3",
+                "results_path": str(results_file),
+                "neighbor_evidence": neighbor_evidence,
+                "similar_cases": similar_cases,
+                "embedding_dim": len(avg_embedding),
+            }
+            await self.nats_client.publish(self.config["nats"]["subjects"]["pipeline_dinov3"], pipeline_result)
+            print(f"DINOv3 pipeline completed for {video_id}")
+        except Exception as e:
+            print(f"Error in DINOv3 pipeline for {video_id}: {e}")
+            import traceback
+            traceback.print_exc()
+
+    # -- main.py:284-296 --------------------------------------------------------------------------
+    async def start(self):
+        import asyncio
+
+        await self.nats_client.connect()
+        subject = self.config["nats"]["subjects"]["video_preprocessed"]
+        print(f"DINOv3 pipeline subscribed to {subject}")
+        await self.nats_client.subscribe(subject, self.process_video)
+        print("DINOv3 pipeline service started. Waiting for videos...")
+        await asyncio.Event().wait()
+
+
+def build_pipeline_from_hf(model, **kw) -> DINOv3Pipeline:
+    """Convenience: HF DINOv3ViTModel (already loaded by the caller) -> B200 pipeline."""
+    max_frames = kw.pop("max_frames", 256)
+    resize = kw.pop("resize", (224, 224))
+    cfg = VitConfig.from_hf(model.config)
+    engine = ClipEmbedEngine(cfg, model.state_dict(), max_frames=max_frames, resize=resize)
+    return DINOv3Pipeline(engine, **kw)
