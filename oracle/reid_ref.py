@@ -71,3 +71,49 @@ def momentum_update(old_unit: np.ndarray, new_emb: np.ndarray, momentum: float =
     new_unit = new_emb / (np.linalg.norm(new_emb) + 1e-8)
     upd = momentum * old_unit + (1 - momentum) * new_unit
     return upd / (np.linalg.norm(upd) + 1e-8)
+
+
+class MatcherOracle:
+    """numpy restatement of CowReIDMatcher's read/decide/write cycle (matcher.py:104-301) over an in-memory
+    COSINE gallery: match_embedding -> threshold decision -> momentum update or create.  Returns dicts shaped
+    like tests/golden/reid_scenario.json steps."""
+
+    def __init__(self, momentum: float = 0.9, auto_create: bool = True, store_dtype=np.float64):
+        self.momentum, self.auto_create = momentum, auto_create
+        self.vectors, self.cow_ids = [], []
+        self.store_dtype = store_dtype
+
+    def match_embedding(self, e: np.ndarray, top_k: int = 5):
+        if not self.vectors:
+            return None, []
+        q = l2_normalise(np.asarray(e, dtype=np.float64))
+        g = np.stack(self.vectors).astype(np.float64)
+        s = g @ q
+        order = np.lexsort((np.arange(len(s)), -s))[:top_k]
+        cands = [{"cow_id": self.cow_ids[r], "similarity": float(s[r]), "confidence": score_to_confidence(s[r]), "row": int(r)}
+                 for r in order]
+        best = cands[0] if cands[0]["similarity"] >= SIMILARITY_THRESHOLD_LOW else None
+        return best, cands
+
+    def match_or_create(self, e: np.ndarray):
+        best, cands = self.match_embedding(e)
+        if best is not None and best["similarity"] >= SIMILARITY_THRESHOLD_MEDIUM:
+            r = best["row"]
+            self.vectors[r] = momentum_update(self.vectors[r].astype(np.float64), np.asarray(e, np.float64),
+                                              self.momentum).astype(self.store_dtype)
+            return {"cow_id": best["cow_id"], "similarity": best["similarity"], "confidence": best["confidence"], "is_new": False}
+        if self.auto_create:
+            self.vectors.append(l2_normalise(np.asarray(e, dtype=np.float64)).astype(self.store_dtype))
+            self.cow_ids.append(f"COW-{len(self.cow_ids) + 1:04d}")
+            return {"cow_id": self.cow_ids[-1], "similarity": 1.0, "confidence": "high", "is_new": True}
+        return {"cow_id": "UNKNOWN", "similarity": cands[0]["similarity"] if cands else 0.0, "confidence": "low", "is_new": True}
+
+
+def neighbor_evidence(similar_cases) -> float:
+    """services/dinov3-pipeline/app/main.py:216-225"""
+    if not similar_cases:
+        return 0.5
+    labels = [c["label"] for c in similar_cases if c["label"] is not None]
+    if not labels:
+        return 0.5
+    return sum(1 for l in labels if l == 1) / len(labels)

@@ -1,0 +1,72 @@
+"""pytest configuration.  `-m "not gpu"`: oracle vs golden vectors, host logic, C-ABI symbols (no compute).
+`-m gpu`: parity of the CUDA path against the oracle / golden vectors, called through the C-ABI."""
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) and the built libcre_b200.so")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests fail loudly (not skip) when selected on a box without CUDA, unless deselected with -m 'not gpu'."""
+    return
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return GOLDEN
+
+
+_MODELS = {}
+
+
+def hf_model_cached(kind="b", layers=None):
+    """Seeded random-init HF models are expensive to build; share them across tests."""
+    from oracle import common
+
+    key = (kind, layers)
+    if key not in _MODELS:
+        if kind == "b":
+            _MODELS[key] = common.hf_model(layers=12 if layers is None else layers)
+        else:
+            _MODELS[key] = common.hf_model(hidden=1024, mlp=4096, layers=24 if layers is None else layers, heads=16)
+    return _MODELS[key]
+
+
+@pytest.fixture(scope="session")
+def model_b():
+    return hf_model_cached("b")
+
+
+_ENGINES = {}
+
+
+def engine_cached(kind="b", layers=None, max_frames=64, resize=(224, 224)):
+    from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
+
+    key = (kind, layers, max_frames, resize)
+    if key not in _ENGINES:
+        m = hf_model_cached(kind, layers)
+        _ENGINES[key] = (ClipEmbedEngine(VitConfig.from_hf(m.config), m.state_dict(), max_frames=max_frames, resize=resize), m)
+    return _ENGINES[key]
+
+
+@pytest.fixture(scope="session")
+def engine_b():
+    """ViT-B/16, 12 layers, seed 0 -- the model the golden vectors were produced with."""
+    return engine_cached("b")
+
+
+@pytest.fixture(scope="session")
+def engine_small():
+    """ViT-B/16 width, 1 layer: enough for kernel-level tests that only need a context."""
+    return engine_cached("b", layers=1, max_frames=16)[0]

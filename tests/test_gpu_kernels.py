@@ -1,0 +1,200 @@
+"""Kernel-level parity on a B200, every call through the C-ABI (ctypes -> libcre_b200.so).  Floating-point
+kernels are compared with a plain fp32 PyTorch statement of the same op; tolerances are bf16-rounding level
+and written next to each check.  Index work (top-k, merge) is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import common, preprocess_ref, reid_ref
+from vision_sam3_yolo_lameless_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert torch.isfinite(got).all(), "non-finite output"
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 32, 64), (1000, 768, 768), (4021, 2304, 768), (515, 768, 3072),
+                                   (300, 1024, 1024), (257, 96, 128)])
+def test_gemm_epilogues(engine_small, cg, m, n, k):
+    eng, dev = engine_small, engine_small.device
+    g = torch.Generator(device=dev).manual_seed(m * 7 + n)
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(n, k, device=dev, generator=g) * 0.5).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev, generator=g)
+    ref = a.float() @ b.float().t() + bias
+    assert rel_err(eng.gemm(a, b, _lib.EPI_F32, bias=bias, cta_group=cg), ref) < 2e-5          # fp32 accumulate
+    assert rel_err(eng.gemm(a, b, _lib.EPI_BF16, bias=bias, cta_group=cg), ref) < 5e-3         # bf16 output rounding
+    assert rel_err(eng.gemm(a, b, _lib.EPI_GELU, bias=bias, cta_group=cg), torch.nn.functional.gelu(ref)) < 5e-3
+    scale = torch.rand(n, device=dev, generator=g) + 0.5
+    res = torch.randn(m, n, device=dev, generator=g)
+    out = res.clone()
+    eng.gemm(a, b, _lib.EPI_RESID, bias=bias, scale=scale, out=out, cta_group=cg)
+    assert rel_err(out, res + scale * ref) < 2e-5
+    out = eng.gemm(a, b, _lib.EPI_F32, bias=None, cta_group=cg)
+    assert rel_err(out, ref - bias) < 2e-5
+
+
+def test_gemm_rejects_bad_shapes(engine_small):
+    eng, dev = engine_small, engine_small.device
+    a = torch.zeros(8, 100, device=dev, dtype=torch.bfloat16)
+    b = torch.zeros(32, 100, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(_lib.CreError, match="multiple of 64"):
+        eng.gemm(a, b)
+    with pytest.raises(_lib.CreError):
+        eng.gemm(a[:, :64].contiguous(), b[:, :64].contiguous(), epilogue=7)
+
+
+@pytest.mark.parametrize("rows,dim", [(1003, 768), (77, 1024), (1, 768)])
+def test_layernorm(engine_small, rows, dim):
+    dev = engine_small.device
+    x = torch.randn(rows, dim, device=dev) * 3 + 1.5
+    g, b = torch.randn(dim, device=dev), torch.randn(dim, device=dev)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-5)
+    assert rel_err(engine_small.layernorm(x, g, b), ref) < 5e-3                                 # bf16 output
+
+
+@pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12)])
+def test_attention(engine_small, t, n, heads):
+    dev = engine_small.device
+    d = heads * 64
+    gen = torch.Generator(device=dev).manual_seed(t)
+    q, k, v = (torch.randn(n, t, heads, 64, device=dev, generator=gen) for _ in range(3))
+    qs, kb, vb = (q * 0.125).to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    qk = torch.cat([qs.reshape(n * t, d), kb.reshape(n * t, d)], dim=1).contiguous()
+    tpad = (t + 7) // 8 * 8
+    vt = torch.zeros(n * heads * 64, tpad, device=dev, dtype=torch.bfloat16)
+    vt.view(n, heads, 64, tpad)[:, :, :, :t] = vb.permute(0, 2, 3, 1)
+    out = engine_small.attention(qk, vt, n, t, heads)
+    att = torch.softmax(qs.float().permute(0, 2, 1, 3) @ kb.float().permute(0, 2, 3, 1), dim=-1)
+    ref = (att @ vb.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(n * t, d)
+    assert rel_err(out, ref) < 8e-3                                                             # bf16 P and bf16 output
+
+
+@pytest.mark.parametrize("h,w,kind,bgr", [(1080, 1920, "noise", True), (720, 1280, "smooth", True), (224, 224, "noise", False),
+                                          (270, 482, "noise", True), (100, 60, "noise", True), (2160, 3840, "noise", True)])
+def test_preprocess_vs_oracle(engine_small, h, w, kind, bgr):
+    fr = common.noise_frames(2, h, w, seed=3) if kind == "noise" else common.smooth_frames(2, h, w, seed=3)
+    ref = preprocess_ref.patchify(preprocess_ref.preprocess(fr, bgr=bgr))
+    out = engine_small.preprocess(torch.from_numpy(fr).to(engine_small.device), bgr=bgr)
+    assert out.shape == (2 * 196, 768) and out.dtype == torch.bfloat16
+    err = (out.float().cpu() - torch.from_numpy(ref)).abs().max().item()
+    assert err < 1.2e-2, err                    # |x| <= 2.64 -> bf16 half-ulp 7.8e-3, plus fp32 summation-order noise
+
+
+def test_preprocess_vs_hf_processor_golden(engine_small, golden):
+    from oracle.make_golden import PREPROCESS_CASES, frames_for
+    want = np.load(golden / "preprocess.npz")
+    for name, n, h, w, kind, seed in PREPROCESS_CASES:
+        fr = frames_for(kind, n, h, w, seed)
+        out = engine_small.preprocess(torch.from_numpy(fr).to(engine_small.device), bgr=True).float().cpu().numpy()
+        ref = preprocess_ref.patchify(want[name][None])
+        assert np.abs(out - ref).max() < 1.2e-2, name
+
+
+def test_preprocess_plain_bilinear_would_fail(engine_small):
+    """The antialias filter is mandatory: a non-antialiased resize of noise differs grossly (hard part 3)."""
+    fr = common.noise_frames(1, 1080, 1920, seed=9)
+    x = torch.from_numpy(fr[..., ::-1].copy()).permute(0, 3, 1, 2).float() / 255
+    plain = torch.nn.functional.interpolate(x, (224, 224), mode="bilinear", antialias=False)
+    plain = (plain - torch.tensor(preprocess_ref.MEAN).view(1, 3, 1, 1)) / torch.tensor(preprocess_ref.STD).view(1, 3, 1, 1)
+    out = engine_small.preprocess(torch.from_numpy(fr).to(engine_small.device), bgr=True).float().cpu().numpy()
+    assert np.abs(out - preprocess_ref.patchify(plain.numpy())).max() > 0.5
+
+
+def test_preprocess_pitched_and_unaligned_input(engine_small):
+    """Row pitch > 3*w and a base pointer that is not 16-byte aligned (scalar-load path) give identical results."""
+    dev = engine_small.device
+    fr = common.noise_frames(2, 300, 500, seed=4)
+    base = engine_small.preprocess(torch.from_numpy(fr).to(dev)).clone()
+    wide = torch.zeros(2, 300, 512, 3, dtype=torch.uint8, device=dev)
+    wide[:, :, :500] = torch.from_numpy(fr).to(dev)
+    assert torch.equal(engine_small.preprocess(wide[:, :, :500]), base)
+    flat = torch.zeros(2 * 300 * 500 * 3 + 1, dtype=torch.uint8, device=dev)
+    flat[1:] = torch.from_numpy(fr).to(dev).reshape(-1)
+    assert torch.equal(engine_small.preprocess(flat[1:].view(2, 300, 500, 3)), base)
+
+
+def test_pool_clips(engine_small):
+    dev = engine_small.device
+    emb = torch.randn(23, 768, device=dev) * 2 + 0.3
+    offs = np.array([0, 1, 1, 9, 23], dtype=np.int32)          # a one-frame clip, an EMPTY clip, ragged lengths
+    mean, unit = engine_small.pool_clips(emb, torch.from_numpy(offs))
+    ref_mean = reid_ref.clip_mean(emb.cpu().numpy(), np.array([0, 1, 1, 9, 23]))
+    ref_mean[1] = 0.0                                          # empty clip -> zeros (np.mean would give NaN)
+    np.testing.assert_allclose(mean.cpu().numpy(), ref_mean, atol=2e-6 * 8)
+    np.testing.assert_allclose(unit.cpu().numpy(), reid_ref.l2_normalise(ref_mean), atol=1e-6)
+    assert torch.isfinite(unit).all()
+
+
+@pytest.mark.parametrize("q,n,dim", [(3, 1000, 768), (130, 5000, 768), (64, 100000, 768), (5, 3, 768), (9, 700, 1024)])
+def test_gallery_topk_bit_exact(engine_small, q, n, dim):
+    eng, dev = engine_small, engine_small.device
+    gen = torch.Generator(device=dev).manual_seed(q + n)
+    g = torch.nn.functional.normalize(torch.randn(n, dim, device=dev, generator=gen), dim=1)
+    if n > 10:
+        g[n // 2] = g[7]
+        g[n - 1] = g[7]                                        # exact duplicate rows -> ties
+    gb = g.to(torch.bfloat16).contiguous()
+    qv = torch.nn.functional.normalize(torch.randn(q, dim, device=dev, generator=gen), dim=1)
+    qv[0] = torch.nn.functional.normalize(g[min(7, n - 1)] + 0.05 * torch.randn(dim, device=dev, generator=gen), dim=0)
+    s, i, dump = eng.gallery_topk(qv, gb, k=5, row_base=1000, dump_scores=True)
+    ref_scores = reid_ref.cosine_scores(qv.cpu().numpy(), gb.float().cpu().numpy())
+    np.testing.assert_allclose(dump.cpu().numpy(), ref_scores, atol=5e-6)      # fp32 query (hi+lo bf16) x bf16 gallery
+    kk = min(5, n)
+    ref_top, ref_idx = reid_ref.topk_rule(dump.cpu().numpy(), kk, row_base=1000)
+    assert (i.cpu().numpy()[:, :kk] == ref_idx).all(), "top-k indices must be bit-exact under (score desc, index asc)"
+    assert (s.cpu().numpy()[:, :kk] == ref_top).all()
+    if kk < 5:
+        assert (i.cpu().numpy()[:, kk:] == 0x7FFFFFFF).all() and np.isneginf(s.cpu().numpy()[:, kk:]).all()
+    if n > 10:
+        assert i[0].tolist()[:3] == [1007, 1000 + n // 2, 1000 + n - 1]
+
+
+def test_gallery_topk_empty_and_k_range(engine_small):
+    eng, dev = engine_small, engine_small.device
+    qv = torch.nn.functional.normalize(torch.randn(4, 768, device=dev), dim=1)
+    s, i = eng.gallery_topk(qv, torch.zeros(0, 768, device=dev, dtype=torch.bfloat16), k=5)
+    assert np.isneginf(s.cpu().numpy()).all() and (i.cpu().numpy() == 0x7FFFFFFF).all()
+    gb = torch.nn.functional.normalize(torch.randn(300, 768, device=dev), dim=1).to(torch.bfloat16)
+    for k in (1, 8):
+        s, i, dump = eng.gallery_topk(qv, gb, k=k, dump_scores=True)
+        assert (i.cpu().numpy() == reid_ref.topk_rule(dump.cpu().numpy(), k)[1]).all()
+    with pytest.raises(_lib.CreError):
+        eng.gallery_topk(qv, gb, k=9)
+
+
+def test_sharded_topk_merge_equals_whole(engine_small):
+    """Row shards scored separately (global indices via row_base) + cre_merge_topk == one scan of the whole gallery."""
+    eng, dev = engine_small, engine_small.device
+    gen = torch.Generator(device=dev).manual_seed(11)
+    n, q = 10007, 33
+    g = torch.nn.functional.normalize(torch.randn(n, 768, device=dev, generator=gen), dim=1)
+    g[9000] = g[5]
+    g[123] = g[5]
+    gb = g.to(torch.bfloat16).contiguous()
+    qv = torch.nn.functional.normalize(torch.randn(q, 768, device=dev, generator=gen), dim=1)
+    qv[0] = g[5]
+    whole_s, whole_i = eng.gallery_topk(qv, gb, k=5)
+    from vision_sam3_yolo_lameless_b200.sharded import shard_range
+    parts = [eng.gallery_topk(qv, gb[lo:hi].contiguous(), k=5, row_base=lo) for lo, hi in (shard_range(n, r, 8) for r in range(8))]
+    ms, mi = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, whole_i) and torch.equal(ms, whole_s)
+    rs, ri = reid_ref.merge_rule(torch.stack([p[0] for p in parts]).cpu().numpy(), torch.stack([p[1] for p in parts]).cpu().numpy(), 5)
+    assert (ri == mi.cpu().numpy()).all() and mi[0].tolist()[:3] == [5, 123, 9000]
+
+
+def test_gallery_update_row(engine_small):
+    eng, dev = engine_small, engine_small.device
+    gal = torch.nn.functional.normalize(torch.randn(6, 768, device=dev), dim=1).to(torch.bfloat16)
+    old = gal[2].float().cpu().numpy().astype(np.float64)
+    new = np.random.default_rng(0).standard_normal(768)
+    uq = torch.from_numpy(reid_ref.l2_normalise(new).astype(np.float32)).to(dev)
+    eng.gallery_update_row(gal, 2, uq, 0.9)
+    np.testing.assert_allclose(gal[2].float().cpu().numpy(), reid_ref.momentum_update(old, new, 0.9), atol=4e-4)   # bf16 store
+    eng.gallery_update_row(gal, 4, uq, 0.0)
+    np.testing.assert_allclose(gal[4].float().cpu().numpy(), reid_ref.l2_normalise(new), atol=4e-4)

@@ -1,0 +1,167 @@
+"""End-to-end parity on a B200 through the public API: uint8 frames -> clip embeddings -> re-ID, against the
+fp32 oracle and against the reference's own outputs in tests/golden/.  Gate (BASELINE.json): per-clip embedding
+cosine >= 0.999 vs fp32; top-k indices bit-exact on the same scores."""
+import asyncio
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import common, fake_services, preprocess_ref, reid_ref, vit_ref
+from oracle.make_golden import EMBED_CASES, frames_for, reid_queries, write_clip
+
+from conftest import engine_cached
+
+pytestmark = pytest.mark.gpu
+
+COS_GATE = 0.999          # BASELINE.json north_star tolerance
+SUBJECTS = {"nats": {"subjects": {"pipeline_dinov3": "pipeline.dinov3", "video_preprocessed": "video.preprocessed"}},
+            "qdrant": {"collection_name": "cow_embeddings"}}
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_forward_tokens_vs_fp32_oracle(engine_b, cg):
+    from vision_sam3_yolo_lameless_b200.engine import set_cta_group
+    eng, model = engine_b
+    fr = common.noise_frames(5, 224, 224, seed=4)
+    pv = preprocess_ref.preprocess(fr, bgr=True)
+    ref_tok = vit_ref.vit_forward(model.state_dict(), torch.from_numpy(pv), heads=12, layers=12)
+    set_cta_group(cg)
+    try:
+        patches = eng.preprocess(torch.from_numpy(fr).to(eng.device), bgr=True)
+        emb, tok = eng.forward_patches(patches, 5, want_tokens=True)
+    finally:
+        set_cta_group(1)
+    tok, emb = tok.cpu(), emb.cpu()
+    assert torch.isfinite(tok).all()
+    assert ((tok - ref_tok).abs().max() / ref_tok.abs().max()).item() < 2e-2        # bf16 operands through 12 layers
+    cos = common.cosine(emb.numpy(), ref_tok.mean(1).numpy())
+    assert (cos >= 0.9999).all(), cos
+
+
+def test_extract_embedding_vs_reference_golden(engine_b, golden, tmp_path):
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    eng, _ = engine_b
+    pipe = DINOv3Pipeline(eng, config=SUBJECTS, results_dir=tmp_path)
+    want = np.load(golden / "embed_vitb.npz")
+    for name, h, w, kind, seed in EMBED_CASES:
+        e = pipe.extract_embedding(frames_for(kind, 1, h, w, seed)[0])
+        assert e.shape == (768,) and e.dtype == np.float32
+        assert common.cosine(e, want[name]) >= COS_GATE, name
+        assert np.abs(e - want[name]).max() < 2e-2, name
+    g = pipe.extract_embedding(common.noise_frames(1, 224, 224, 36)[0, :, :, 0])
+    assert common.cosine(g, want["gray_224"]) >= COS_GATE
+
+
+def test_vit_l_vs_reference_golden(golden):
+    eng, _ = engine_cached("l", max_frames=8)
+    want = np.load(golden / "embed_vitl.npz")
+    for name, h, w, kind, seed in EMBED_CASES[:2]:
+        e = eng.embed_host_frames(frames_for(kind, 1, h, w, seed)).cpu().numpy()[0]
+        assert e.shape == (1024,) and common.cosine(e, want[name]) >= COS_GATE, name
+
+
+@pytest.mark.parametrize("size,t", [(518, 1029), (592, 1374)])
+def test_large_grid_vs_fp32_oracle(size, t):
+    """BASELINE config 3: 518x518 (32x32 patches, 6 px unused border) and 592x592 (1369 patches); no resize."""
+    eng, model = engine_cached("b", layers=2, max_frames=2, resize=(size, size))
+    assert eng.tokens == t
+    fr = common.smooth_frames(2, size, size, seed=6)
+    pv = preprocess_ref.preprocess(fr, bgr=True, size=(size, size))
+    ref = vit_ref.frame_embeddings(model.state_dict(), torch.from_numpy(pv), heads=12, layers=2).numpy()
+    got = eng.embed_host_frames(fr).cpu().numpy()
+    assert (common.cosine(got, ref) >= 0.9999).all()
+
+
+def test_clip_embeddings_meet_cosine_gate(engine_b):
+    """Per-clip mean-pooled, L2-normalised embedding vs the fp32 oracle; host frames through the pipelined H2D path,
+    chunked (max_frames=64 < 150 frames) and ragged clips."""
+    eng, model = engine_b
+    fr = np.concatenate([common.noise_frames(80, 224, 224, seed=8), common.smooth_frames(70, 224, 224, seed=9)])
+    offs = np.array([0, 50, 80, 150], dtype=np.int32)
+    emb = eng.embed_host_frames(fr)
+    mean, unit = eng.pool_clips(emb, torch.from_numpy(offs))
+    pv = preprocess_ref.preprocess(fr, bgr=True)
+    ref = vit_ref.frame_embeddings(model.state_dict(), torch.from_numpy(pv), heads=12, layers=12).numpy()
+    ref_unit = reid_ref.l2_normalise(reid_ref.clip_mean(ref, offs))
+    assert (common.cosine(emb.cpu().numpy(), ref) >= COS_GATE).all()
+    cos = common.cosine(unit.cpu().numpy(), ref_unit)
+    assert (cos >= COS_GATE).all(), cos
+    np.testing.assert_allclose(np.linalg.norm(unit.cpu().numpy(), axis=1), 1.0, atol=1e-5)
+    # batch invariance: a frame's embedding does not depend on what else is in the batch (bitwise)
+    again = eng.embed_host_frames(fr[40:47])
+    assert torch.equal(again, emb[40:47])
+    # pinned input takes the zero-staging path and gives the same bits
+    pinned = torch.from_numpy(fr).pin_memory()
+    assert torch.equal(eng.embed_host_frames(pinned), emb)
+
+
+def test_process_video_vs_reference_transcript(engine_b, golden, tmp_path):
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    eng, _ = engine_b
+    want = json.load(open(golden / "process_video.json"))
+    for backend in ("qdrant", "gpu"):
+        qd, nats = fake_services.FakeQdrant(), fake_services.FakeNats()
+        out = tmp_path / backend
+        pipe = DINOv3Pipeline(eng, config=SUBJECTS, nats_client=nats, qdrant_client=qd, results_dir=out, gallery_backend=backend)
+        for i, (seed, t) in enumerate(zip(want["clip_seeds"], want["transcript"])):
+            clip = tmp_path / f"{backend}{i}.avi"
+            write_clip(clip, seed=seed)
+            asyncio.run(pipe.process_video({"video_id": f"vid-{i}", "processed_path": str(clip), "filename": clip.name,
+                                            "metadata": {"n": i}}))
+            res, ref = json.load(open(out / f"vid-{i}_dinov3.json")), t["results"]
+            assert list(res) == list(ref) and res["num_embeddings"] == ref["num_embeddings"]
+            assert res["neighbor_evidence"] == ref["neighbor_evidence"]
+            assert [c["video_id"] for c in res["similar_cases"]] == [c["video_id"] for c in ref["similar_cases"]]
+            np.testing.assert_allclose([c["score"] for c in res["similar_cases"]], [c["score"] for c in ref["similar_cases"]], atol=5e-3)
+            for a, b in zip(res["canonical_frames"], ref["canonical_frames"]):
+                assert a["frame"] == b["frame"] and a["time"] == b["time"]
+                assert common.cosine(np.array(a["embedding"]), np.array(b["embedding"])) >= COS_GATE
+            assert nats.published[-1][0] == "pipeline.dinov3" and list(nats.published[-1][1]) == list(t["message"])
+            qd.set_payload("cow_embeddings", {"label": i % 2}, [f"vid-{i}"])
+            if pipe.gallery is not None:
+                pipe.gallery.payloads[pipe.gallery._row_of[f"vid-{i}"]]["label"] = i % 2
+
+
+def test_matcher_scenario_vs_reference_transcript(engine_b, golden):
+    from vision_sam3_yolo_lameless_b200.reid import CowReIDMatcher
+    eng, _ = engine_b
+    want = json.load(open(golden / "reid_scenario.json"))
+    qd = fake_services.FakeQdrant()
+    m = CowReIDMatcher(engine=eng, qdrant_client=qd)
+    asyncio.run(m.connect())
+    for k, ((name, q), step) in enumerate(zip(reid_queries(), want["steps"])):
+        got = m.match_or_create(np.asarray(q), video_id=f"video-{name}", track_id=k)
+        assert (got.cow_id, got.confidence, got.is_new_identity) == (step["cow_id"], step["confidence"], step["is_new"]), name
+        assert abs(got.similarity - step["similarity"]) < 5e-3, name        # gallery rows are stored in bf16
+    _, cands = m.match_embedding(np.asarray(reid_queries()[0][1]))
+    assert [c.cow_id for c in cands] == [c["cow_id"] for c in want["final_candidates"]]
+    np.testing.assert_allclose([c.similarity for c in cands], [c["similarity"] for c in want["final_candidates"]], atol=5e-3)
+
+
+def test_full_size_properties(engine_b):
+    """BASELINE sizes, size-independent properties: (1) a 100k-row gallery scan returns, for queries that ARE gallery
+    rows, that row first with score ~1; (2) permuting the clips permutes the result; (3) 8-way sharding + merge is
+    idempotent w.r.t. the single scan; (4) a 1080p batch gives the same bits as the same frames one by one."""
+    eng, _ = engine_b
+    dev = eng.device
+    gen = torch.Generator(device=dev).manual_seed(7)
+    n, q = 100_000, 1024
+    gal = torch.nn.functional.normalize(torch.randn(n, 768, device=dev, generator=gen), dim=1).to(torch.bfloat16)
+    rows = torch.randperm(n, device=dev, generator=gen)[:q]
+    qv = torch.nn.functional.normalize(gal[rows].float(), dim=1)
+    s, i = eng.gallery_topk(qv, gal, k=5)
+    assert torch.equal(i[:, 0].long(), rows) and (s[:, 0] > 0.998).all()
+    assert (s[:, :-1] >= s[:, 1:]).all(), "scores must be sorted descending"
+    perm = torch.randperm(q, device=dev, generator=gen)
+    s2, i2 = eng.gallery_topk(qv[perm].contiguous(), gal, k=5)
+    assert torch.equal(i2, i[perm]) and torch.equal(s2, s[perm])
+    from vision_sam3_yolo_lameless_b200.sharded import shard_range
+    parts = [eng.gallery_topk(qv, gal[lo:hi], k=5, row_base=lo) for lo, hi in (shard_range(n, r, 8) for r in range(8))]
+    ms, mi = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+    big = torch.randint(0, 256, (6, 1080, 1920, 3), device=dev, dtype=torch.uint8, generator=gen)
+    whole = eng.embed_frames(big)
+    single = torch.cat([eng.embed_frames(big[j:j + 1]) for j in range(6)])
+    assert torch.equal(whole, single)

@@ -1,0 +1,209 @@
+"""Host-side mirrors of the reference interfaces (extractor.py / gallery.py / reid.py) against the reference's
+own transcripts in tests/golden/, with the kernels replaced by the oracle-backed StubEngine.  CPU only."""
+import asyncio
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import common, fake_services
+from oracle.make_golden import reid_queries, write_clip
+from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+from vision_sam3_yolo_lameless_b200.gallery import GpuGallery
+from vision_sam3_yolo_lameless_b200.reid import CowReIDMatcher, TrackingReIDHandler
+
+from stub_engine import StubEngine
+
+SUBJECTS = {"nats": {"subjects": {"pipeline_dinov3": "pipeline.dinov3", "video_preprocessed": "video.preprocessed"}},
+            "qdrant": {"collection_name": "cow_embeddings"}}
+
+
+@pytest.fixture(scope="module")
+def stub(model_b):
+    return StubEngine(model_b)
+
+
+def make_pipeline(stub, tmp_path, **kw):
+    qd, nats = fake_services.FakeQdrant(), fake_services.FakeNats()
+    pipe = DINOv3Pipeline(stub, config=SUBJECTS, nats_client=nats, qdrant_client=qd, results_dir=tmp_path, **kw)
+    return pipe, qd, nats
+
+
+def test_ensure_collection_created(stub, tmp_path):
+    pipe, qd, _ = make_pipeline(stub, tmp_path)
+    assert "cow_embeddings" in qd.collections and pipe.collection_name == "cow_embeddings"
+
+
+def test_extract_video_embeddings_matches_reference(stub, tmp_path, golden):
+    want = json.load(open(golden / "video.json"))
+    pipe, _, _ = make_pipeline(stub, tmp_path)
+    stub.calls.clear()
+    got = pipe.extract_video_embeddings(golden / "clip_48x64_15fps.avi")
+    assert stub.calls == [("embed", (3, 48, 64, 3))], "sampled frames must go to the engine as ONE batch"
+    assert set(got) == {"embeddings", "canonical_frames", "total_frames", "fps"}
+    assert got["fps"] == want["fps"] and got["total_frames"] == want["total_frames"]
+    assert [e["frame"] for e in got["embeddings"]] == want["frames"]
+    assert [e["time"] for e in got["embeddings"]] == want["times"]
+    assert [e["frame"] for e in got["canonical_frames"]] == want["canonical"]
+    assert all(isinstance(v, float) for v in got["embeddings"][0]["embedding"])
+    np.testing.assert_allclose(np.array([e["embedding"] for e in got["embeddings"]]), np.array(want["embeddings"]), atol=2e-4)
+    with pytest.raises(Exception, match="Failed to open video"):
+        pipe.extract_video_embeddings(tmp_path / "nope.avi")
+
+
+def test_extract_embedding_shapes(stub, tmp_path, golden):
+    pipe, _, _ = make_pipeline(stub, tmp_path)
+    want = np.load(golden / "embed_vitb.npz")
+    e = pipe.extract_embedding(common.noise_frames(1, 224, 224, 31)[0])
+    assert e.shape == (768,) and e.dtype == np.float32
+    np.testing.assert_allclose(e, want["noise_224_a"], atol=2e-4)
+    g = pipe.extract_embedding(common.noise_frames(1, 224, 224, 36)[0, :, :, 0])
+    np.testing.assert_allclose(g, want["gray_224"], atol=2e-4)
+    with pytest.raises(ValueError):
+        pipe.extract_embedding(np.zeros((4, 4, 4), dtype=np.uint8))
+
+
+@pytest.mark.parametrize("backend", ["qdrant", "gpu"])
+def test_process_video_transcript_matches_reference(stub, tmp_path, golden, backend):
+    want = json.load(open(golden / "process_video.json"))
+    pipe, qd, nats = make_pipeline(stub, tmp_path, gallery_backend=backend)
+    for i, (seed, t) in enumerate(zip(want["clip_seeds"], want["transcript"])):
+        clip = tmp_path / f"v{i}.avi"
+        write_clip(clip, seed=seed)
+        asyncio.run(pipe.process_video({"video_id": f"vid-{i}", "processed_path": str(clip), "filename": clip.name,
+                                        "metadata": {"n": i}}))
+        res = json.load(open(tmp_path / f"vid-{i}_dinov3.json"))
+        ref = t["results"]
+        assert list(res) == list(ref), "results JSON must be key-for-key identical (order included)"
+        assert res["video_id"] == ref["video_id"] and res["embedding_dim"] == ref["embedding_dim"] == 768
+        assert res["num_embeddings"] == ref["num_embeddings"] and res["neighbor_evidence"] == ref["neighbor_evidence"]
+        assert [c["video_id"] for c in res["similar_cases"]] == [c["video_id"] for c in ref["similar_cases"]]
+        assert [c["label"] for c in res["similar_cases"]] == [c["label"] for c in ref["similar_cases"]]
+        assert [c["metadata"] for c in res["similar_cases"]] == [c["metadata"] for c in ref["similar_cases"]]
+        tol = 1e-4 if backend == "qdrant" else 4e-3          # gpu backend stores bf16 rows
+        np.testing.assert_allclose([c["score"] for c in res["similar_cases"]], [c["score"] for c in ref["similar_cases"]], atol=tol)
+        assert [f["frame"] for f in res["canonical_frames"]] == [f["frame"] for f in ref["canonical_frames"]]
+        np.testing.assert_allclose(res["canonical_frames"][1]["embedding"], ref["canonical_frames"][1]["embedding"], atol=2e-4)
+        subject, msg = nats.published[-1]
+        assert subject == t["subject"] == "pipeline.dinov3"
+        assert list(msg) == list(t["message"]) and Path(msg["results_path"]).name == t["message"]["results_path"]
+        assert msg["pipeline"] == "dinov3" and msg["neighbor_evidence"] == t["message"]["neighbor_evidence"]
+        # "labelled later": the admin UI sets the label on the stored point
+        qd.set_payload("cow_embeddings", {"label": i % 2}, [f"vid-{i}"])
+        if pipe.gallery is not None:
+            pipe.gallery.payloads[pipe.gallery._row_of[f"vid-{i}"]]["label"] = i % 2
+        stored = qd.retrieve("cow_embeddings", [f"vid-{i}"], with_vectors=True)[0]
+        assert stored.payload["filename"] == clip.name and stored.payload["metadata"] == {"n": i}
+    n = len(nats.published)
+    asyncio.run(pipe.process_video({"video_id": "missing", "processed_path": str(tmp_path / "nope.avi")}))
+    assert len(nats.published) == n, "a missing file returns silently (main.py:195-197)"
+    asyncio.run(pipe.process_video({"video_id": "empty", "processed_path": str(tmp_path)}))   # cannot be opened
+    assert len(nats.published) == n, "handler never raises out of the callback (main.py:279-282)"
+
+
+def test_emit_embedding_is_opt_in(stub, tmp_path):
+    clip = tmp_path / "c.avi"
+    write_clip(clip, seed=51)
+    pipe, _, _ = make_pipeline(stub, tmp_path, emit_embedding=True, frame_interval=20)
+    asyncio.run(pipe.process_video({"video_id": "x", "processed_path": str(clip)}))
+    res = json.load(open(tmp_path / "x_dinov3.json"))
+    assert len(res["embedding"]) == 768 and res["num_embeddings"] == 3   # frames 0, 20, 40
+
+
+def test_gallery_matches_fake_qdrant(stub):
+    rng = np.random.default_rng(3)
+    qd = fake_services.FakeQdrant()
+    qd.create_collection("c")
+    gal = GpuGallery(stub, 768, capacity=4)
+    from types import SimpleNamespace
+    vecs = rng.standard_normal((9, 768))
+    vecs[5] = vecs[2] * 2.0                                   # exact tie after normalisation
+    for i, v in enumerate(vecs):
+        gal.upsert(f"p{i}", v, {"i": i})
+        qd.upsert("c", [SimpleNamespace(id=f"p{i}", vector=v.tolist(), payload={"i": i})])
+    assert len(gal) == 9 and gal.capacity >= 9
+    q = vecs[2] + 0.1 * rng.standard_normal(768)
+    got, want = gal.search(q, 5), qd.search("c", q.tolist(), 5)
+    assert [p.id for p in got][:2] == ["p2", "p5"]
+    assert [p.id for p in got] == [p.id for p in want]
+    np.testing.assert_allclose([p.score for p in got], [p.score for p in want], atol=4e-3)
+    assert GpuGallery(stub, 768).search(q, 5) == []
+    gal.upsert("p0", vecs[1], {"i": 100})                    # overwrite keeps the row
+    assert len(gal) == 9 and gal.payloads[0] == {"i": 100}
+
+
+def test_matcher_scenario_matches_reference(stub, golden):
+    want = json.load(open(golden / "reid_scenario.json"))
+    qd = fake_services.FakeQdrant()
+    m = CowReIDMatcher(qdrant_url="fake://", engine=stub, qdrant_client=qd)
+    with pytest.raises(RuntimeError, match="Not connected"):
+        m.match_embedding(np.zeros(768))
+    asyncio.run(m.connect())
+    assert "cow_identities" in qd.collections
+    for k, ((name, q), step) in enumerate(zip(reid_queries(), want["steps"])):
+        got = m.match_or_create(np.asarray(q), video_id=f"video-{name}", track_id=k)
+        assert (got.cow_id, got.confidence, got.is_new_identity) == (step["cow_id"], step["confidence"], step["is_new"]), name
+        assert abs(got.similarity - step["similarity"]) < 5e-3, name
+    best, cands = m.match_embedding(np.asarray(reid_queries()[0][1]))
+    assert best.cow_id == "COW-0001"
+    assert [c.cow_id for c in cands] == [c["cow_id"] for c in want["final_candidates"]]
+    st = m.get_statistics()
+    assert st == {**want["statistics"], "total_identities": 4}
+    assert len(qd.collections["cow_identities"]["ids"]) == 4, "writes go through to Qdrant"
+    ident = m.get_identity(best.identity_id)
+    assert ident.cow_id == "COW-0001" and ident.total_sightings == 4
+    assert [i.cow_id for i in m.get_all_identities()] == ["COW-0001", "COW-0002", "COW-0003", "COW-0004"]
+    # a second matcher connecting to the same Qdrant mirrors the stored points onto the device
+    m2 = CowReIDMatcher(qdrant_url="fake://", engine=stub, qdrant_client=qd)
+    asyncio.run(m2.connect())
+    assert m2.identity_counter == 4 and m2.match_embedding(np.asarray(reid_queries()[0][1]))[0].cow_id == "COW-0001"
+    # batched read path == one-by-one read path on a snapshot
+    qs = np.stack([q for _, q in reid_queries()])
+    for (b1, c1), q in zip(m2.match_embeddings(qs), qs):
+        b2, c2 = m2.match_embedding(q)
+        assert [c.cow_id for c in c1] == [c.cow_id for c in c2] and (b1 is None) == (b2 is None)
+
+
+def test_matcher_without_auto_create(stub):
+    m = CowReIDMatcher(engine=stub, auto_create_identities=False)
+    asyncio.run(m.connect())
+    r = m.match_or_create(np.ones(768), "v", 0)
+    assert r.cow_id == "UNKNOWN" and r.is_new_identity and r.confidence == "low" and r.similarity == 0.0
+    with pytest.raises(RuntimeError):
+        asyncio.run(CowReIDMatcher().connect())
+
+
+def test_tracking_handler_flow(stub, tmp_path, golden):
+    """tracking main.py:268-381: embedding is read from the results FILE (canonical-frame mean when there is no
+    'embedding' key), every pending track is re-identified with the same video embedding, JSON rewritten, NATS out."""
+    nats = fake_services.FakeNats()
+    m = CowReIDMatcher(engine=stub)
+    asyncio.run(m.connect())
+    saved = []
+
+    async def save_track(video_id, track, match):
+        saved.append((video_id, track["track_id"], match.cow_id))
+
+    h = TrackingReIDHandler(m, nats, tmp_path, save_track=save_track)
+    vid = json.load(open(golden / "video.json"))
+    canon = [{"frame": f, "time": 0.0, "embedding": e} for f, e in zip(vid["frames"], vid["embeddings"])]
+    (tmp_path / "a_dinov3.json").write_text(json.dumps({"video_id": "a", "canonical_frames": canon}))
+    (tmp_path / "a_tracking.json").write_text(json.dumps({"video_id": "a", "tracks": []}))
+    h.pending_tracks["a"] = [{"track_id": 1, "start_frame": 0, "end_frame": 10}, {"track_id": 2, "start_frame": 3, "end_frame": 9}]
+    asyncio.run(h.process_dinov3_results({"video_id": "a", "results_path": str(tmp_path / "a_dinov3.json")}))
+    np.testing.assert_allclose(h.video_embeddings["a"], np.mean(np.array(vid["embeddings"]), axis=0))
+    subject, msg = nats.published[-1]
+    assert subject == "tracking.reid.match" and msg["video_id"] == "a" and msg["new_identities"] == 1
+    assert [(r["track_id"], r["cow_id"], r["is_new"]) for r in msg["matches"]] == [(1, "COW-0001", True), (2, "COW-0001", False)]
+    assert set(msg["matches"][0]) == {"track_id", "cow_id", "identity_id", "similarity", "confidence", "is_new"}
+    out = json.load(open(tmp_path / "a_tracking.json"))
+    assert out["reid_complete"] is True and len(out["reid_results"]) == 2
+    assert saved == [("a", 1, "COW-0001"), ("a", 2, "COW-0001")] and "a" not in h.pending_tracks
+    # 'embedding' key takes precedence (tracking main.py:292-293); no pending tracks -> only cached
+    (tmp_path / "b_dinov3.json").write_text(json.dumps({"embedding": [1.0] * 768, "canonical_frames": canon}))
+    asyncio.run(h.process_dinov3_results({"video_id": "b", "results_path": str(tmp_path / "b_dinov3.json")}))
+    assert h.video_embeddings["b"].tolist() == [1.0] * 768 and len(nats.published) == 1
+    asyncio.run(h.process_dinov3_results({"results_path": "x"}))            # no video_id -> ignored
+    asyncio.run(h.process_dinov3_results({"video_id": "c", "results_path": str(tmp_path / "missing.json")}))
+    assert "c" not in h.video_embeddings

@@ -180,6 +180,7 @@ class ClipEmbedEngine:
             self.patches = torch.empty((self.max_frames * self.grid[0] * self.grid[1], 3 * cfg.patch * cfg.patch),
                                        dtype=torch.bfloat16, device=self.device)
         self._gallery_scratch: Optional[torch.Tensor] = None
+        self._staging = None
 
     # ------------------------------------------------------------------------------------------
     def close(self) -> None:
@@ -215,11 +216,14 @@ class ClipEmbedEngine:
             "cre_preprocess_patchify")
         return out
 
-    def forward_patches(self, patches: torch.Tensor, n: int, want_tokens: bool = False):
+    def forward_patches(self, patches: torch.Tensor, n: int, want_tokens: bool = False,
+                        out: Optional[torch.Tensor] = None):
         """bf16 patch rows -> f32 frame embeddings [n, D] (final LayerNorm + mean over all tokens)."""
         if n > self.max_frames:
             raise ValueError(f"{n} frames > max_frames={self.max_frames}")
-        emb = torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        emb = out if out is not None else torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        if emb.shape != (n, self.cfg.hidden) or emb.dtype != torch.float32 or not emb.is_contiguous():
+            raise ValueError("out must be a contiguous f32 [n, hidden] tensor")
         tokens = (torch.empty((n, self.tokens, self.cfg.hidden), dtype=torch.float32, device=self.device)
                   if want_tokens else None)
         _lib.check(self.lib.cre_vit_forward(
@@ -227,14 +231,67 @@ class ClipEmbedEngine:
             emb.data_ptr(), _ptr(tokens), self._stream()), "cre_vit_forward")
         return (emb, tokens) if want_tokens else emb
 
-    def embed_frames(self, frames: torch.Tensor, bgr: bool = True) -> torch.Tensor:
-        """uint8 [n, H, W, 3] (device) -> f32 [n, D]; processed in chunks of max_frames."""
-        outs = []
-        for s in range(0, frames.shape[0], self.max_frames):
+    def embed_frames(self, frames: torch.Tensor, bgr: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 [n, H, W, 3] (device) -> f32 [n, D]; processed in chunks of max_frames on the current stream."""
+        n = frames.shape[0]
+        if out is None:
+            out = torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        for s in range(0, n, self.max_frames):
             chunk = frames[s:s + self.max_frames]
             patches = self.preprocess(chunk, bgr=bgr)
-            outs.append(self.forward_patches(patches, chunk.shape[0]))
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+            self.forward_patches(patches, chunk.shape[0], out=out[s:s + chunk.shape[0]])
+        return out
+
+    def embed_host_frames(self, frames, bgr: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """HOST uint8 [n, H, W, 3] (numpy array or CPU tensor) -> DEVICE f32 [n, D].
+
+        Chunks of max_frames are copied host->device on a side stream while the previous chunk is being
+        embedded (two device frame buffers, events both ways).  Pinned CPU tensors are copied in place;
+        pageable input is staged through two pinned buffers first.  Returns after queueing; the caller
+        synchronises by reading the result (``.cpu()``) or on the current stream."""
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(np.ascontiguousarray(frames))
+        if frames.is_cuda:
+            return self.embed_frames(frames, bgr=bgr, out=out)
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [n, H, W, 3]")
+        frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        if out is None:
+            out = torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        cf = min(self.max_frames, n)
+        per = h * w * 3
+        st = self._staging
+        if st is None or st["dev"][0].numel() < cf * per:
+            st = {"dev": [torch.empty(cf * per, dtype=torch.uint8, device=self.device) for _ in range(2)],
+                  "pin": [None, None],
+                  "copied": [torch.cuda.Event() for _ in range(2)], "freed": [torch.cuda.Event() for _ in range(2)],
+                  "stream": torch.cuda.Stream(device=self.device)}
+            self._staging = st
+        pinned = frames.is_pinned()
+        if not pinned and (st["pin"][0] is None or st["pin"][0].numel() < cf * per):
+            st["pin"] = [torch.empty(cf * per, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        compute = torch.cuda.current_stream(self.device)
+        st["stream"].wait_stream(compute)
+        for i, s in enumerate(range(0, n, cf)):
+            b = i & 1
+            m = min(cf, n - s)
+            src = frames[s:s + m].reshape(-1)
+            if not pinned:
+                if i >= 2:
+                    st["copied"][b].synchronize()      # the pinned slot is being re-used: its H2D must be done
+                st["pin"][b][: m * per].copy_(src)
+                src = st["pin"][b][: m * per]
+            dev = st["dev"][b][: m * per]
+            with torch.cuda.stream(st["stream"]):
+                if i >= 2:
+                    st["stream"].wait_event(st["freed"][b])
+                dev.copy_(src, non_blocking=True)
+                st["copied"][b].record(st["stream"])
+            compute.wait_event(st["copied"][b])
+            self.embed_frames(dev.view(m, h, w, 3), bgr=bgr, out=out[s:s + m])
+            st["freed"][b].record(compute)
+        return out
 
     def pool_clips(self, frame_emb: torch.Tensor, clip_offsets: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """f32 [F, D] + int32 offsets [Q + 1] -> (raw clip mean [Q, D], unit-norm [Q, D])  (K3b)."""

@@ -70,7 +70,6 @@ class DINOv3Pipeline:
         self.processed_dir = Path("/app/data/processed")
         self.results_dir = Path(results_dir) if results_dir is not None else Path("/app/data/results/dinov3")
         self.results_dir.mkdir(parents=True, exist_ok=True)
-        self._pinned: Optional[torch.Tensor] = None
         self._ensure_collection()
 
     # -- main.py:70-93 ---------------------------------------------------------------------------
@@ -90,20 +89,22 @@ class DINOv3Pipeline:
         except Exception as e:
             print(f"Error ensuring collection: {e}")
 
-    # -- host staging ------------------------------------------------------------------------------
-    def _to_device(self, frames: np.ndarray) -> torch.Tensor:
-        """uint8 [n, H, W, 3] host -> device through a reusable pinned buffer (async H2D on the current stream)."""
-        n = frames.size
-        if self._pinned is None or self._pinned.numel() < n:
-            self._pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        host = self._pinned[:n].view(frames.shape)
-        host.numpy()[...] = frames
-        return host.to(self.device, non_blocking=True)
-
+    # -- batched entry points (new; the reference embeds one frame per call) ------------------------
     def embed_frames(self, frames: np.ndarray, bgr: bool = True) -> np.ndarray:
-        """uint8 [n, H, W, 3] (cv2 BGR by default) -> float32 [n, D] per-frame embeddings (token mean)."""
-        emb = self.engine.embed_frames(self._to_device(np.ascontiguousarray(frames)), bgr=bgr)
-        return emb.cpu().numpy()
+        """HOST uint8 [n, H, W, 3] (cv2 BGR by default) -> float32 [n, D] per-frame embeddings (token mean).
+        H2D copies are pipelined with the kernels inside the engine."""
+        return self.engine.embed_host_frames(frames, bgr=bgr).cpu().numpy()
+
+    def embed_clips(self, frames, clip_offsets, bgr: bool = True, top_k: int = 0):
+        """Many clips in one call: HOST frames uint8 [F, H, W, 3] (numpy or pinned CPU tensor), clip c = frames
+        [clip_offsets[c], clip_offsets[c+1]).  Returns (clip_mean [Q, D], clip_unit [Q, D]) as numpy, plus
+        (scores [Q, k], ids) against the GPU gallery when top_k > 0 and gallery_backend == 'gpu'."""
+        emb = self.engine.embed_host_frames(frames, bgr=bgr)
+        mean, unit = self.engine.pool_clips(emb, torch.as_tensor(np.asarray(clip_offsets, dtype=np.int32)))
+        if top_k > 0 and self.gallery is not None and len(self.gallery) > 0:
+            scores, idx = self.engine.gallery_topk(unit, self.gallery.matrix[: len(self.gallery)], k=top_k)
+            return mean.cpu().numpy(), unit.cpu().numpy(), scores.cpu().numpy(), idx.cpu().numpy()
+        return mean.cpu().numpy(), unit.cpu().numpy()
 
     # -- main.py:95-115 ---------------------------------------------------------------------------
     def extract_embedding(self, image: np.ndarray) -> np.ndarray:
