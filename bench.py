@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Headline benchmark of the clip-embedding + re-ID hot path (BASELINE.json metric: DINOv3 ViT-B/16 frames/s).
+
+    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (rank 0 only)
+
+One STEP = one pass of the hot path over one batch of synthetic clips: BASELINE.json configs[1] --
+64 clips x 150 frames of 1920x1080 uint8 BGR (9 600 frames) -> fused antialiased resize/normalise/patchify ->
+ViT-B/16 forward (random-init weights, seed 0) -> per-clip mean + L2 -> cosine top-5 against a 100 000-row gallery.
+N > 1 (torchrun, one rank per GPU): every rank embeds its own 64 clips (weak scaling, no data-path collective),
+the gallery is row-sharded, NCCL all-gathers the query embeddings and the per-shard top-5 (sharded.py).
+
+`value`: frames/s over all ranks with the step's frames already resident in HBM (device timing, CUDA events, max over
+ranks).  `e2e`: the same step through the reference-facing API (DINOv3Pipeline.embed_clips) with the frames in PINNED HOST
+memory: host->device copies (pipelined with compute) and the device->host read of the results are inside the timed region.
+`roofline`: the tcgen05 GEMM kernel (dominant: ~75 % of the step) -- algorithmic FLOPs / CUDA-event launch durations taken in
+one extra instrumented step after the timed region (cre_profile_start/stop bracket every launch on its stream).
+`cpu_baseline`: the reference's per-frame path (oracle/pipeline_ref.py = HF processor + HF DINOv3ViTModel fp32, batch 1) on
+this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "DINOv3 ViT-B/16 clip-embedding + re-ID throughput"
+UNIT = "frames/s"
+GFLOP_PER_FRAME_NOTE = "35.864 GFLOP/frame (2MNK per GEMM + 4T^2D attention per layer, T=201)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--clips", type=int, default=64, help="clips per rank per step")
+    ap.add_argument("--frames-per-clip", type=int, default=150)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--gallery-rows", type=int, default=100_000)
+    ap.add_argument("--batch-frames", type=int, default=300, help="frames per ViT launch sequence")
+    ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table of the instrumented step to stderr")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = Path(f"/tmp/cre_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.path.read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            self.path.unlink()
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own per-frame CPU path (oracle/pipeline_ref.py), bounded sample
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(args, seconds: float, frames_cap: int = 10_000):
+    """Times ReferencePipelineCPU.extract_embedding (main.py:95-115 semantics: cvtColor -> PIL -> HF processor -> batch-1 fp32
+    forward -> token mean) on frames of the benchmark's shape for about `seconds`; returns (frames/s, frames, threads)."""
+    import numpy as np
+    import torch
+
+    from oracle import common, pipeline_ref
+
+    pipe = pipeline_ref.ReferencePipelineCPU(common.hf_model())
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, size=(4, args.height, args.width, 3), dtype=np.uint8)
+    pipe.extract_embedding(frames[0])                      # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    n = 0
+    embs = []
+    while n < frames_cap:
+        embs.append(pipe.extract_embedding(frames[n % 4]))
+        n += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, torch.get_num_threads(), np.stack(embs)
+
+
+def run_reference(args, rank: int):
+    """`--impl reference`: every step = a bounded sample of the workload on the host cores (frames + clip mean + numpy top-5)."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    from oracle import common, pipeline_ref, reid_ref
+
+    pipe = pipeline_ref.ReferencePipelineCPU(common.hf_model())
+    rng = np.random.default_rng(0)
+    sample = 8                                             # frames per step: 1 clip sampled at 8 frames
+    frames = rng.integers(0, 256, size=(sample, args.height, args.width, 3), dtype=np.uint8)
+    gal = reid_ref.l2_normalise(np.random.default_rng(7).standard_normal((args.gallery_rows, 768))).astype(np.float32)
+
+    def step():
+        emb = np.stack([pipe.extract_embedding(f) for f in frames])
+        q = reid_ref.l2_normalise(reid_ref.clip_mean(emb, np.array([0, sample])))
+        s = (gal @ q[0].astype(np.float32))[None, :]
+        return reid_ref.topk_rule(s, 5)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    sample_desc = (f"{sample} frames/step of {args.height}x{args.width} uint8 through extract_embedding (HF processor + fp32 batch-1 "
+                   f"forward) + clip mean + numpy top-5 over {args.gallery_rows} rows")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample_desc,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": f"configs[1]: ViT-B/16 embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
+                        f"({args.clips * args.frames_per_clip} frames) decoded as {args.width}x{args.height} uint8 incl. fused "
+                        f"resize/normalize, + cosine top-5 re-ID against a {args.gallery_rows}-row gallery; per rank",
+            "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip, "frame_hw": [args.height, args.width],
+            "gallery_rows": args.gallery_rows, "top_k": 5, "batch_frames": args.batch_frames,
+            "parallelism": f"dp{world} clips + row-sharded gallery",
+            "l2": "inputs (59.7 GB of frames per step) are far larger than L2; no flush needed",
+            "flops": GFLOP_PER_FRAME_NOTE}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle import common                        # seeded random-init weights only (test/bench infrastructure)
+    from vision_sam3_yolo_lameless_b200 import _lib
+    from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig, set_cta_group
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    from vision_sam3_yolo_lameless_b200.sharded import ShardedReID, shard_range
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.cta_group:
+        set_cta_group(args.cta_group)
+
+    model = common.hf_model()
+    cfg = VitConfig.from_hf(model.config)
+    eng = ClipEmbedEngine(cfg, model.state_dict(), device=local_rank, max_frames=args.batch_frames)
+    del model
+    h, w, fpc, clips = args.height, args.width, args.frames_per_clip, args.clips
+    frames_total = clips * fpc
+    per = h * w * 3
+
+    # ---- resident input: as many distinct frames as fit (all 9 600 on a 180 GB part) ---------------------------
+    free, _ = torch.cuda.mem_get_info(dev)
+    fit = int((free - 12 * 2**30) // per)
+    resident = max(fpc, min(frames_total, fit))
+    frames_dev = torch.empty((resident, h, w, 3), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev)
+    for c0 in range(0, resident, 256):
+        gen.manual_seed(1000 + rank * 100_003 + c0)
+        c1 = min(resident, c0 + 256)
+        frames_dev[c0:c1] = torch.randint(0, 256, (c1 - c0, h, w, 3), dtype=torch.uint8, device=dev, generator=gen)
+    offsets = torch.arange(0, frames_total + 1, fpc, dtype=torch.int32, device=dev)
+
+    # ---- gallery shard ---------------------------------------------------------------------------------------------
+    lo, hi = shard_range(args.gallery_rows, rank, world)
+    gen.manual_seed(7 + rank)
+    shard = torch.nn.functional.normalize(torch.randn(hi - lo, cfg.hidden, device=dev, generator=gen), dim=1).to(torch.bfloat16)
+    reid = ShardedReID(eng, shard, row_base=lo)
+    frame_emb = torch.empty((frames_total, cfg.hidden), dtype=torch.float32, device=dev)
+
+    def step_resident():
+        for s in range(0, frames_total, resident):
+            m = min(resident, frames_total - s)
+            eng.embed_frames(frames_dev[:m], bgr=True, out=frame_emb[s:s + m])
+        _, unit = eng.pool_clips(frame_emb, offsets)
+        return reid.search(unit, k=5)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 0)):
+        step_resident()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        scores, idx = step_resident()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    value = world * frames_total * args.steps / (ms_max / 1e3)
+
+    # ---- instrumented step: per-kernel CUDA-event durations (roofline) ----------------------------------------------
+    kernels = {}
+    roofline = None
+    if rank == 0:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)     # a kernel timed inside a long step -> sustained figure
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        which = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
+        _lib.profile_start(1 << 17)
+        step_resident()
+        recs = _lib.profile_stop(1 << 17)
+        tot = sum(r[1] for r in recs) or 1.0
+        for name, ms_k, work in recs:
+            k = kernels.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            k["launches"] += 1; k["ms"] += ms_k; k["work"] += work
+        for name, k in kernels.items():
+            k["share"] = k["ms"] / tot
+            k["avg_us"] = k["ms"] / k["launches"] * 1e3
+            if k["work"] > 0 and k["ms"] > 0:
+                if name in _lib.FLOP_KERNELS:
+                    k["tflops"] = k["work"] / (k["ms"] * 1e-3) / 1e12
+                    k["frac"] = k["tflops"] / tf_peak
+                else:
+                    k["gbs"] = k["work"] / (k["ms"] * 1e-3) / 1e9
+                    k["frac"] = k["gbs"] / hbm_peak
+        gemm = [k for n, k in kernels.items() if n.startswith("gemm_") and n != "gemm_topk"]
+        g_ms, g_work, g_l = sum(k["ms"] for k in gemm), sum(k["work"] for k in gemm), sum(k["launches"] for k in gemm)
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic.json"
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get("gemm_tn_kernel_dram_bytes_per_launch")
+        roofline = {"kernel": "gemm_tn_kernel (tcgen05, all ViT epilogues)", "bound": "tensor",
+                    "achieved": g_work / (g_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": g_work / (g_ms * 1e-3) / 1e12 / tf_peak, "traffic": traffic, "peak_source": which,
+                    "launches": g_l, "avg_launch_us": g_ms / g_l * 1e3, "flops_per_launch": g_work / g_l,
+                    "share_of_step": g_ms / tot,
+                    "how": "CUDA events around every launch (cre_profile_start/stop) in one instrumented step after the timed region"}
+        if args.breakdown:
+            for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]):
+                perf = f"{k.get('tflops', 0):8.1f} TF/s" if "tflops" in k else f"{k.get('gbs', 0):8.1f} GB/s"
+                print(f"  {name:16s} n={k['launches']:5d} total={k['ms']:9.3f} ms share={k['share'] * 100:5.1f}% avg={k['avg_us']:8.1f} us "
+                      f"{perf} frac={k.get('frac', 0):.3f}", file=sys.stderr)
+
+    # ---- e2e: reference-facing API, frames in pinned host memory --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pipe = DINOv3Pipeline(eng, results_dir=Path("/tmp/cre_bench_results"), gallery_backend="gpu")
+        pipe.gallery.load(list(range(lo, hi)), shard)
+        distinct = min(clips, 4)
+        host = torch.empty((distinct, fpc, h, w, 3), dtype=torch.uint8, pin_memory=True)
+        host.copy_(frames_dev[: distinct * fpc].view(distinct, fpc, h, w, 3) if resident >= distinct * fpc
+                   else frames_dev[:fpc].expand(distinct, -1, -1, -1, -1))
+        torch.cuda.synchronize(dev)
+        clip_list = [host[c % distinct] for c in range(clips)]
+        offs_host = np.arange(0, frames_total + 1, fpc, dtype=np.int32)
+
+        def step_e2e():
+            mean, unit, sc, ix = pipe.embed_clips(clip_list, offs_host, bgr=True, top_k=5)   # returns numpy (D2H inside)
+            return mean, sc, ix
+
+        e2e_steps = max(1, min(args.steps, 3))
+        step_e2e()
+        sync_all()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        wall0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            mean, sc, ix = step_e2e()
+        t1.record()
+        sync_all()
+        wall = time.perf_counter() - wall0
+        ems = max(t0.elapsed_time(t1), wall * 1e3)       # results are on the host when the call returns: wall clock counts
+        te = torch.tensor([ems], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        d2h = int(mean.nbytes * 2 + sc.nbytes + ix.nbytes)
+        e2e = {"value": world * frames_total * e2e_steps / (te.item() / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(frames_total * per), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "api": "DINOv3Pipeline.embed_clips(list of pinned host clips) -> numpy clip embeddings + top-5",
+               "note": f"{distinct} distinct pinned clips cycled to form the {clips}-clip batch (all bytes are copied every step); "
+                       "re-ID in e2e is against the rank-local gallery shard"}
+        del host
+
+    # ---- cpu baseline (rank 0, N=1 only) ----------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, n, threads, _ = cpu_reference_sample(args, args.cpu_seconds)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{n} frames of {h}x{w} uint8 through the reference's per-frame path (cvtColor, PIL, HF DINOv3ViTImageProcessor, "
+                         "HF DINOv3ViTModel fp32 batch 1, token mean; oracle/pipeline_ref.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+            "clips_per_s": value / fpc,
+            "vit_tflops": value * cfg.flops_per_frame(14, 14) / 1e12,
+            "vit_frac_of_bf16_burst_peak": value / world * cfg.flops_per_frame(14, 14) / 1e12 / 1623.1,
+            "resident_frames": resident,
+            "roofline": roofline, "kernels": {n: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in k.items()}
+                                              for n, k in kernels.items()},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,7 +113,7 @@ int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_d
  * fp32-query x bf16-gallery dot products accumulated in fp32 (queries are split hi+lo bf16 internally).
  * Writes the k best (score desc, index asc) per query: out_scores_dev f32 [q, k], out_idx_dev i32 [q, k]
  * with idx = row_base + local row; missing entries (rows < k) are (-inf, INT32_MAX).
- * scratch_dev: cre_gallery_scratch_bytes(q, dim, k) bytes.  dump_scores_dev (optional, may be NULL):
+ * scratch_dev: cre_gallery_scratch_bytes(q, dim, k) bytes, 256-byte aligned.  dump_scores_dev (optional, may be NULL):
  * f32 [q, rows] full score matrix for parity tests. */
 int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k);
 int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int32_t dim,
@@ -136,7 +136,8 @@ enum cre_gemm_epilogue {
     CRE_EPI_BF16 = 0,  /* out_bf16 = acc + bias                         */
     CRE_EPI_F32 = 1,   /* out_f32  = acc + bias                         */
     CRE_EPI_GELU = 3,  /* out_bf16 = gelu_erf(acc + bias)               */
-    CRE_EPI_RESID = 4  /* out_f32 += scale * (acc + bias)   (in place)  */
+    CRE_EPI_RESID = 4, /* out_f32 += scale * (acc + bias)   (in place)  */
+    CRE_EPI_NONE = 7   /* accumulators dropped: main-loop timing only   */
 };
 /* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0, n % 32 == 0.
  * cta_group = 1 or 2 (CTA pair, cta_group::2). bias/scale may be NULL where unused. */
@@ -152,9 +153,28 @@ int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const flo
 int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k_col0, const void* vt_dev,
                       int32_t t_pad, int32_t n, int32_t t, int32_t heads, void* out_dev, void* stream);
 
+/* ---- launch accounting -------------------------------------------------------------------------------
+ * cre_kernel_launches: kernels launched by this library in this process so far (bench.py's gpu_launches).
+ * cre_profile_start(max): from now on bracket every launch with a CUDA-event pair on its stream (at most `max`
+ * launches are recorded).  cre_profile_stop: stop recording, wait for the recorded launches and return their
+ * count; ids_out[i] is a cre_kernel_id, ms_out[i] the device time of that launch, work_out[i] its algorithmic
+ * work (FLOPs for GEMM / attention kernels, bytes for memory-bound kernels).  Synchronises; not a hot call. */
+enum cre_kernel_id {
+    CRE_K_PREPROCESS = 0, CRE_K_FILL_PREFIX = 1, CRE_K_GEMM_PATCH = 2, CRE_K_LAYERNORM = 3, CRE_K_GEMM_QKV = 4,
+    CRE_K_ATTENTION = 5, CRE_K_GEMM_RESID = 6, CRE_K_GEMM_GELU = 7, CRE_K_FINAL_NORM_MEAN = 8, CRE_K_POOL_CLIPS = 9,
+    CRE_K_SPLIT_HI_LO = 10, CRE_K_FILL_TOPK = 11, CRE_K_GEMM_TOPK = 12, CRE_K_MERGE_TOPK = 13, CRE_K_GEMM_PLAIN = 14,
+    CRE_K_GALLERY_UPDATE = 15, CRE_KERNEL_IDS = 16
+};
+int64_t cre_kernel_launches(void);
+int32_t cre_profile_start(int32_t max_launches);
+int32_t cre_profile_stop(int32_t* ids_out, float* ms_out, double* work_out, int32_t cap);
+
 /* Process-wide tuning knob: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs on
  * 256x256 tiles (cta_group::2) for the ViT GEMMs.  Results are identical either way. */
 int32_t cre_set_cta_group(int32_t cta_group);
+/* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..7:
+ * TMA pipeline depth of the cre_gemm_bf16 building block).  Unknown keys return -1. */
+int32_t cre_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus
 }

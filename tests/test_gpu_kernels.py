@@ -46,7 +46,7 @@ def test_gemm_rejects_bad_shapes(engine_small):
     with pytest.raises(_lib.CreError, match="multiple of 64"):
         eng.gemm(a, b)
     with pytest.raises(_lib.CreError):
-        eng.gemm(a[:, :64].contiguous(), b[:, :64].contiguous(), epilogue=7)
+        eng.gemm(a[:, :64].contiguous(), b[:, :64].contiguous(), epilogue=9)
 
 
 @pytest.mark.parametrize("rows,dim", [(1003, 768), (77, 1024), (1, 768)])
@@ -195,6 +195,6 @@ def test_gallery_update_row(engine_small):
     new = np.random.default_rng(0).standard_normal(768)
     uq = torch.from_numpy(reid_ref.l2_normalise(new).astype(np.float32)).to(dev)
     eng.gallery_update_row(gal, 2, uq, 0.9)
-    np.testing.assert_allclose(gal[2].float().cpu().numpy(), reid_ref.momentum_update(old, new, 0.9), atol=4e-4)   # bf16 store
+    np.testing.assert_allclose(gal[2].float().cpu().numpy(), reid_ref.momentum_update(old, new, 0.9), atol=1e-3)   # bf16 store: half-ulp 4.9e-4 at |x| in [0.125, 0.25)
     eng.gallery_update_row(gal, 4, uq, 0.0)
-    np.testing.assert_allclose(gal[4].float().cpu().numpy(), reid_ref.l2_normalise(new), atol=4e-4)
+    np.testing.assert_allclose(gal[4].float().cpu().numpy(), reid_ref.l2_normalise(new), atol=1e-3)

@@ -22,8 +22,15 @@ LN2_G, LN2_B, W_UP, B_UP, W_DOWN, B_DOWN, LS2 = 12, 13, 14, 15, 16, 17, 18
 WEIGHT_KINDS = 19
 BF16_KINDS = {W_PATCH, W_QKV, W_O, W_UP, W_DOWN}
 
+# enum cre_kernel_id
+KERNEL_NAMES = ["preprocess", "fill_prefix", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu",
+                "final_norm_mean", "pool_clips", "split_hi_lo", "fill_topk", "gemm_topk", "merge_topk", "gemm_plain",
+                "gallery_update"]
+# kernels whose `work` is FLOPs (tensor-bound); the others report bytes (HBM-bound)
+FLOP_KERNELS = {"gemm_patch", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu", "gemm_plain"}
+
 # enum cre_gemm_epilogue
-EPI_BF16, EPI_F32, EPI_GELU, EPI_RESID = 0, 1, 3, 4
+EPI_BF16, EPI_F32, EPI_GELU, EPI_RESID, EPI_NONE = 0, 1, 3, 4, 7
 
 
 class CreError(RuntimeError):
@@ -68,6 +75,10 @@ PROTOTYPES = {
     "cre_layernorm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cre_set_cta_group": (_i32, [_i32]),
+    "cre_set_tuning": (_i32, [C.c_char_p, _i32]),
+    "cre_kernel_launches": (_i64, []),
+    "cre_profile_start": (_i32, [_i32]),
+    "cre_profile_stop": (_i32, [_vp, _vp, _vp, _i32]),
 }
 
 _lib = None
@@ -107,3 +118,27 @@ def check_size(value: int, what: str) -> int:
     if value < 0:
         raise CreError(f"{what} failed: {last_error()}")
     return int(value)
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libcre_b200 in this process so far."""
+    return int(load().cre_kernel_launches())
+
+
+def profile_start(max_launches: int = 1 << 16) -> None:
+    check(load().cre_profile_start(int(max_launches)), "cre_profile_start")
+
+
+def profile_stop(cap: int = 1 << 16):
+    """-> list of (kernel name, milliseconds, work) for every launch since profile_start (synchronises)."""
+    ids = (C.c_int32 * cap)()
+    ms = (C.c_float * cap)()
+    work = (C.c_double * cap)()
+    n = load().cre_profile_stop(ids, ms, work, cap)
+    if n < 0:
+        raise CreError(f"cre_profile_stop failed: {last_error()}")
+    return [(KERNEL_NAMES[ids[i]], float(ms[i]), float(work[i])) for i in range(n)]
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(load().cre_set_tuning(key.encode(), int(value)), f"cre_set_tuning({key})")

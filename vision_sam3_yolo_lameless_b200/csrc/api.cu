@@ -497,7 +497,7 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
                     out_idx_dev != nullptr, "gallery_topk: NULL argument");
     CRE_REQUIRE(q > 0 && dim > 0 && dim % 64 == 0 && rows >= 0, "gallery_topk: q=%d dim=%d rows=%d", q, dim, rows);
     CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX, "gallery_topk: k=%d out of range (1..%d)", k, CRE_TOPK_MAX);
-    CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 1023) == 0, "gallery_topk: scratch must be 1024-byte aligned");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 255) == 0, "gallery_topk: scratch must be 256-byte aligned");
     const int64_t need = cre_gallery_scratch_bytes(q, dim, k);
     CRE_REQUIRE(scratch_bytes >= need, "gallery_topk: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)need);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -551,8 +551,8 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
                       int32_t epilogue, const float* bias_dev, const float* scale_dev, void* out_dev, int32_t cta_group,
                       void* stream) {
     CRE_REQUIRE(ctx != nullptr && a_dev != nullptr && b_dev != nullptr && out_dev != nullptr, "gemm: NULL argument");
-    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_F32 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID,
-                "gemm: epilogue %d is not exposed", epilogue);
+    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_F32 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID ||
+                    epilogue == CRE_EPI_NONE, "gemm: epilogue %d is not exposed", epilogue);
     CRE_REQUIRE(epilogue != CRE_EPI_RESID || scale_dev != nullptr, "gemm: RESID epilogue needs scale");
     GemmParams p = base_params(m, n, k);
     p.bias = bias_dev;
@@ -584,6 +584,30 @@ int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k
     a.heads = heads;
     a.out = out_dev;
     return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+int64_t cre_kernel_launches(void) { return launch_count(); }
+int32_t cre_profile_start(int32_t max_launches) { return profile_start(max_launches); }
+int32_t cre_profile_stop(int32_t* ids_out, float* ms_out, double* work_out, int32_t cap) {
+    CRE_REQUIRE(ids_out != nullptr && ms_out != nullptr && work_out != nullptr && cap >= 0, "profile_stop: NULL argument");
+    return profile_stop(ids_out, ms_out, work_out, cap);
+}
+
+// generic process-wide tuning knobs (benchmark / tuning harness; defaults are what the parity tests cover)
+int32_t cre_set_tuning(const char* key, int32_t value) {
+    CRE_REQUIRE(key != nullptr, "set_tuning: NULL key");
+    if (strcmp(key, "cta_group") == 0) return cre_set_cta_group(value);
+    if (strcmp(key, "gemm_stages") == 0) {
+        CRE_REQUIRE(value == 0 || (value >= 3 && value <= 7), "set_tuning: gemm_stages=%d", value);
+        set_gemm_stages(value);
+        return 0;
+    }
+    if (strcmp(key, "gemm_debug") == 0) {
+        set_gemm_debug(value);
+        return 0;
+    }
+    set_error("set_tuning: unknown key '%s'", key);
+    return -1;
 }
 
 // 1 = one CTA per tile (cta_group::1), 2 = CTA pairs (cta_group::2) for the ViT GEMMs

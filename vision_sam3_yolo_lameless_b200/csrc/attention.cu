@@ -233,6 +233,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     p.ld_out = a.heads * 64;
     p.k_col0 = a.k_col0;
     dim3 grid((a.t + 127) / 128, a.heads, a.n);
+    LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
     attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tk, tv, p);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -87,12 +87,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same smem offset inside CTA `cta` of this cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+// arrive on the barrier at the same smem offset inside CTA `cta` of this cluster.  Default semantics
+// (.release at .cta scope) on purpose: a cluster-scope release is a cluster-wide fence that costs ~700
+// cycles per arrive and, issued once per pipeline stage, halved the throughput of the CTA-pair GEMM.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
         "r"(cta)
         : "memory");
 }

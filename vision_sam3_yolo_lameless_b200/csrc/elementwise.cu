@@ -56,6 +56,7 @@ int launch_layernorm_bf16(const float* x, const float* g, const float* b, int ro
                           __nv_bfloat16* out, cudaStream_t stream) {
     CRE_REQUIRE(rows > 0, "layernorm: no rows");
     const int grid = (rows + 7) / 8;
+    LaunchScope scope(CRE_K_LAYERNORM, 6.0 * rows * dim, stream);
     if (dim == 768) layernorm_bf16_kernel<768><<<grid, 256, 0, stream>>>(x, g, b, rows, eps, out);
     else if (dim == 1024) layernorm_bf16_kernel<1024><<<grid, 256, 0, stream>>>(x, g, b, rows, eps, out);
     else {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __res
 int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
                            float* frame_emb, float* tokens_out, cudaStream_t stream) {
     CRE_REQUIRE(frames > 0 && t > 0, "final_norm_mean: empty input");
+    LaunchScope scope(CRE_K_FINAL_NORM_MEAN, 4.0 * frames * t * dim * (tokens_out != nullptr ? 2.0 : 1.0), stream);
     if (dim == 768) final_norm_mean_kernel<768><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
     else if (dim == 1024) final_norm_mean_kernel<1024><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
     else {
@@ -158,6 +160,7 @@ __global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restric
 int launch_fill_prefix(float* x, const float* prefix, int frames, int t, int prefix_tokens, int dim,
                        cudaStream_t stream) {
     const int64_t total4 = static_cast<int64_t>(frames) * prefix_tokens * (dim / 4);
+    LaunchScope scope(CRE_K_FILL_PREFIX, 16.0 * total4, stream);
     fill_prefix_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(x, prefix, t, prefix_tokens,
                                                                                          dim / 4, total4);
     CRE_CUDA_OK(cudaGetLastError());
@@ -209,6 +212,7 @@ int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, in
                       float* out_unit, cudaStream_t stream) {
     CRE_REQUIRE(clips > 0, "pool_clips: no clips");
     CRE_REQUIRE(dim > 0 && dim <= 1024, "pool_clips: dim %d out of range (<= 1024)", dim);
+    LaunchScope scope(CRE_K_POOL_CLIPS, 0.0, stream);
     pool_clips_kernel<<<clips, 256, 0, stream>>>(frame_emb, offs, dim, out_mean, out_unit);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -230,6 +234,7 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ q, int dim, int64_t
 
 int launch_split_hi_lo(const float* q, int rows, int dim, __nv_bfloat16* out, cudaStream_t stream) {
     const int64_t total = static_cast<int64_t>(rows) * dim;
+    LaunchScope scope(CRE_K_SPLIT_HI_LO, 8.0 * total, stream);
     split_hi_lo_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(q, dim, total, out);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -244,6 +249,7 @@ __global__ void fill_topk_kernel(float* __restrict__ s, int32_t* __restrict__ id
 }
 
 int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t stream) {
+    LaunchScope scope(CRE_K_FILL_TOPK, 8.0 * count, stream);
     fill_topk_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, stream>>>(scores, idx, count);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -314,6 +320,7 @@ int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stri
     CRE_REQUIRE(q > 0 && lists > 0, "merge_topk: empty input");
     CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX && per_list >= 1 && per_list <= CRE_TOPK_MAX, "merge_topk: k=%d per_list=%d out of range (1..%d)", k,
                 per_list, CRE_TOPK_MAX);
+    LaunchScope scope(CRE_K_MERGE_TOPK, 8.0 * lists * per_list * q, stream);
     merge_topk_kernel<<<(q + 3) / 4, 128, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, q, k,
                                                        out_scores, out_idx);
     CRE_CUDA_OK(cudaGetLastError());
@@ -352,6 +359,7 @@ __global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* 
 int launch_gallery_update_row(__nv_bfloat16* gallery, int dim, int row, const float* unit_q, float momentum,
                               cudaStream_t stream) {
     CRE_REQUIRE(dim > 0 && dim <= 1024 && row >= 0, "gallery_update_row: bad dim/row");
+    LaunchScope scope(CRE_K_GALLERY_UPDATE, 8.0 * dim, stream);
     gallery_update_row_kernel<<<1, 256, 0, stream>>>(gallery + static_cast<size_t>(row) * dim, dim, unit_q, momentum);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;

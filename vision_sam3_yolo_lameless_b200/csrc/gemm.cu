@@ -54,11 +54,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
     return 0;
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, int STAGES = default_stages(CG)>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                       cudaStream_t stream) {
-    using Cfg = GemmCfg<CG>;
-    auto* kern = gemm_tn_kernel<EPI, CG>;
+    using Cfg = GemmCfg<CG, STAGES>;
+    static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline does not fit in shared memory");
+    auto* kern = gemm_tn_kernel<EPI, CG, STAGES>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         CRE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -82,6 +83,11 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    constexpr int kid = EPI == EPI_PATCH ? CRE_K_GEMM_PATCH : EPI == EPI_QKV ? CRE_K_GEMM_QKV : EPI == EPI_RESID ? CRE_K_GEMM_RESID
+                      : EPI == EPI_GELU ? CRE_K_GEMM_GELU : EPI == EPI_TOPK ? CRE_K_GEMM_TOPK : CRE_K_GEMM_PLAIN;
+    // work: FLOPs, except the gallery scan which is bound by reading the bf16 gallery once (bytes)
+    const double work = EPI == EPI_TOPK ? 2.0 * p.N * p.b_k_extent : 2.0 * p.M * static_cast<double>(p.N) * p.K;
+    LaunchScope scope(kid, work, stream);
     CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     return 0;
 }
@@ -94,6 +100,29 @@ int gemm_workers(int m, int n, int cg, int num_sms) {
     return workers < 1 ? 1 : workers;
 }
 
+static int g_debug_mode = 0;
+void set_gemm_debug(int mode) { g_debug_mode = mode; }
+static int g_tune_stages = 0;  // 0 = default_stages(cg); otherwise a tuning override for the plain epilogues
+void set_gemm_stages(int stages) { g_tune_stages = stages; }
+
+// non-default pipeline depths exist only for the epilogues cre_gemm_bf16 exposes (tuning harness)
+template <int EPI>
+static int launch_tuned(int cg, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                        cudaStream_t stream) {
+    if (cg == 1) {
+        if (stages == 3) return launch_one<EPI, 1, 3>(ta, tb, p, num_sms, stream);
+        if (stages == 4) return launch_one<EPI, 1, 4>(ta, tb, p, num_sms, stream);
+    } else {
+        if (stages == 3) return launch_one<EPI, 2, 3>(ta, tb, p, num_sms, stream);
+        if (stages == 4) return launch_one<EPI, 2, 4>(ta, tb, p, num_sms, stream);
+        if (stages == 5) return launch_one<EPI, 2, 5>(ta, tb, p, num_sms, stream);
+        if (stages == 6) return launch_one<EPI, 2, 6>(ta, tb, p, num_sms, stream);
+        if (stages == 7) return launch_one<EPI, 2, 7>(ta, tb, p, num_sms, stream);
+    }
+    set_error("gemm: no instantiation for cta_group=%d stages=%d", cg, stages);
+    return -3;
+}
+
 int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int64_t ldb, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
     CRE_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
@@ -101,11 +130,29 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     CRE_REQUIRE(p.b_k_extent % kBlockK == 0 && p.b_k_extent > 0, "gemm: bad b_k_extent %d", p.b_k_extent);
     CRE_REQUIRE(epi == EPI_TOPK || p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
     CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
+    if (g_debug_mode != 0 && epi == EPI_NONE) {
+        GemmParams q = p;
+        q.debug_mode = g_debug_mode;
+        const int saved = g_debug_mode;
+        g_debug_mode = 0;
+        const int r = launch_gemm(epi, cg, a, lda, b, ldb, q, num_sms, stream);
+        g_debug_mode = saved;
+        return r;
+    }
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16(&ta, a, p.M, p.K, lda, kBlockM);
     if (rc) return rc;
     rc = make_tmap_bf16(&tb, b, p.N, p.b_k_extent, ldb, kBlockN / cg);
     if (rc) return rc;
+    if (g_tune_stages != 0 && g_tune_stages != default_stages(cg)) {
+        switch (epi) {
+            case EPI_BF16: return launch_tuned<EPI_BF16>(cg, g_tune_stages, ta, tb, p, num_sms, stream);
+            case EPI_GELU: return launch_tuned<EPI_GELU>(cg, g_tune_stages, ta, tb, p, num_sms, stream);
+            case EPI_RESID: return launch_tuned<EPI_RESID>(cg, g_tune_stages, ta, tb, p, num_sms, stream);
+            case EPI_NONE: return launch_tuned<EPI_NONE>(cg, g_tune_stages, ta, tb, p, num_sms, stream);
+            default: break;
+        }
+    }
 #define CRE_CASE(E)                                                        \
     case E:                                                                \
         return cg == 1 ? launch_one<E, 1>(ta, tb, p, num_sms, stream)      \
@@ -117,6 +164,7 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         CRE_CASE(EPI_GELU)
         CRE_CASE(EPI_RESID)
         CRE_CASE(EPI_PATCH)
+        CRE_CASE(EPI_NONE)
         case EPI_TOPK:
             return launch_one<EPI_TOPK, 1>(ta, tb, p, num_sms, stream);
         default:

@@ -26,6 +26,7 @@ enum GemmEpi : int {
     EPI_RESID = 4,  // out_f32[m, n] += scale[n] * (acc + bias[n])            (residual stream, in place)
     EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]               (patch rows -> token rows)
     EPI_TOPK = 6,   // running per-row top-k over the columns this CTA visits  (gallery scan)
+    EPI_NONE = 7,   // accumulators are dropped (main-loop tuning only)
 };
 
 constexpr int kTopKMax = 8;
@@ -54,6 +55,7 @@ struct GemmParams {
     int* part_idx;       // [M, slots, k]
     int part_slots;      // 2 * gridDim.x
     float* dump_scores;  // optional [M, N] full score matrix (parity tests)
+    int debug_mode;      // tuning only: 1 = no TMA (MMA issue rate), 2 = no MMA (TMA rate); results are garbage
 };
 
 constexpr int kBlockM = 128;
@@ -63,9 +65,11 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 
-template <int CG>
+constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
+
+template <int CG, int STAGES>
 struct GemmCfg {
-    static constexpr int kStages = (CG == 1) ? 4 : 6;
+    static constexpr int kStages = STAGES;
     static constexpr int kSmemA = kBlockM * kBlockK * 2;          // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kBarOff = kStages * (kSmemA + kSmemB);
@@ -76,11 +80,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-    using Cfg = GemmCfg<CG>;
+    using Cfg = GemmCfg<CG, STAGES>;
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -148,7 +152,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // =============================== TMA producer ===============================
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = t_begin; t < t_end; t += t_step) {
+        for (int t = t_begin; t < t_end && p.debug_mode != 1; t += t_step) {
             const int mt = t / num_nt, nt = t % num_nt;
             const int row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM;
             const int col0 = nt * kBlockN + static_cast<int>(cta_rank) * (kBlockN / CG);
@@ -158,8 +162,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if constexpr (CG == 1) {
                     mbar_arrive_expect_tx(fb, Cfg::kSmemA + Cfg::kSmemB);
                 } else {
+                    // the leader's barrier tracks both halves of the stage: 2 arrivals + the bytes of both CTAs
                     if (is_leader) mbar_arrive_expect_tx(fb, 2 * (Cfg::kSmemA + Cfg::kSmemB));
-                    else mbar_arrive_cluster(fb, 0);
+                    else mbar_arrive_remote(fb, 0);
                 }
                 const int ka = kb * kBlockK;
                 const int kbb = ka % p.b_k_extent;
@@ -181,14 +186,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * kBlockN;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar(stage), phase);
+                if (p.debug_mode != 1) mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint64_t da = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA);
                 const uint64_t db = umma_desc_k_sw128(smem_b + stage * Cfg::kSmemB);
+                if (p.debug_mode != 2) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
-                    umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
+                        umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
                 }
                 umma_commit<CG>(empty_bar(stage));
                 if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(as));
@@ -240,7 +247,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
 
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (EPI == EPI_NONE) {
+                (void)taddr; (void)ncol0; (void)row_ok;
+            } else if constexpr (EPI == EPI_QKV) {
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -392,7 +401,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) {
                 if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(as));
-                else mbar_arrive_cluster(tmem_empty_bar(as), 0);
+                else mbar_arrive_remote(tmem_empty_bar(as), 0);
             }
         }
         if constexpr (EPI == EPI_TOPK) {

@@ -13,6 +13,25 @@ namespace cre {
 void set_error(const char* fmt, ...);
 const char* last_error();
 int gemm_workers(int m, int n, int cg, int num_sms);
+void set_gemm_stages(int stages);
+void set_gemm_debug(int mode);
+
+// Kernel ids reported by cre_profile_stop (include/cre.h enum cre_kernel_id)
+// RAII bracket around one kernel launch: bumps the launch counter and, when the profiler is on, records an
+// event pair on `stream`.  `work` = algorithmic FLOPs (GEMM / attention) or bytes (memory-bound kernels).
+class LaunchScope {
+public:
+    LaunchScope(int id, double work, cudaStream_t stream);
+    ~LaunchScope();
+    LaunchScope(const LaunchScope&) = delete;
+    LaunchScope& operator=(const LaunchScope&) = delete;
+private:
+    cudaStream_t stream_;
+    int slot_;
+};
+int64_t launch_count();
+int profile_start(int max_launches);
+int profile_stop(int32_t* ids, float* ms, double* work, int cap);
 
 // 2-D bf16 row-major tensor [rows, cols] (row stride ld elements) -> TMA descriptor with a
 // [box_rows x 64] box and 128-byte swizzle.  Returns 0 / negative error code.

@@ -146,6 +146,7 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
         smem_set = smem;
     }
     dim3 grid((a.gw + kBandPatches - 1) / kBandPatches, a.gh, a.n);
+    LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
     preprocess_kernel<<<grid, kPreThreads, smem, stream>>>(p);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -243,24 +243,29 @@ class ClipEmbedEngine:
         return out
 
     def embed_host_frames(self, frames, bgr: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """HOST uint8 [n, H, W, 3] (numpy array or CPU tensor) -> DEVICE f32 [n, D].
+        """HOST uint8 frames -> DEVICE f32 [n, D].  ``frames``: one [n, H, W, 3] numpy array / CPU tensor, or a list of
+        them (e.g. one per clip; all the same H x W), embedded as if concatenated.
 
-        Chunks of max_frames are copied host->device on a side stream while the previous chunk is being
+        Batches of max_frames are copied host->device on a side stream while the previous batch is being
         embedded (two device frame buffers, events both ways).  Pinned CPU tensors are copied in place;
         pageable input is staged through two pinned buffers first.  Returns after queueing; the caller
         synchronises by reading the result (``.cpu()``) or on the current stream."""
-        if isinstance(frames, np.ndarray):
-            frames = torch.from_numpy(np.ascontiguousarray(frames))
-        if frames.is_cuda:
-            return self.embed_frames(frames, bgr=bgr, out=out)
-        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
-            raise ValueError("frames must be uint8 [n, H, W, 3]")
-        frames = frames.contiguous()
-        n, h, w, _ = frames.shape
+        srcs = list(frames) if isinstance(frames, (list, tuple)) else [frames]
+        srcs = [torch.from_numpy(np.ascontiguousarray(f)) if isinstance(f, np.ndarray) else f for f in srcs]
+        if len(srcs) == 1 and srcs[0].is_cuda:
+            return self.embed_frames(srcs[0], bgr=bgr, out=out)
+        for f in srcs:
+            if f.is_cuda or f.dtype != torch.uint8 or f.dim() != 4 or f.shape[-1] != 3 or f.shape[1:] != srcs[0].shape[1:]:
+                raise ValueError("frames must be host uint8 [n, H, W, 3] arrays of one common H x W")
+        srcs = [f.contiguous() for f in srcs if f.shape[0] > 0]
+        n = sum(f.shape[0] for f in srcs)
         if out is None:
             out = torch.empty((n, self.cfg.hidden), dtype=torch.float32, device=self.device)
-        cf = min(self.max_frames, n)
+        if n == 0:
+            return out
+        h, w = int(srcs[0].shape[1]), int(srcs[0].shape[2])
         per = h * w * 3
+        cf = min(self.max_frames, n)
         st = self._staging
         if st is None or st["dev"][0].numel() < cf * per:
             st = {"dev": [torch.empty(cf * per, dtype=torch.uint8, device=self.device) for _ in range(2)],
@@ -268,28 +273,37 @@ class ClipEmbedEngine:
                   "copied": [torch.cuda.Event() for _ in range(2)], "freed": [torch.cuda.Event() for _ in range(2)],
                   "stream": torch.cuda.Stream(device=self.device)}
             self._staging = st
-        pinned = frames.is_pinned()
-        if not pinned and (st["pin"][0] is None or st["pin"][0].numel() < cf * per):
+        all_pinned = all(f.is_pinned() for f in srcs)
+        if not all_pinned and (st["pin"][0] is None or st["pin"][0].numel() < cf * per):
             st["pin"] = [torch.empty(cf * per, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        starts = np.cumsum([0] + [f.shape[0] for f in srcs])
         compute = torch.cuda.current_stream(self.device)
         st["stream"].wait_stream(compute)
         for i, s in enumerate(range(0, n, cf)):
             b = i & 1
             m = min(cf, n - s)
-            src = frames[s:s + m].reshape(-1)
-            if not pinned:
-                if i >= 2:
-                    st["copied"][b].synchronize()      # the pinned slot is being re-used: its H2D must be done
-                st["pin"][b][: m * per].copy_(src)
-                src = st["pin"][b][: m * per]
-            dev = st["dev"][b][: m * per]
+            dev = st["dev"][b]
+            if not all_pinned and i >= 2:
+                st["copied"][b].synchronize()          # this pinned slot's previous H2D must have finished
             with torch.cuda.stream(st["stream"]):
                 if i >= 2:
                     st["stream"].wait_event(st["freed"][b])
-                dev.copy_(src, non_blocking=True)
+                k = int(np.searchsorted(starts, s, side="right")) - 1
+                pos = s
+                while pos < s + m:                     # one copy per source segment overlapping this batch
+                    lo = pos - int(starts[k])
+                    cnt = min(srcs[k].shape[0] - lo, s + m - pos)
+                    src = srcs[k][lo:lo + cnt].reshape(-1)
+                    if not all_pinned:
+                        stage = st["pin"][b][(pos - s) * per:(pos - s + cnt) * per]
+                        stage.copy_(src)
+                        src = stage
+                    dev[(pos - s) * per:(pos - s + cnt) * per].copy_(src, non_blocking=True)
+                    pos += cnt
+                    k += 1
                 st["copied"][b].record(st["stream"])
             compute.wait_event(st["copied"][b])
-            self.embed_frames(dev.view(m, h, w, 3), bgr=bgr, out=out[s:s + m])
+            self.embed_frames(dev[: m * per].view(m, h, w, 3), bgr=bgr, out=out[s:s + m])
             st["freed"][b].record(compute)
         return out
 
