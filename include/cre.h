@@ -139,7 +139,8 @@ enum cre_gemm_epilogue {
     CRE_EPI_RESID = 4, /* out_f32 += scale * (acc + bias)   (in place)  */
     CRE_EPI_NONE = 7   /* accumulators dropped: main-loop timing only   */
 };
-/* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0, n % 32 == 0.
+/* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0; n % 64 == 0 for the bf16-out
+ * epilogues, n % 32 == 0 for the fp32-out ones; out_dev 16-byte aligned (written by TMA).
  * cta_group = 1 or 2 (CTA pair, cta_group::2). bias/scale may be NULL where unused. */
 int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k,
                       int32_t epilogue, const float* bias_dev, const float* scale_dev, void* out_dev,
@@ -147,11 +148,11 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
 /* out bf16 [rows, dim] = LayerNorm(x f32 [rows, dim]) * gamma + beta */
 int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const float* beta_dev, int32_t rows,
                            int32_t dim, float eps, void* out_dev, void* stream);
-/* Non-causal attention over frames: q/k bf16 rows [n*t, ld_qk] (q at column head*64, k at column
- * k_col0 + head*64; q pre-scaled by 1/8, rotary already applied), vt bf16 [n*heads*64, t_pad]
- * (v transposed), out bf16 [n*t, heads*64]. */
-int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k_col0, const void* vt_dev,
-                      int32_t t_pad, int32_t n, int32_t t, int32_t heads, void* out_dev, void* stream);
+/* Non-causal attention over frames on the fused projection matrix qkv bf16 [n*t, ld]: q at column head*64
+ * (pre-scaled by 1/8, rotary already applied), k at k_col0 + head*64 (rotary applied), v at v_col0 + head*64;
+ * out bf16 [n*t, heads*64].  ld and the column offsets are multiples of 8 elements. */
+int32_t cre_attention(cre_ctx* ctx, const void* qkv_dev, int32_t ld, int32_t k_col0, int32_t v_col0, int32_t n,
+                      int32_t t, int32_t heads, void* out_dev, void* stream);
 
 /* ---- launch accounting -------------------------------------------------------------------------------
  * cre_kernel_launches: kernels launched by this library in this process so far (bench.py's gpu_launches).

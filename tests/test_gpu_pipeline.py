@@ -32,7 +32,7 @@ def test_forward_tokens_vs_fp32_oracle(engine_b, cg):
         patches = eng.preprocess(torch.from_numpy(fr).to(eng.device), bgr=True)
         emb, tok = eng.forward_patches(patches, 5, want_tokens=True)
     finally:
-        set_cta_group(1)
+        set_cta_group(2)
     tok, emb = tok.cpu(), emb.cpu()
     assert torch.isfinite(tok).all()
     assert ((tok - ref_tok).abs().max() / ref_tok.abs().max()).item() < 2e-2        # bf16 operands through 12 layers

@@ -73,7 +73,7 @@ PROTOTYPES = {
     "cre_gallery_update_row": (_i32, [_vp, _i32, _i32, _vp, _f32, _vp]),
     "cre_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "cre_layernorm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
-    "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cre_set_cta_group": (_i32, [_i32]),
     "cre_set_tuning": (_i32, [C.c_char_p, _i32]),
     "cre_kernel_launches": (_i64, []),

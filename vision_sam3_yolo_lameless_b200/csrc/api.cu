@@ -109,25 +109,20 @@ int64_t weight_offset(const cre_model_cfg* c, int layer, int kind) {
 struct Workspace {
     float* x;            // [M, D] residual stream, fp32
     __nv_bfloat16* h;    // [M, D] LayerNorm output / attention output
-    __nv_bfloat16* qk;   // [M, 2D] q (pre-scaled, rotated) | k (rotated)
-    __nv_bfloat16* vt;   // [n*heads*64, t_pad] v transposed
+    __nv_bfloat16* qkv;  // [M, 3D] q (pre-scaled, rotated) | k (rotated) | v
     __nv_bfloat16* mlp;  // [M, F]
-    int64_t vt_bytes;
     int64_t total;
 };
 Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) {
     const int64_t T = static_cast<int64_t>(gh) * gw + 1 + c->registers;
     const int64_t M = frames * T, D = c->hidden, F = c->mlp;
-    const int64_t tpad = align_up(T, 8);
     uint8_t* p = static_cast<uint8_t*>(base);
     int64_t off = 0;
     Workspace w;
     auto take = [&](int64_t bytes) { uint8_t* r = p + off; off += align_up(bytes, 1024); return r; };
     w.x = reinterpret_cast<float*>(take(M * D * 4));
     w.h = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
-    w.qk = reinterpret_cast<__nv_bfloat16*>(take(M * 2 * D * 2));
-    w.vt_bytes = static_cast<int64_t>(frames) * D * tpad * 2;
-    w.vt = reinterpret_cast<__nv_bfloat16*>(take(w.vt_bytes));
+    w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * 2));
     w.mlp = reinterpret_cast<__nv_bfloat16*>(take(M * F * 2));
     w.total = off;
     return w;
@@ -262,7 +257,7 @@ GemmParams base_params(int M, int N, int K) {
     return p;
 }
 
-int g_default_cg = 1;
+int g_default_cg = 2;  // CTA pairs: less smem traffic per FLOP, measured 3-5 % faster in the full step
 
 }  // namespace
 
@@ -384,14 +379,11 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
     const int64_t M64 = static_cast<int64_t>(n) * T;
     CRE_REQUIRE(M64 < (1LL << 31) / 4, "vit_forward: too many token rows (%lld); split the batch", (long long)M64);
     const int M = static_cast<int>(M64), D = c.hidden, F = c.mlp, PK = 3 * c.patch * c.patch;
-    const int tpad = static_cast<int>(align_up(T, 8));
     const int cg = g_default_cg;
     RopeTable rope;
     int rc = get_rope_table(ctx, grid_h, grid_w, &rope);
     if (rc) return rc;
 
-    // pad columns of vt must be finite zeros: P is zero there, but 0 * NaN would poison the PV product
-    CRE_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, stream));
     rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
     if (rc) return rc;
     {   // patch embedding: [n*P, 768] x [D, 768]^T + bias -> token rows prefix.. of x
@@ -411,26 +403,23 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
         {
             GemmParams p = base_params(M, 3 * D, D);
             p.bias = ctx->w<float>(l, CRE_B_QKV);
-            p.out_bf16 = ws.qk;
-            p.ldo = 2 * D;
+            p.out_bf16 = ws.qkv;
+            p.ldo = 3 * D;
             p.rope_cos = rope.cos;
             p.rope_sin = rope.sin;
             p.tokens_per_frame = T;
             p.prefix_tokens = prefix;
             p.hidden = D;
             p.q_scale = 0.125f;  // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284)
-            p.vt = ws.vt;
-            p.t_pad = tpad;
             rc = launch_gemm(EPI_QKV, cg, ws.h, D, ctx->w<void>(l, CRE_W_QKV), D, p, ctx->num_sms, stream);
             if (rc) return rc;
         }
         {
             AttnArgs a;
-            a.qk = ws.qk;
-            a.ld_qk = 2 * D;
+            a.qkv = ws.qkv;
+            a.ld = 3 * D;
             a.k_col0 = D;
-            a.vt = ws.vt;
-            a.t_pad = tpad;
+            a.v_col0 = 2 * D;
             a.n = n;
             a.t = T;
             a.heads = c.heads;
@@ -570,15 +559,14 @@ int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const flo
                                  static_cast<cudaStream_t>(stream));
 }
 
-int32_t cre_attention(cre_ctx* ctx, const void* qk_dev, int32_t ld_qk, int32_t k_col0, const void* vt_dev, int32_t t_pad,
-                      int32_t n, int32_t t, int32_t heads, void* out_dev, void* stream) {
-    CRE_REQUIRE(ctx != nullptr && qk_dev != nullptr && vt_dev != nullptr && out_dev != nullptr, "attention: NULL argument");
+int32_t cre_attention(cre_ctx* ctx, const void* qkv_dev, int32_t ld, int32_t k_col0, int32_t v_col0, int32_t n, int32_t t,
+                      int32_t heads, void* out_dev, void* stream) {
+    CRE_REQUIRE(ctx != nullptr && qkv_dev != nullptr && out_dev != nullptr, "attention: NULL argument");
     AttnArgs a;
-    a.qk = qk_dev;
-    a.ld_qk = ld_qk;
+    a.qkv = qkv_dev;
+    a.ld = ld;
     a.k_col0 = k_col0;
-    a.vt = vt_dev;
-    a.t_pad = t_pad;
+    a.v_col0 = v_col0;
     a.n = n;
     a.t = t;
     a.heads = heads;
@@ -598,7 +586,7 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     CRE_REQUIRE(key != nullptr, "set_tuning: NULL key");
     if (strcmp(key, "cta_group") == 0) return cre_set_cta_group(value);
     if (strcmp(key, "gemm_stages") == 0) {
-        CRE_REQUIRE(value == 0 || (value >= 3 && value <= 7), "set_tuning: gemm_stages=%d", value);
+        CRE_REQUIRE(value == 0 || (value >= 3 && value <= 6), "set_tuning: gemm_stages=%d", value);
         set_gemm_stages(value);
         return 0;
     }

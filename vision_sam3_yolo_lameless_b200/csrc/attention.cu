@@ -1,17 +1,21 @@
 // Non-causal multi-head attention for the ViT blocks (HF:modeling_dinov3_vit.py:210-235,316-329):
 //   O = softmax(Q K^T) V   per (frame, head), head_dim 64, no mask, fp32 softmax.
-// Q arrives pre-scaled by head_dim^-0.5 and Q/K arrive with the rotary embedding already applied
-// (both done on the fp32 accumulators in the QKV GEMM epilogue, gemm_tcgen05.cuh EPI_QKV), V arrives
-// transposed so that both tensor-core contractions read K-major, 128B-swizzled operands:
+// Input is the fused projection matrix qkv bf16 [n*t, ld] written by the QKV GEMM epilogue
+// (gemm_tcgen05.cuh EPI_QKV): q at column head*64 (pre-scaled by head_dim^-0.5, rotary applied), k at
+// k_col0 + head*64 (rotary applied), v at v_col0 + head*64.  All three operands are fetched by TMA straight from
+// that matrix; nothing is transposed or padded in memory:
 //
-//   S[128, KB] = Q[128, 64] * K[KB, 64]^T        tcgen05.mma, accumulator in TMEM columns [0, KB)
+//   S[128, KB] = Q[128, 64] * K[KB, 64]^T        tcgen05.mma, both operands K-major, accumulator in TMEM cols [0, KB)
 //   P = exp2((S - rowmax) * log2 e)              one thread per query row (tcgen05.ld 32x32b),
-//                                                 bf16 P written to smem in the UMMA K-major layout
-//   O[128, 64] += P[128, KB] * Vt[64, KB]^T      tcgen05.mma, accumulator in TMEM columns [0, 64)
+//                                                 bf16 P written to smem in the UMMA K-major 128B-swizzle layout
+//   O[128, 64] += P[128, KB] * V[KB, 64]         tcgen05.mma, B = the V tile as loaded ([key][dim], dim contiguous)
+//                                                 = an MN-major operand (instruction-descriptor bit 16), TMEM cols [0, 64)
 //
 // One CTA = one 128-row query tile of one (frame, head); keys are visited in blocks of KB <= 256
-// (a single block for the 201-token 224x224 case) with the usual running max / running sum.
+// (a single block for the 201-token 224x224 case) with the usual running max / running sum.  Keys past the end
+// of the frame inside a block belong to the next frame (or are TMA zero fill): their P is forced to 0.
 #include "common.cuh"
+#include "gemm_tcgen05.cuh"
 #include "internal.h"
 
 namespace cre {
@@ -19,14 +23,14 @@ namespace cre {
 constexpr int kAttnThreads = 128;
 constexpr int kAttnQBytes = 128 * 128;           // 128 rows x 64 bf16
 constexpr int kAttnKPBytes = 4 * 128 * 128;      // K block (<= 256 x 128 B) aliased with P (4 chunks of 128 x 128 B)
-constexpr int kAttnVtBytes = 4 * 64 * 128;       // 4 chunks of 64 (d) x 64 (keys) bf16
-constexpr int kAttnSmemBytes = kAttnQBytes + kAttnKPBytes + kAttnVtBytes + 128;
+constexpr int kAttnVBytes = 256 * 128;           // V block: <= 256 keys x 64 dims
+constexpr int kAttnSmemBytes = kAttnQBytes + kAttnKPBytes + kAttnVBytes + 128;   // x2 CTAs (+1 KB reserved each) fits one SM
 
 struct AttnParams {
     int t, heads, kb, nblocks;
     __nv_bfloat16* out;
     int ld_out;
-    int k_col0;
+    int k_col0, v_col0;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -38,23 +42,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// UMMA shared-memory descriptor for an MN-major operand tile stored [k][64 elements] with 128-byte rows and the
+// 128B swizzle (exactly what a TMA box of 64 bf16 columns x k rows produces): the 64 MN elements of one k are
+// contiguous, 8 consecutive k form a 1024-byte swizzle atom, atoms along k are SBO = 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;                      // LBO: stride between 64-element MN blocks (single block: unused)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO: 8 k-rows
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t n) {
+    return umma_idesc_bf16(m, n) | (1u << 16);                // B operand is MN-major
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                 const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();  // 128B swizzle atoms need 1024-byte alignment
     const uint32_t s_q = smem_base;
     const uint32_t s_kp = s_q + kAttnQBytes;
-    const uint32_t s_vt = s_kp + kAttnKPBytes;
-    const uint32_t bar_q = s_vt + kAttnVtBytes;
+    const uint32_t s_v = s_kp + kAttnKPBytes;
+    const uint32_t bar_q = s_v + kAttnVBytes;
     const uint32_t bar_kv = bar_q + 8;
     const uint32_t bar_s = bar_q + 16;
     const uint32_t bar_o = bar_q + 24;
     const uint32_t tmem_slot = bar_q + 32;
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
-    uint8_t* p_gen = smem_raw + kAttnQBytes;  // generic pointer to the K/P region
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint8_t* p_gen = smem_raw + (s_kp - smem_u32(smem_raw));  // generic pointer to the K/P region
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -63,8 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_vt);
+        tma_prefetch_desc(&tmap_kv);
         mbar_init(bar_q, 1);
         mbar_init(bar_kv, 1);
         mbar_init(bar_s, 1);
@@ -92,16 +121,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int j = 0; j < 64; ++j) o_acc[j] = 0.0f;
     float m_run = -INFINITY, l_run = 0.0f;
 
-    const int nchunks = (KB + 63) >> 6;
+    const uint32_t r7 = tid & 7;
+    uint8_t* p_row = p_gen + (tid >> 3) * 1024 + r7 * 128;
+    const int nchunk16 = KB >> 4;
+
     for (int kb = 0; kb < p.nblocks; ++kb) {
         const int key0 = kb * KB;
         const uint32_t ph = kb & 1;
+        const int valid = min(KB, T - key0);      // keys of this frame inside the block (>= 1)
         if (tid == 0) {
-            mbar_arrive_expect_tx(bar_kv, KB * 128 + nchunks * 64 * 128);
-            tma_load_2d<1>(&tmap_k, bar_kv, s_kp, p.k_col0 + head * 64, frame * T + key0, kEvictNormal);
-            for (int c = 0; c < nchunks; ++c)
-                tma_load_2d<1>(&tmap_vt, bar_kv, s_vt + c * (64 * 128), key0 + c * 64, (frame * p.heads + head) * 64,
-                               kEvictNormal);
+            mbar_arrive_expect_tx(bar_kv, 2 * KB * 128);
+            tma_load_2d<1>(&tmap_kv, bar_kv, s_kp, p.k_col0 + head * 64, frame * T + key0, kEvictNormal);
+            tma_load_2d<1>(&tmap_kv, bar_kv, s_v, p.v_col0 + head * 64, frame * T + key0, kEvictNormal);
             if (kb == 0) mbar_wait(bar_q, 0);
             mbar_wait(bar_kv, ph);
             tc_fence_after();
@@ -118,54 +149,82 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
         // ---- pass 1: row maximum over the valid keys of this block ----
         float m_blk = -INFINITY;
-        for (int c = 0; c < KB; c += 16) {
+        const int nfull = valid >> 4, rem = valid & 15;
+        for (int c = 0; c < nfull; ++c) {
             uint32_t v[16];
-            tmem_ld16(t_row + c, v);
+            tmem_ld16(t_row + c * 16, v);
+            tmem_ld_wait();
+            float a = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+            float b = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+            for (int j = 4; j < 16; j += 4) {
+                a = fmaxf(a, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                b = fmaxf(b, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            }
+            m_blk = fmaxf(m_blk, fmaxf(a, b));
+        }
+        if (rem != 0) {
+            uint32_t v[16];
+            tmem_ld16(t_row + nfull * 16, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (key0 + c + j < T) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+                if (j < rem) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
         }
         const float m_new = fmaxf(m_run, m_blk);
-        const float alpha = exp2f((m_run - m_new) * kLog2e);  // 0 on the first block (m_run = -inf)
-        const float m_scaled = m_new * kLog2e;
+        const float alpha = ex2_approx((m_run - m_new) * kLog2e);  // 0 on the first block (m_run = -inf)
+        const uint64_t neg_m2 = pack2(-m_new * kLog2e, -m_new * kLog2e);
+        const uint64_t l2e2 = pack2(kLog2e, kLog2e);
 
         // ---- pass 2: P = exp2(S*log2e - m), row sum, bf16 P into the swizzled K-major smem tile ----
-        float l_blk = 0.0f;
-        const uint32_t r7 = tid & 7;
-        uint8_t* p_row = p_gen + (tid >> 3) * 1024 + r7 * 128;
-        for (int c = 0; c < KB; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_row + c, v);
-            tmem_ld_wait();
-            float e[16];
+        uint64_t l2 = pack2(0.0f, 0.0f);
+        for (int c = 0; c < nchunk16; ++c) {
+            uint32_t pk[8];
+            if (c < nfull || (c == nfull && rem != 0)) {
+                uint32_t v[16];
+                tmem_ld16(t_row + c * 16, v);
+                tmem_ld_wait();
+                float e[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float pj = (key0 + c + j < T) ? exp2f(fmaf(__uint_as_float(v[j]), kLog2e, -m_scaled)) : 0.0f;
-                e[j] = pj;
-                l_blk += pj;
+                for (int j = 0; j < 16; j += 2) {
+                    float x0, x1;
+                    unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
+                    e[j] = ex2_approx(x0);
+                    e[j + 1] = ex2_approx(x1);
+                }
+                if (c == nfull) {   // partial chunk: keys >= valid belong to another frame
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j >= rem) e[j] = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    l2 = add2(l2, pack2(e[j], e[j + 1]));
+                    pk[j >> 1] = pack_bf16x2(e[j], e[j + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = 0u;
             }
-            const int chunk = c >> 6;
-            const uint32_t u0 = (c & 63) >> 3;  // first 16-byte unit inside the 128-byte row
+            const int chunk = c >> 2;                       // 64-key smem chunk
+            const uint32_t u0 = (static_cast<uint32_t>(c) & 3u) << 1;  // first 16-byte unit inside the 128-byte row
             uint8_t* base = p_row + chunk * (128 * 128);
-            *reinterpret_cast<uint4*>(base + ((u0 ^ r7) << 4)) =
-                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                           pack_bf16x2(e[6], e[7]));
-            *reinterpret_cast<uint4*>(base + (((u0 + 1) ^ r7) << 4)) =
-                make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]),
-                           pack_bf16x2(e[14], e[15]));
+            *reinterpret_cast<uint4*>(base + ((u0 ^ r7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(base + (((u0 + 1) ^ r7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        float l_lo, l_hi;
+        unpack2(l2, l_lo, l_hi);
+        const float l_blk = l_lo + l_hi;
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
 
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16(128, 64);
-            const int ksteps = KB >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
+            for (int ks = 0; ks < nchunk16; ++ks) {
                 const uint64_t dp = umma_desc_k_sw128(s_kp + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
-                const uint64_t dv = umma_desc_k_sw128(s_vt + (ks >> 2) * (64 * 128)) + 2 * (ks & 3);
+                const uint64_t dv = umma_desc_mn_sw128(s_v + ks * 2048);   // 16 keys = two 8-row atoms
                 umma_bf16<1>(tmem_base, dp, dv, idesc, ks != 0);
             }
             umma_commit<1>(bar_o);
@@ -205,19 +264,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.n > 0 && a.t > 0 && a.heads > 0, "attention: empty problem");
-    CRE_REQUIRE(a.t_pad % 8 == 0 && a.t_pad >= a.t, "attention: t_pad=%d must be a multiple of 8 and >= t=%d", a.t_pad,
-                a.t);
+    CRE_REQUIRE(a.ld % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0, "attention: ld / column offsets must be multiples of 8");
     const int nblocks = (a.t + 255) / 256;
     int kb = (a.t + nblocks - 1) / nblocks;
     kb = (kb + 15) & ~15;
     CRE_REQUIRE(kb >= 16 && kb <= 256, "attention: key block %d out of range", kb);
     const int64_t rows = static_cast<int64_t>(a.n) * a.t;
-    CUtensorMap tq, tk, tv;
-    int rc = make_tmap_bf16(&tq, a.qk, rows, a.ld_qk, a.ld_qk, 128);
+    CUtensorMap tq, tkv;
+    int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 128);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tk, a.qk, rows, a.ld_qk, a.ld_qk, kb);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tv, a.vt, static_cast<int64_t>(a.n) * a.heads * 64, a.t_pad, a.t_pad, 64);
+    rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -232,9 +288,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     p.out = static_cast<__nv_bfloat16*>(a.out);
     p.ld_out = a.heads * 64;
     p.k_col0 = a.k_col0;
+    p.v_col0 = a.v_col0;
     dim3 grid((a.t + 127) / 128, a.heads, a.n);
     LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
-    attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tk, tv, p);
+    attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tkv, p);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -54,10 +54,36 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
     return 0;
 }
 
+// output tile map for the TMA-store epilogues: box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B swizzle
+static int make_tmap_out(CUtensorMap* out, int epi, const GemmParams& p) {
+    EncodeTiledFn fn = get_encode_fn();
+    CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    const bool bf16 = epi_out_bf16(epi);
+    void* base = bf16 ? static_cast<void*>(p.out_bf16) : static_cast<void*>(p.out_f32);
+    const int esize = bf16 ? 2 : 4;
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: output pointer must be 16-byte aligned");
+    CRE_REQUIRE((static_cast<int64_t>(p.ldo) * esize) % 16 == 0, "gemm: output row stride must be a multiple of 16 bytes");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.ldo) * esize};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (output) failed with CUresult %d (M=%d N=%d ldo=%d)", (int)r, p.M, p.N,
+                p.ldo);
+    return 0;
+}
+
 template <int EPI, int CG, int STAGES = default_stages(CG)>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                       cudaStream_t stream) {
-    using Cfg = GemmCfg<CG, STAGES>;
+    using Cfg = GemmCfg<EPI, CG, STAGES>;
+    CUtensorMap tout = ta;   // placeholder for the epilogues that store directly
+    if constexpr (epi_tma_store(EPI)) {
+        const int rc = make_tmap_out(&tout, EPI, p);
+        if (rc) return rc;
+    }
     static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline does not fit in shared memory");
     auto* kern = gemm_tn_kernel<EPI, CG, STAGES>;
     static bool attr_set = false;  // per instantiation
@@ -88,7 +114,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     // work: FLOPs, except the gallery scan which is bound by reading the bf16 gallery once (bytes)
     const double work = EPI == EPI_TOPK ? 2.0 * p.N * p.b_k_extent : 2.0 * p.M * static_cast<double>(p.N) * p.K;
     LaunchScope scope(kid, work, stream);
-    CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p));
     return 0;
 }
 
@@ -117,7 +143,6 @@ static int launch_tuned(int cg, int stages, const CUtensorMap& ta, const CUtenso
         if (stages == 4) return launch_one<EPI, 2, 4>(ta, tb, p, num_sms, stream);
         if (stages == 5) return launch_one<EPI, 2, 5>(ta, tb, p, num_sms, stream);
         if (stages == 6) return launch_one<EPI, 2, 6>(ta, tb, p, num_sms, stream);
-        if (stages == 7) return launch_one<EPI, 2, 7>(ta, tb, p, num_sms, stream);
     }
     set_error("gemm: no instantiation for cta_group=%d stages=%d", cg, stages);
     return -3;
@@ -128,7 +153,8 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     CRE_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
     CRE_REQUIRE(p.K % kBlockK == 0, "gemm: K=%d must be a multiple of %d", p.K, kBlockK);
     CRE_REQUIRE(p.b_k_extent % kBlockK == 0 && p.b_k_extent > 0, "gemm: bad b_k_extent %d", p.b_k_extent);
-    CRE_REQUIRE(epi == EPI_TOPK || p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
+    CRE_REQUIRE(epi == EPI_TOPK || p.N % (epi_out_bf16(epi) ? 64 : 32) == 0, "gemm: N=%d must be a multiple of %d for this epilogue",
+                p.N, epi_out_bf16(epi) ? 64 : 32);
     CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
     if (g_debug_mode != 0 && epi == EPI_NONE) {
         GemmParams q = p;

@@ -4,10 +4,17 @@
 //   warp 0 lane 0 : TMA producer   (A tile 128x64, B tile (256/CG)x64, 128B swizzle, mbarrier ring)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma kind::f16, M = 128*CG, N = 256, K = 16 per instruction)
 //   warp 2        : TMEM allocator (512 columns = two 256-column accumulator stages)
-//   warps 4..11   : epilogue       (tcgen05.ld 32x32b -> fused bias/RoPE/GELU/LayerScale/residual -> global)
+//   warps 4..11   : epilogue       (tcgen05.ld 32x32b -> fused math -> swizzled smem staging -> TMA store / TMA reduce-add)
 //
 // CG = 1: one CTA per SM.  CG = 2: a CTA pair (cluster of 2, cta_group::2) shares one 256x256
 // accumulator tile; each CTA loads its own 128 A rows and half of the B rows, the leader issues.
+//
+// Epilogue data path.  tcgen05.ld 32x32b hands every thread one accumulator ROW; writing rows straight to
+// global memory touches 32 different 128-byte lines per instruction (LSU-wavefront bound, measured: the
+// residual epilogue kept the tensor pipe 21 % busy).  Instead each epilogue warp parks its 32 rows x 128 bytes
+// in a private 4 KB smem tile in the TMA 128B-swizzle layout (conflict-free 16-byte stores) and one lane issues
+// a bulk tensor store; the residual update  x += lambda * (acc + bias)  is a TMA reduce-add, so the fp32
+// residual stream is never read by the SMs at all.
 //
 // Epilogues implement the arithmetic of HF DINOv3ViT (transformers 5.5.0,
 // models/dinov3_vit/modeling_dinov3_vit.py): patch embedding :75-92, q/k/v projection + rotary on
@@ -19,12 +26,12 @@
 namespace cre {
 
 enum GemmEpi : int {
-    EPI_BF16 = 0,   // out_bf16[m, n] = acc + bias[n]
-    EPI_F32 = 1,    // out_f32[m, n]  = acc + bias[n]
-    EPI_QKV = 2,    // bias, rotary on q/k columns of patch tokens, q * q_scale -> bf16
-    EPI_GELU = 3,   // out_bf16 = gelu_erf(acc + bias)
-    EPI_RESID = 4,  // out_f32[m, n] += scale[n] * (acc + bias[n])            (residual stream, in place)
-    EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]               (patch rows -> token rows)
+    EPI_BF16 = 0,   // out_bf16[m, n] = acc + bias[n]                                   (TMA store)
+    EPI_F32 = 1,    // out_f32[m, n]  = acc + bias[n]                                   (TMA store)
+    EPI_QKV = 2,    // bias, rotary on q/k columns of patch tokens, q * q_scale -> bf16  (TMA store, [M, 3*hidden])
+    EPI_GELU = 3,   // out_bf16 = gelu_erf(acc + bias)                                  (TMA store)
+    EPI_RESID = 4,  // out_f32[m, n] += scale[n] * (acc + bias[n])                      (TMA reduce-add, in place)
+    EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]   (patch rows -> token rows, direct stores)
     EPI_TOPK = 6,   // running per-row top-k over the columns this CTA visits  (gallery scan)
     EPI_NONE = 7,   // accumulators are dropped (main-loop tuning only)
 };
@@ -44,8 +51,6 @@ struct GemmParams {
     const float* rope_sin;
     int tokens_per_frame, prefix_tokens, hidden;
     float q_scale;
-    __nv_bfloat16* vt;   // [frames * heads * 64, t_pad]: v written transposed for the attention PV operand
-    int t_pad;
     // EPI_PATCH
     int patches_per_frame;
     // EPI_TOPK
@@ -64,27 +69,93 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytes = 32 * 128;  // one epilogue warp's staging tile: 32 rows x 128 bytes
 
+constexpr bool epi_tma_store(int epi) {
+    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID;
+}
+constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
 
-template <int CG, int STAGES>
+template <int EPI, int CG, int STAGES>
 struct GemmCfg {
     static constexpr int kStages = STAGES;
     static constexpr int kSmemA = kBlockM * kBlockK * 2;          // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
-    static constexpr int kBarOff = kStages * (kSmemA + kSmemB);
+    static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
+    static constexpr int kEpiBytes = epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
+    static constexpr int kBarOff = kEpiOff + kEpiBytes;
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;       // barriers + tmem ptr + align slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (FFMA2 / FMUL2): two accumulator columns per instruction in the epilogues
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
 }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// gelu(x) = x * Phi(x) with the exact-erf Phi of nn.functional.gelu (HF:activations.py "gelu").  Phi(x) - 1/2 is odd:
+// Phi(x) = 1/2 + xc * P(xc^2), xc = clamp(x, +-4.5), P a degree-8 near-minimax fit constrained so that Phi(4.5) = 1
+// exactly (|x| > 4.5 then gives x and 0).  Max |error| on gelu over all x: 5.7e-5 (bf16 output half-ulp at |y| = 1 is
+// 2e-3); erff() costs ~30 FMA-pipe instructions per element and made the up-projection epilogue slower than its MMAs.
+__device__ __forceinline__ void gelu2(float& x0, float& x1) {
+    const float a = fminf(fmaxf(x0, -4.5f), 4.5f), b = fminf(fmaxf(x1, -4.5f), 4.5f);
+    const uint64_t xc = pack2(a, b);
+    const uint64_t t = mul2(xc, xc);
+    uint64_t p = pack2(2.999970758e-11f, 2.999970758e-11f);
+    p = fma2(p, t, pack2(-3.283879391e-09f, -3.283879391e-09f));
+    p = fma2(p, t, pack2(1.580244771e-07f, 1.580244771e-07f));
+    p = fma2(p, t, pack2(-4.431659363e-06f, -4.431659363e-06f));
+    p = fma2(p, t, pack2(8.120941493e-05f, 8.120941493e-05f));
+    p = fma2(p, t, pack2(-1.036251313e-03f, -1.036251313e-03f));
+    p = fma2(p, t, pack2(9.580645710e-03f, 9.580645710e-03f));
+    p = fma2(p, t, pack2(-6.597725302e-02f, -6.597725302e-02f));
+    p = fma2(p, t, pack2(3.987085521e-01f, 3.987085521e-01f));
+    const uint64_t g = fma2(xc, p, pack2(0.5f, 0.5f));
+    const uint64_t y = mul2(pack2(x0, x1), g);
+    unpack2(y, x0, x1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA store / reduce (smem tile in the 128B-swizzle layout -> global), bulk-group bookkeeping
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int EPI, int CG, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
-    using Cfg = GemmCfg<CG, STAGES>;
+               const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+    using Cfg = GemmCfg<EPI, CG, STAGES>;
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -109,6 +180,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if constexpr (epi_tma_store(EPI)) tma_prefetch_desc(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -207,6 +279,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int quarter = warp & 3;          // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;      // which 128 accumulator columns
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        // this warp's staging tile (TMA-store epilogues): row r at r*128, 16-byte unit u at (u ^ (r & 7))
+        const uint32_t stage_u32 = smem_base + Cfg::kEpiOff + (warp - 4) * kEpiStageBytes;
+        uint8_t* stage_row = smem_raw + (stage_u32 - smem_u32(smem_raw)) + lane * 128;
+        const uint32_t r7 = lane & 7;
+        auto stage_store = [&](int u, uint4 v) {
+            *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(u) ^ r7) << 4)) = v;
+        };
+        // wait until the previous bulk store has drained this warp's tile, then it may be overwritten
+        auto stage_begin = [&]() {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+        };
+        // hand the staged 32 x 128 B tile to the TMA
+        auto stage_commit = [&](int col, int row) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (EPI == EPI_RESID) tma_reduce_add_2d(&tmap_out, stage_u32, col, row);
+                else tma_store_2d(&tmap_out, stage_u32, col, row);
+                bulk_commit();
+            }
+        };
 
         // EPI_TOPK running state
         float tk_s[kTopKMax];
@@ -232,11 +326,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int mt = t / num_nt, nt = t % num_nt;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int row = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+            const int row_base = (mt * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
+            const int row = row_base + lane;
             const bool row_ok = row < p.M;
-            mbar_wait(tmem_full_bar(as), aphase);
-            __syncwarp();
-            tc_fence_after();
             const uint32_t taddr = tmem_base + lane_off + as * kBlockN + half * 128;
             const int ncol0 = nt * kBlockN + half * 128;
 
@@ -246,10 +338,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tk_mt = mt;
                 }
             }
+            mbar_wait(tmem_full_bar(as), aphase);
+            __syncwarp();
+            tc_fence_after();
 
             if constexpr (EPI == EPI_NONE) {
                 (void)taddr; (void)ncol0; (void)row_ok;
             } else if constexpr (EPI == EPI_QKV) {
+                // one 64-column chunk = one head of q, k or v
+                const int tok = row_ok ? row % p.tokens_per_frame : 0;
+                const bool patch_row = tok >= p.prefix_tokens;
+                const size_t rope_row = static_cast<size_t>(patch_row ? tok - p.prefix_tokens : 0) * 64;
+                const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + rope_row);
+                const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + rope_row);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -257,24 +358,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint32_t a[32], b[32];
                     tmem_ld32(taddr + hh * 64, a);
                     tmem_ld32(taddr + hh * 64 + 32, b);
-                    tmem_ld_wait();
                     const int which = n0 / p.hidden;  // 0 = q, 1 = k, 2 = v
-                    const int tok = row % p.tokens_per_frame;
-                    const bool rot = which < 2 && tok >= p.prefix_tokens;
-                    const float* cs = p.rope_cos + static_cast<size_t>(rot ? tok - p.prefix_tokens : 0) * 64;
-                    const float* sn = p.rope_sin + static_cast<size_t>(rot ? tok - p.prefix_tokens : 0) * 64;
+                    const bool rot = which < 2 && patch_row;
                     const float qs = which == 0 ? p.q_scale : 1.0f;
+                    tmem_ld_wait();
                     float x1[32], x2[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        x1[j] = __uint_as_float(a[j]) + __ldg(p.bias + n0 + j);
-                        x2[j] = __uint_as_float(b[j]) + __ldg(p.bias + n0 + 32 + j);
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
+                        x1[4 * j4] = __uint_as_float(a[4 * j4]) + b1.x;
+                        x1[4 * j4 + 1] = __uint_as_float(a[4 * j4 + 1]) + b1.y;
+                        x1[4 * j4 + 2] = __uint_as_float(a[4 * j4 + 2]) + b1.z;
+                        x1[4 * j4 + 3] = __uint_as_float(a[4 * j4 + 3]) + b1.w;
+                        x2[4 * j4] = __uint_as_float(b[4 * j4]) + b2.x;
+                        x2[4 * j4 + 1] = __uint_as_float(b[4 * j4 + 1]) + b2.y;
+                        x2[4 * j4 + 2] = __uint_as_float(b[4 * j4 + 2]) + b2.z;
+                        x2[4 * j4 + 3] = __uint_as_float(b[4 * j4 + 3]) + b2.w;
                     }
                     if (rot) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + j4);
-                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn) + j4);
+                            const float4 c4 = __ldg(cs + j4);
+                            const float4 s4 = __ldg(sn + j4);
                             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
                             const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
@@ -286,36 +392,87 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             }
                         }
                     }
-                    if (row_ok && which < 2) {
-                        // q and k: [row, 2*hidden], 128 contiguous bytes per (row, head)
-                        uint4* o1 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * p.ldo + n0);
-                        uint4* o2 = o1 + 4;
+                    stage_begin();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            o1[j] = make_uint4(pack_bf16x2(x1[8 * j] * qs, x1[8 * j + 1] * qs),
-                                               pack_bf16x2(x1[8 * j + 2] * qs, x1[8 * j + 3] * qs),
-                                               pack_bf16x2(x1[8 * j + 4] * qs, x1[8 * j + 5] * qs),
-                                               pack_bf16x2(x1[8 * j + 6] * qs, x1[8 * j + 7] * qs));
-                            o2[j] = make_uint4(pack_bf16x2(x2[8 * j] * qs, x2[8 * j + 1] * qs),
-                                               pack_bf16x2(x2[8 * j + 2] * qs, x2[8 * j + 3] * qs),
-                                               pack_bf16x2(x2[8 * j + 4] * qs, x2[8 * j + 5] * qs),
-                                               pack_bf16x2(x2[8 * j + 6] * qs, x2[8 * j + 7] * qs));
+                    for (int j = 0; j < 4; ++j) {
+                        stage_store(j, make_uint4(pack_bf16x2(x1[8 * j] * qs, x1[8 * j + 1] * qs),
+                                                  pack_bf16x2(x1[8 * j + 2] * qs, x1[8 * j + 3] * qs),
+                                                  pack_bf16x2(x1[8 * j + 4] * qs, x1[8 * j + 5] * qs),
+                                                  pack_bf16x2(x1[8 * j + 6] * qs, x1[8 * j + 7] * qs)));
+                        stage_store(j + 4, make_uint4(pack_bf16x2(x2[8 * j] * qs, x2[8 * j + 1] * qs),
+                                                      pack_bf16x2(x2[8 * j + 2] * qs, x2[8 * j + 3] * qs),
+                                                      pack_bf16x2(x2[8 * j + 4] * qs, x2[8 * j + 5] * qs),
+                                                      pack_bf16x2(x2[8 * j + 6] * qs, x2[8 * j + 7] * qs)));
+                    }
+                    stage_commit(n0, row_base);
+                }
+            } else if constexpr (epi_tma_store(EPI) && epi_out_bf16(EPI)) {
+                // EPI_BF16 / EPI_GELU: 64-column chunks, bf16 out
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int n0 = ncol0 + hh * 64;
+                    if (n0 >= p.N) break;
+                    uint32_t a[32], b[32];
+                    tmem_ld32(taddr + hh * 64, a);
+                    tmem_ld32(taddr + hh * 64 + 32, b);
+                    tmem_ld_wait();
+                    uint32_t o[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+                        if (p.bias != nullptr) {
+                            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                            b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
                         }
-                    } else if (row_ok) {
-                        // v: transposed, vt[(frame*heads + head)*64 + d, tok]; a warp's 32 lanes are
-                        // 32 consecutive tokens, so each store instruction writes one 64-byte run
-                        const int frame = row / p.tokens_per_frame;
-                        const int head = (n0 - 2 * p.hidden) >> 6;
-                        const int heads = p.hidden >> 6;
-                        __nv_bfloat16* o = p.vt + (static_cast<size_t>(frame) * heads + head) * 64 * p.t_pad + tok;
+                        float v0 = __uint_as_float(a[4 * j4]) + b1.x, v1 = __uint_as_float(a[4 * j4 + 1]) + b1.y;
+                        float v2 = __uint_as_float(a[4 * j4 + 2]) + b1.z, v3 = __uint_as_float(a[4 * j4 + 3]) + b1.w;
+                        float w0 = __uint_as_float(b[4 * j4]) + b2.x, w1 = __uint_as_float(b[4 * j4 + 1]) + b2.y;
+                        float w2 = __uint_as_float(b[4 * j4 + 2]) + b2.z, w3 = __uint_as_float(b[4 * j4 + 3]) + b2.w;
+                        if constexpr (EPI == EPI_GELU) {
+                            gelu2(v0, v1); gelu2(v2, v3); gelu2(w0, w1); gelu2(w2, w3);
+                        }
+                        o[2 * j4] = pack_bf16x2(v0, v1);
+                        o[2 * j4 + 1] = pack_bf16x2(v2, v3);
+                        o[16 + 2 * j4] = pack_bf16x2(w0, w1);
+                        o[16 + 2 * j4 + 1] = pack_bf16x2(w2, w3);
+                    }
+                    stage_begin();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            o[static_cast<size_t>(j) * p.t_pad] = __float2bfloat16_rn(x1[j]);
-                            o[static_cast<size_t>(j + 32) * p.t_pad] = __float2bfloat16_rn(x2[j]);
+                    for (int u = 0; u < 8; ++u) stage_store(u, make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]));
+                    stage_commit(n0, row_base);
+                }
+            } else if constexpr (epi_tma_store(EPI)) {
+                // EPI_F32 / EPI_RESID: 32-column chunks, fp32 out (store / reduce-add)
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int n0 = ncol0 + c * 32;
+                    if (n0 >= p.N) break;
+                    uint32_t a[32];
+                    tmem_ld32(taddr + c * 32, a);
+                    tmem_ld_wait();
+                    float x[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                        x[4 * j4] = __uint_as_float(a[4 * j4]) + b4.x;
+                        x[4 * j4 + 1] = __uint_as_float(a[4 * j4 + 1]) + b4.y;
+                        x[4 * j4 + 2] = __uint_as_float(a[4 * j4 + 2]) + b4.z;
+                        x[4 * j4 + 3] = __uint_as_float(a[4 * j4 + 3]) + b4.w;
+                        if constexpr (EPI == EPI_RESID) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + j4);
+                            x[4 * j4] *= sc.x; x[4 * j4 + 1] *= sc.y; x[4 * j4 + 2] *= sc.z; x[4 * j4 + 3] *= sc.w;
                         }
                     }
+                    stage_begin();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        stage_store(u, make_uint4(__float_as_uint(x[4 * u]), __float_as_uint(x[4 * u + 1]),
+                                                  __float_as_uint(x[4 * u + 2]), __float_as_uint(x[4 * u + 3])));
+                    stage_commit(n0, row_base);
                 }
             } else {
+                // EPI_PATCH / EPI_TOPK: direct path
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = ncol0 + c * 32;
@@ -352,46 +509,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 }
                             }
                         }
-                    } else {
-                        if (p.bias != nullptr) {
+                    } else {  // EPI_PATCH
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-                                x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
-                            }
-                        }
-                        if constexpr (EPI == EPI_GELU) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                            x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
                         }
                         if (row_ok) {
-                            if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU) {
-                                uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * p.ldo + n0);
+                            const size_t orow = static_cast<size_t>(row / p.patches_per_frame) * p.tokens_per_frame +
+                                                p.prefix_tokens + row % p.patches_per_frame;
+                            float4* o = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + n0);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    o[j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                                      pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
-                            } else {
-                                size_t orow = static_cast<size_t>(row);
-                                if constexpr (EPI == EPI_PATCH)
-                                    orow = static_cast<size_t>(row / p.patches_per_frame) * p.tokens_per_frame +
-                                           p.prefix_tokens + row % p.patches_per_frame;
-                                float4* o = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + n0);
-                                if constexpr (EPI == EPI_RESID) {
-#pragma unroll
-                                    for (int j4 = 0; j4 < 8; ++j4) {
-                                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + j4);
-                                        float4 r = o[j4];
-                                        r.x += sc.x * x[4 * j4]; r.y += sc.y * x[4 * j4 + 1];
-                                        r.z += sc.z * x[4 * j4 + 2]; r.w += sc.w * x[4 * j4 + 3];
-                                        o[j4] = r;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j4 = 0; j4 < 8; ++j4)
-                                        o[j4] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
-                                }
-                            }
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                o[j4] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
                         }
                     }
                 }
@@ -406,6 +536,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if constexpr (EPI == EPI_TOPK) {
             if (tk_mt >= 0) topk_flush(tk_mt);
+        }
+        if constexpr (epi_tma_store(EPI)) {
+            if (lane == 0) bulk_wait0();   // every bulk store of this warp has completed before the CTA may exit
         }
     }
 

@@ -43,11 +43,9 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
                 int num_sms, cudaStream_t stream);
 
 struct AttnArgs {
-    const void* qk;   // bf16 [n*t, ld_qk]
-    int ld_qk;
-    int k_col0;
-    const void* vt;   // bf16 [n*heads*64, t_pad]
-    int t_pad;
+    const void* qkv;  // bf16 [n*t, ld]: q at column head*64, k at k_col0 + head*64, v at v_col0 + head*64
+    int ld;
+    int k_col0, v_col0;
     int n, t, heads;
     void* out;        // bf16 [n*t, heads*64]
 };

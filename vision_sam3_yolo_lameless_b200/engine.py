@@ -373,10 +373,12 @@ class ClipEmbedEngine:
                                                out.data_ptr(), self._stream()), "cre_layernorm_bf16")
         return out
 
-    def attention(self, qk: torch.Tensor, vt: torch.Tensor, n: int, t: int, heads: int) -> torch.Tensor:
-        out = torch.empty((n * t, heads * 64), dtype=torch.bfloat16, device=self.device)
-        _lib.check(self.lib.cre_attention(self._ctx, qk.data_ptr(), qk.shape[1], heads * 64, vt.data_ptr(), vt.shape[1],
-                                          n, t, heads, out.data_ptr(), self._stream()), "cre_attention")
+    def attention(self, qkv: torch.Tensor, n: int, t: int, heads: int) -> torch.Tensor:
+        """qkv bf16 [n*t, 3*heads*64] (q pre-scaled, rotary applied) -> bf16 [n*t, heads*64]."""
+        d = heads * 64
+        out = torch.empty((n * t, d), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.cre_attention(self._ctx, qkv.data_ptr(), qkv.shape[1], d, 2 * d, n, t, heads, out.data_ptr(),
+                                          self._stream()), "cre_attention")
         return out
 
 
