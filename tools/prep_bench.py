@@ -1,0 +1,16 @@
+"""K1 standalone timing on 1080p / 720p noise frames (device resident)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from oracle import common
+from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
+from gemm_tune import timeit
+
+model = common.hf_model(layers=1)
+eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=600)
+for (n, h, w) in [(600, 1080, 1920), (600, 720, 1280), (600, 224, 224)]:
+    fr = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=eng.device)
+    ms = timeit(lambda: eng.preprocess(fr), iters=10)
+    b = n * (h * w * 3 + 196 * 1536)
+    print(f"preprocess {n}x{h}x{w}: {ms:.3f} ms  {ms / n * 1e3:.2f} us/frame  {b / ms / 1e6:.0f} GB/s", flush=True)

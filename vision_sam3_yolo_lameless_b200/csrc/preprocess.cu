@@ -15,12 +15,13 @@
 //           memory, normalise, bf16, fully coalesced 1536-byte stores per patch.
 // Each input byte is read from DRAM once (neighbouring CTAs share at most the filter support via L2).
 #include "common.cuh"
+#include "gemm_tcgen05.cuh"
 #include "internal.h"
 
 namespace cre {
 
 constexpr int kBandPatches = 2;
-constexpr int kPreThreads = 512;
+constexpr int kPreThreads = 448;   // x3 CTAs per SM (<= 48 registers)
 
 struct PreParams {
     const uint8_t* frames;
@@ -36,7 +37,14 @@ struct PreParams {
     int vec;      // 1: 16-byte aligned rows, vector loads allowed
 };
 
-__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams p) {
+// byte j of `word` -> the float 1 + b * 2^-15 (bits 0x3F80bb00) with ONE byte-permute: no shift / mask / int->float
+// conversion per byte.  The vertical filter accumulates sum_k w_k * (1 + b_k * 2^-15) with packed FFMA2 and removes the
+// offset exactly afterwards (minus sum_k w_k, times 2^15): rounding error <= 0.02 byte units, 2e-4 after normalisation.
+__device__ __forceinline__ float byte_as_unit_float(uint32_t word, uint32_t selector) {
+    return __uint_as_float(__byte_perm(word, 0x3F800000u, selector));
+}
+
+__global__ void __launch_bounds__(kPreThreads, 3) preprocess_kernel(const PreParams p) {
     extern __shared__ __align__(16) float vbuf[];  // [16][sstride]
     const int band = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
     const int px0 = band * kBandPatches;
@@ -49,36 +57,58 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     const int nvec = (nbytes + 15) >> 4;
     const int row_bytes = p.w * 3;
     const uint8_t* fbase = p.frames + static_cast<int64_t>(frame) * p.frame_pitch;
+    const int nthreads = blockDim.x;
 
-    // ---- pass 1: vertical filter ----
-    for (int item = threadIdx.x; item < 16 * nvec; item += kPreThreads) {
+    // ---- pass 1: vertical filter (each item = one output row x one 16-byte column group) ----
+    for (int item = threadIdx.x; item < 16 * nvec; item += nthreads) {
         const int r = item / nvec, v = item - r * nvec;
         const int oy = py * 16 + r;
         const int y0 = p.ylo[oy], cnt = p.ycnt[oy];
         const float* wy = p.yw + static_cast<size_t>(oy) * p.ykmax;
         const int col = b0 + v * 16;
         float acc[16];
+        const uint8_t* src = fbase + static_cast<int64_t>(y0) * p.row_pitch + col;
+        if (p.vec && (col + 16 <= row_bytes)) {
+            uint64_t acc2[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
-        const bool full = p.vec && (col + 16 <= row_bytes);
-        for (int k = 0; k < cnt; ++k) {
-            const float wk = __ldg(wy + k);
-            const uint8_t* src = fbase + static_cast<int64_t>(y0 + k) * p.row_pitch + col;
-            if (full) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+            for (int i = 0; i < 8; ++i) acc2[i] = pack2(0.0f, 0.0f);
+            float wsum = 0.0f;
+#pragma unroll 3
+            for (int k = 0; k < cnt; ++k) {
+                const float wk = __ldg(wy + k);
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(k) * p.row_pitch));
+                const uint64_t w2 = pack2(wk, wk);
+                wsum += wk;
                 const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    acc[4 * i + 0] = fmaf(wk, static_cast<float>(wds[i] & 0xffu), acc[4 * i + 0]);
-                    acc[4 * i + 1] = fmaf(wk, static_cast<float>((wds[i] >> 8) & 0xffu), acc[4 * i + 1]);
-                    acc[4 * i + 2] = fmaf(wk, static_cast<float>((wds[i] >> 16) & 0xffu), acc[4 * i + 2]);
-                    acc[4 * i + 3] = fmaf(wk, static_cast<float>(wds[i] >> 24), acc[4 * i + 3]);
+                    acc2[2 * i] = fma2(pack2(byte_as_unit_float(wds[i], 0x7604u), byte_as_unit_float(wds[i], 0x7614u)), w2, acc2[2 * i]);
+                    acc2[2 * i + 1] = fma2(pack2(byte_as_unit_float(wds[i], 0x7624u), byte_as_unit_float(wds[i], 0x7634u)), w2, acc2[2 * i + 1]);
                 }
-            } else {
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float lo, hi;
+                unpack2(acc2[i], lo, hi);
+                acc[2 * i] = (lo - wsum) * 32768.0f;
+                acc[2 * i + 1] = (hi - wsum) * 32768.0f;
+            }
+        } else {
+            // unaligned / ragged edge: byte loads, SAME arithmetic (1 + b * 2^-15, same FMA order) -> bit-identical results
+            float wsum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+            for (int k = 0; k < cnt; ++k) {
+                const float wk = __ldg(wy + k);
+                wsum += wk;
+                const uint8_t* s8 = src + static_cast<int64_t>(k) * p.row_pitch;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (col + i < row_bytes) acc[i] = fmaf(wk, static_cast<float>(__ldg(src + i)), acc[i]);
+                    if (col + i < row_bytes)
+                        acc[i] = fmaf(__uint_as_float(0x3F800000u | (static_cast<uint32_t>(__ldg(s8 + i)) << 8)), wk, acc[i]);
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = (col + i < row_bytes) ? (acc[i] - wsum) * 32768.0f : 0.0f;
         }
         float4* dst = reinterpret_cast<float4*>(vbuf + static_cast<size_t>(r) * p.sstride + v * 16);
 #pragma unroll
@@ -86,21 +116,30 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     }
     __syncthreads();
 
-    // ---- pass 2: horizontal filter + normalise + patchify ----
-    const int nout = npatch * 768;
-    for (int t = threadIdx.x; t < nout; t += kPreThreads) {
-        const int pl = t / 768, kidx = t - pl * 768;
-        const int c = kidx >> 8, ky = (kidx >> 4) & 15, kx = kidx & 15;
+    // ---- pass 2: horizontal filter + normalise + patchify; one thread = one output pixel, all 3 channels ----
+    const int nout = npatch * 256;
+    for (int t = threadIdx.x; t < nout; t += nthreads) {
+        const int pl = t >> 8, ky = (t >> 4) & 15, kx = t & 15;
         const int ox = (px0 + pl) * 16 + kx;
         const int x0 = __ldg(p.xlo + ox), cnt = __ldg(p.xcnt + ox);
         const float* wx = p.xw + static_cast<size_t>(ox) * p.xkmax;
-        const int cin = p.bgr ? 2 - c : c;
-        const float* src = vbuf + static_cast<size_t>(ky) * p.sstride + (x0 * 3 + cin - b0);
-        float s = 0.0f;
-        for (int k = 0; k < cnt; ++k) s = fmaf(__ldg(wx + k), src[3 * k], s);
-        const float val = (s * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c];
+        const float* src = vbuf + static_cast<size_t>(ky) * p.sstride + (x0 * 3 - b0);
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const float w = __ldg(wx + k);
+            s0 = fmaf(w, src[3 * k], s0);
+            s1 = fmaf(w, src[3 * k + 1], s1);
+            s2 = fmaf(w, src[3 * k + 2], s2);
+        }
+        const float sm[3] = {s0, s1, s2};   // memory channel order
         const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px0 + pl;
-        p.out[patch * 768 + kidx] = __float2bfloat16_rn(val);
+        __nv_bfloat16* o = p.out + patch * 768 + ky * 16 + kx;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = p.bgr ? 2 - j : j;  // output (RGB) channel of memory channel j
+            o[c * 256] = __float2bfloat16_rn((sm[j] * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c]);
+        }
     }
 }
 
@@ -146,8 +185,12 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
         smem_set = smem;
     }
     dim3 grid((a.gw + kBandPatches - 1) / kBandPatches, a.gh, a.n);
+    // two balanced rounds of the vertical pass: 16 rows x nvec column groups over the block
+    const int nvec_max = (span_px * 3 + 15 + 15) / 16;
+    int threads = ((16 * nvec_max + 1) / 2 + 31) / 32 * 32;
+    threads = threads < 128 ? 128 : (threads > kPreThreads ? kPreThreads : threads);
     LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
-    preprocess_kernel<<<grid, kPreThreads, smem, stream>>>(p);
+    preprocess_kernel<<<grid, threads, smem, stream>>>(p);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }
