@@ -173,8 +173,9 @@ int32_t cre_profile_stop(int32_t* ids_out, float* ms_out, double* work_out, int3
 /* Process-wide tuning knob: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs on
  * 256x256 tiles (cta_group::2) for the ViT GEMMs.  Results are identical either way. */
 int32_t cre_set_cta_group(int32_t cta_group);
-/* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..7:
- * TMA pipeline depth of the cre_gemm_bf16 building block).  Unknown keys return -1. */
+/* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..6:
+ * TMA pipeline depth of the cre_gemm_bf16 building block), "attention_fast" (1 = persistent TMEM-resident kernel for
+ * T <= 256, default; 0 = general kernel), "gemm_debug".  Unknown keys return -1. */
 int32_t cre_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus

@@ -590,6 +590,14 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_gemm_stages(value);
         return 0;
     }
+    if (strcmp(key, "attention_fast") == 0) {
+        set_attention_fast(value);
+        return 0;
+    }
+    if (strcmp(key, "attention_debug") == 0) {
+        set_attention_debug(value);
+        return 0;
+    }
     if (strcmp(key, "gemm_debug") == 0) {
         set_gemm_debug(value);
         return 0;

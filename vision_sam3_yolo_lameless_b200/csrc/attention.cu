@@ -14,6 +14,8 @@
 // One CTA = one 128-row query tile of one (frame, head); keys are visited in blocks of KB <= 256
 // (a single block for the 201-token 224x224 case) with the usual running max / running sum.  Keys past the end
 // of the frame inside a block belong to the next frame (or are TMA zero fill): their P is forced to 0.
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 #include "internal.h"
@@ -42,10 +44,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ uint64_t add2_(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// exp2 of two arguments <= 0 on the FMA + ALU pipes (no MUFU): n = round(x) via the 1.5 * 2^23 magic add, f = x - n in
+// [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16 precision of P), and the
+// 2^n scale added straight into the exponent field ((bits(t) << 23): the magic's mantissa bit shifts out).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    const uint64_t xc = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t t2 = add2_(xc, pack2(12582912.0f, 12582912.0f));
+    const uint64_t n2 = add2_(t2, pack2(-12582912.0f, -12582912.0f));
+    const uint64_t f2 = fma2(n2, pack2(-1.0f, -1.0f), xc);
+    uint64_t p2 = fma2(pack2(5.517165735e-02f, 5.517165735e-02f), f2, pack2(2.426111251e-01f, 2.426111251e-01f));
+    p2 = fma2(p2, f2, pack2(6.932609677e-01f, 6.932609677e-01f));
+    p2 = fma2(p2, f2, pack2(9.999280572e-01f, 9.999280572e-01f));
+    float t0, t1, p0, p1;
+    unpack2(t2, t0, t1);
+    unpack2(p2, p0, p1);
+    r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+// two non-negative fp32 -> packed bf16x2 without the XU-pipe convert (F2FP shares the MUFU pipe, which bounds this kernel):
+// scale by 1 + 2^-9 (adds half a bf16 ulp, FMUL2 on the FMA pipe) and keep the high halves (one byte-permute).
+// Rounds half-up instead of half-even: same 2^-9 relative error bound.
+__device__ __forceinline__ uint32_t pack_bf16x2_pos(float lo, float hi) {
+    float a, b;
+    unpack2(mul2(pack2(lo, hi), pack2(1.001953125f, 1.001953125f)), a, b);
+    return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632u);
 }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d;
@@ -200,7 +235,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     l2 = add2(l2, pack2(e[j], e[j + 1]));
-                    pk[j >> 1] = pack_bf16x2(e[j], e[j + 1]);
+                    pk[j >> 1] = pack_bf16x2_pos(e[j], e[j + 1]);
                 }
             } else {
 #pragma unroll
@@ -262,6 +297,319 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
+// =====================================================================================================================
+// Fast path for T <= 256 keys (the 224x224 case, T = 201): persistent, warp-specialised, one (frame, head) per iteration.
+//
+//   warp 0      TMA producer: Q (256 rows), K, V (KB rows each) of the NEXT unit into a 2-stage smem ring
+//   warp 1      MMA issuer:   S_g = Q_g K^T (g = 0, 1: the two 128-row query tiles) -> TMEM;  O_g = P_g V with P_g read
+//                             from TMEM (tcgen05.mma A-operand-in-TMEM form) and V as an MN-major smem operand
+//   warps 2-5   softmax group 0 (rows 0..127), warps 6-9 softmax group 1 (rows 128..255): one thread per query row;
+//               row max, exp2, bf16 P written back to TMEM over the S columns (tcgen05.st), O read-back, 1/l, store.
+//
+// P never touches shared memory, K/V/Q are loaded once per (frame, head) for both query tiles, and the two softmax
+// groups ping-pong on the MUFU while the tensor core works for the other group.  TMEM columns of group g (base 256 g):
+// S = [0, KB) fp32, P = [0, KB/2) packed bf16x2 (written chunk by chunk behind the S read pointer), O = [128, 192).
+// =====================================================================================================================
+constexpr int kFaThreads = 320;
+constexpr uint32_t kFaPolyMask = 0x44;   // pairs 2 and 6 of every 8: 25 % of the exponentials bypass the MUFU (XU vs issue-slot balance)
+constexpr int kFaQBytes = 256 * 128, kFaKVBytes = 256 * 128;
+constexpr int kFaStageBytes = kFaQBytes + 2 * kFaKVBytes;            // 96 KB
+constexpr int kFaSmemBytes = 2 * kFaStageBytes + 256 + 1024;
+
+struct FaParams {
+    int t, heads, kb, units;
+    __nv_bfloat16* out;
+    int ld_out;
+    int k_col0, v_col0;
+    int debug;   // tuning only: 1 skip softmax math, 2 skip PV MMAs, 4 skip S MMAs, 8 skip O read/store, 16 skip TMA loads
+};
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kFaThreads, 1)
+attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      const FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto s_q = [&](int s) { return smem_base + s * kFaStageBytes; };
+    auto s_k = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes; };
+    auto s_v = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes + kFaKVBytes; };
+    const uint32_t bar_base = smem_base + 2 * kFaStageBytes;
+    auto kv_full = [&](int s) { return bar_base + 8u * s; };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto s_full = [&](int g) { return bar_base + 8u * (4 + g); };
+    auto p_full = [&](int g) { return bar_base + 8u * (6 + g); };
+    auto o_full = [&](int g) { return bar_base + 8u * (8 + g); };
+    auto tmem_free = [&](int g) { return bar_base + 8u * (10 + g); };
+    const uint32_t tmem_slot = bar_base + 8u * 12;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.t, KB = p.kb;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(kv_full(i), 1);
+            mbar_init(kv_empty(i), 1);
+            mbar_init(s_full(i), 1);
+            mbar_init(p_full(i), 4);
+            mbar_init(o_full(i), 1);
+            mbar_init(tmem_free(i), 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int nk = (T + 15) >> 4;             // 16-key steps that hold at least one valid key
+
+    if (warp == 0 && lane == 0) {
+        // =============================== TMA producer ===============================
+        int i = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+            const int s = i & 1;
+            const int frame = u / p.heads, head = u - frame * p.heads;
+            mbar_wait(kv_empty(s), ((i >> 1) & 1) ^ 1u);
+            if (p.debug & 16) {
+                mbar_arrive(kv_full(s));
+                continue;
+            }
+            mbar_arrive_expect_tx(kv_full(s), kFaQBytes + 2 * KB * 128);
+            tma_load_2d<1>(&tmap_q, kv_full(s), s_q(s), head * 64, frame * T, kEvictFirst);
+            tma_load_2d<1>(&tmap_kv, kv_full(s), s_k(s), p.k_col0 + head * 64, frame * T, kEvictFirst);
+            tma_load_2d<1>(&tmap_kv, kv_full(s), s_v(s), p.v_col0 + head * 64, frame * T, kEvictFirst);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // =============================== MMA issuer ===============================
+        // Event driven: each softmax group advances through (S, PV) of its own unit counter as soon as its barrier
+        // flips, so the two groups drift apart and one exponentiates while the tensor core works for the other.
+        const uint32_t idesc_s = umma_idesc_bf16(128, KB);
+        const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+        const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        int it[2] = {0, 0};        // unit counter per group
+        int st[2] = {0, 0};        // 0: S of unit it[g] pending, 1: PV of unit it[g] pending
+        int pv_done[2] = {0, 0};   // PV issued for units < pv_done[g]
+        int kv_ready = 0;          // smem stages observed full for units < kv_ready
+        uint32_t spins = 0;
+        while (it[0] < my_units || it[1] < my_units) {
+            if (++spins == (1u << 28)) __trap();   // a barrier never flipped: fail loudly instead of hanging the GPU
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int i = it[g];
+                if (i >= my_units) continue;
+                const int s = i & 1;
+                const uint32_t ph = i & 1;
+                if (st[g] == 0) {
+                    if (i >= kv_ready) {
+                        if (!mbar_test(kv_full(s), (i >> 1) & 1)) continue;
+                        kv_ready = i + 1;
+                    }
+                    if (g * 128 < T) {
+                        if (!mbar_test(tmem_free(g), ph ^ 1u)) continue;   // group g has drained O of its previous unit
+                        tc_fence_after();
+                        const uint64_t dq = umma_desc_k_sw128(s_q(s) + g * (128 * 128));
+                        const uint64_t dk = umma_desc_k_sw128(s_k(s));
+                        if (!(p.debug & 4)) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base + g * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                        }
+                    }
+                    umma_commit<1>(s_full(g));
+                    st[g] = 1;
+                } else {
+                    if (!mbar_test(p_full(g), ph)) continue;
+                    tc_fence_after();
+                    if (g * 128 < T && !(p.debug & 2)) {
+                        for (int ks = 0; ks < nk; ++ks)
+                            umma_bf16_ts(tmem_base + g * 256 + 128, tmem_base + g * 256 + 8 * ks,
+                                         umma_desc_mn_sw128(s_v(s) + ks * 2048), idesc_o, ks != 0);
+                    }
+                    umma_commit<1>(o_full(g));
+                    pv_done[g] = i + 1;
+                    if (pv_done[g ^ 1] > i) umma_commit<1>(kv_empty(s));   // both groups are done with this smem stage
+                    st[g] = 0;
+                    it[g] = i + 1;
+                }
+            }
+        }
+    } else if (warp >= 2) {
+        // =============================== softmax groups ===============================
+        const int g = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = g * 128 + quarter * 32 + lane;          // query token inside the frame
+        const bool warp_active = g * 128 + quarter * 32 < T;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 256;
+        constexpr float kLog2e = 1.4426950408889634f;
+        const uint64_t l2e2 = pack2(kLog2e, kLog2e);
+        const int nfull = T >> 4, rem = T & 15;
+        int i = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+            const uint32_t ph = i & 1;
+            const int frame = u / p.heads, head = u - frame * p.heads;
+            mbar_wait(s_full(g), ph);
+            __syncwarp();
+            tc_fence_after();
+            float l_sum = 1.0f;
+            if (warp_active && !(p.debug & 1)) {
+                // ---- stabiliser: maximum over the FIRST 32 keys only (CLS, registers, first patches).  This kernel is
+                //      bound by the TMEM read port (64 B/clk/SM: a full max pass doubles the S traffic), and softmax is
+                //      shift invariant: any m works as long as exp2 neither overflows nor flushes the row's largest term.
+                //      With m <= true max the largest term is >= 1; exponents are clamped at +120 (2^120 is finite in
+                //      fp32 and bf16), which only alters rows where some score exceeds the 32-key max by > 83 nats. ----
+                float m = -INFINITY;
+                {
+                    const int npre = nfull < 2 ? nfull : 2;
+                    uint32_t v0[16], v1[16];
+                    if (npre == 2) {
+                        tmem_ld16(t_row, v0);
+                        tmem_ld16(t_row + 16, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])),
+                                               fmaxf(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1]))));
+                    } else {
+                        tmem_ld16(t_row, v0);
+                        tmem_ld_wait();
+                        const int lim = npre == 1 ? 16 : rem;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < lim) m = fmaxf(m, __uint_as_float(v0[j]));
+                    }
+                }
+                const uint64_t neg_m2 = pack2(-m * kLog2e, -m * kLog2e);
+                // ---- pass 2: P = exp2(S log2e - m log2e) -> bf16x2 into TMEM columns [8c, 8c + 8); the TMEM read of
+                //      chunk c + 1 is in flight while chunk c is exponentiated ----
+                uint64_t l2 = pack2(0.0f, 0.0f);
+                auto softmax_chunk = [&](int cc, const uint32_t (&v)[16], auto partial) {
+                    float e[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float x0, x1;
+                        unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
+                        x0 = fminf(x0, 120.0f);
+                        x1 = fminf(x1, 120.0f);
+                        if ((kFaPolyMask >> (j >> 1)) & 1) {   // this pair on the FMA / ALU pipes
+                            exp2_poly2(pack2(x0, x1), e[j], e[j + 1]);
+                        } else {                                 // this pair on the MUFU
+                            e[j] = ex2_approx(x0);
+                            e[j + 1] = ex2_approx(x1);
+                        }
+                    }
+                    if constexpr (decltype(partial)::value) {   // last chunk: keys >= T belong to the next frame
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j >= rem) e[j] = 0.0f;
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        l2 = add2(l2, pack2(e[j], e[j + 1]));
+                        pk[j >> 1] = pack_bf16x2_pos(e[j], e[j + 1]);
+                    }
+                    tmem_st8(t_row + cc * 8, pk);
+                };
+                using True = std::true_type;
+                using False = std::false_type;
+                // full chunks two at a time (the TMEM read of the next chunk is in flight during the exponentials)
+                uint32_t va[16], vb[16];
+                tmem_ld16(t_row, va);
+                tmem_ld_wait();
+                int cc = 0;
+                for (; cc + 2 <= nfull; cc += 2) {
+                    tmem_ld16(t_row + (cc + 1) * 16, vb);
+                    softmax_chunk(cc, va, False{});
+                    tmem_ld_wait();
+                    if (cc + 2 < nk) tmem_ld16(t_row + (cc + 2) * 16, va);
+                    softmax_chunk(cc + 1, vb, False{});
+                    tmem_ld_wait();
+                }
+                if (cc < nfull) {                          // odd full chunk left (va holds it)
+                    if (cc + 1 < nk) tmem_ld16(t_row + (cc + 1) * 16, vb);
+                    softmax_chunk(cc, va, False{});
+                    tmem_ld_wait();
+                    ++cc;
+                    if (cc < nk) softmax_chunk(cc, vb, True{});
+                } else if (cc < nk) {
+                    softmax_chunk(cc, va, True{});         // the partial chunk
+                }
+                tmem_st_wait();
+                float l_lo, l_hi;
+                unpack2(l2, l_lo, l_hi);
+                l_sum = l_lo + l_hi;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(g));
+
+            mbar_wait(o_full(g), ph);
+            __syncwarp();
+            tc_fence_after();
+            if (warp_active && !(p.debug & 8)) {
+                uint32_t o[64];
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + 128 + c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[c + j] = v[j];
+                }
+                tmem_ld_wait();
+                // O is in registers: hand the TMEM columns back before the global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_free(g));
+                if (row < T) {
+                    const float inv = 1.0f / l_sum;
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + row) * p.ld_out + head * 64);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+                }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_free(g));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+static int g_attn_fast = 1;
+static int g_attn_debug = 0;
+void set_attention_debug(int mask) { g_attn_debug = mask; }
+void set_attention_fast(int on) { g_attn_fast = on; }
+
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.n > 0 && a.t > 0 && a.heads > 0, "attention: empty problem");
     CRE_REQUIRE(a.ld % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0, "attention: ld / column offsets must be multiples of 8");
@@ -271,6 +619,35 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(kb >= 16 && kb <= 256, "attention: key block %d out of range", kb);
     const int64_t rows = static_cast<int64_t>(a.n) * a.t;
     CUtensorMap tq, tkv;
+    if (nblocks == 1 && g_attn_fast) {
+        int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 256);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
+        if (rc) return rc;
+        static bool fast_attr_set = false;
+        if (!fast_attr_set) {
+            CRE_CUDA_OK(cudaFuncSetAttribute(attention_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+            fast_attr_set = true;
+        }
+        FaParams fp;
+        fp.t = a.t;
+        fp.heads = a.heads;
+        fp.kb = kb;
+        fp.units = a.n * a.heads;
+        fp.out = static_cast<__nv_bfloat16*>(a.out);
+        fp.ld_out = a.heads * 64;
+        fp.k_col0 = a.k_col0;
+        fp.v_col0 = a.v_col0;
+        fp.debug = g_attn_debug;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = fp.units < sms ? fp.units : sms;
+        LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+        attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
+        CRE_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 128);
     if (rc) return rc;
     rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);

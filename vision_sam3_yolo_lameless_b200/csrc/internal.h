@@ -15,6 +15,8 @@ const char* last_error();
 int gemm_workers(int m, int n, int cg, int num_sms);
 void set_gemm_stages(int stages);
 void set_gemm_debug(int mode);
+void set_attention_fast(int on);
+void set_attention_debug(int mask);
 
 // Kernel ids reported by cre_profile_stop (include/cre.h enum cre_kernel_id)
 // RAII bracket around one kernel launch: bumps the launch counter and, when the profiler is on, records an
