@@ -207,7 +207,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("CRE_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if args.cta_group:
         set_cta_group(args.cta_group)
 
@@ -276,14 +279,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ---- instrumented step: per-kernel CUDA-event durations (roofline) ----------------------------------------------
     kernels = {}
     roofline = None
+    # every rank runs the instrumented step (it contains the re-ID collectives); only rank 0 records events
+    if rank == 0:
+        _lib.profile_start(1 << 17)
+    step_resident()
+    recs = _lib.profile_stop(1 << 17) if rank == 0 else []
+    sync_all()
     if rank == 0:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)     # a kernel timed inside a long step -> sustained figure
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         which = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
-        _lib.profile_start(1 << 17)
-        step_resident()
-        recs = _lib.profile_stop(1 << 17)
         tot = sum(r[1] for r in recs) or 1.0
         for name, ms_k, work in recs:
             k = kernels.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
