@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--gallery-rows", type=int, default=100_000)
-    ap.add_argument("--batch-frames", type=int, default=600, help="frames per ViT launch sequence")
+    ap.add_argument("--batch-frames", type=int, default=1130, help="frames per ViT launch sequence")
     ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -24,9 +24,9 @@ struct DevTable {
     float* w = nullptr;
     int kmax = 0, in = 0, out = 0;
 };
+constexpr int kRopeRowFloats = 36;   // 16 cos + 16 sin per axis position, padded to 36 floats (bank spreading in smem)
 struct RopeTable {
-    float* cos = nullptr;
-    float* sin = nullptr;
+    float* axis = nullptr;   // [(gh + gw), 36]: rows 0..gh-1 = y positions, rows gh.. = x positions; {cos[16], sin[16], pad[4]}
 };
 
 bool cfg_ok(const cre_model_cfg* c) {
@@ -216,31 +216,25 @@ int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
         *t = it->second;
         return 0;
     }
-    const int P = gh * gw;
-    std::vector<float> c(static_cast<size_t>(P) * 64), s(static_cast<size_t>(P) * 64);
+    // The HF table is cos/sin of [y*f0..f15, x*f0..f15] tiled twice: per token only the 16 y-angles of its patch row and
+    // the 16 x-angles of its patch column are distinct, so one small per-axis table serves every token.
+    std::vector<float> tab(static_cast<size_t>(gh + gw) * kRopeRowFloats, 0.0f);
     float inv_freq[16];
     for (int k = 0; k < 16; ++k) inv_freq[k] = 1.0f / powf(ctx->cfg.rope_theta, static_cast<float>(k) * (4.0f / 64.0f));
     const float two_pi = static_cast<float>(2.0 * M_PI);
-    for (int py = 0; py < gh; ++py)
-        for (int px = 0; px < gw; ++px) {
-            const float cy = 2.0f * ((static_cast<float>(py) + 0.5f) / static_cast<float>(gh)) - 1.0f;
-            const float cx = 2.0f * ((static_cast<float>(px) + 0.5f) / static_cast<float>(gw)) - 1.0f;
-            float* cr = c.data() + static_cast<size_t>(py * gw + px) * 64;
-            float* sr = s.data() + static_cast<size_t>(py * gw + px) * 64;
-            for (int k = 0; k < 16; ++k) {
-                const float ay = two_pi * cy * inv_freq[k];
-                const float ax = two_pi * cx * inv_freq[k];
-                cr[k] = cr[32 + k] = cosf(ay);
-                sr[k] = sr[32 + k] = sinf(ay);
-                cr[16 + k] = cr[48 + k] = cosf(ax);
-                sr[16 + k] = sr[48 + k] = sinf(ax);
-            }
+    for (int a = 0; a < gh + gw; ++a) {
+        const int pos = a < gh ? a : a - gh, n = a < gh ? gh : gw;
+        const float coord = 2.0f * ((static_cast<float>(pos) + 0.5f) / static_cast<float>(n)) - 1.0f;
+        float* row = tab.data() + static_cast<size_t>(a) * kRopeRowFloats;
+        for (int k = 0; k < 16; ++k) {
+            const float ang = two_pi * coord * inv_freq[k];
+            row[k] = cosf(ang);
+            row[16 + k] = sinf(ang);
         }
+    }
     RopeTable r;
-    CRE_CUDA_OK(cudaMalloc(&r.cos, c.size() * 4));
-    CRE_CUDA_OK(cudaMalloc(&r.sin, s.size() * 4));
-    CRE_CUDA_OK(cudaMemcpy(r.cos, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
-    CRE_CUDA_OK(cudaMemcpy(r.sin, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMalloc(&r.axis, tab.size() * 4));
+    CRE_CUDA_OK(cudaMemcpy(r.axis, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     ctx->rope_tables[key] = r;
     *t = r;
     return 0;
@@ -313,10 +307,7 @@ int32_t cre_destroy(cre_ctx* ctx) {
         cudaFree(kv.second.cnt);
         cudaFree(kv.second.w);
     }
-    for (auto& kv : ctx->rope_tables) {
-        cudaFree(kv.second.cos);
-        cudaFree(kv.second.sin);
-    }
+    for (auto& kv : ctx->rope_tables) cudaFree(kv.second.axis);
     delete ctx;
     return 0;
 }
@@ -405,8 +396,9 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             p.bias = ctx->w<float>(l, CRE_B_QKV);
             p.out_bf16 = ws.qkv;
             p.ldo = 3 * D;
-            p.rope_cos = rope.cos;
-            p.rope_sin = rope.sin;
+            p.rope_axis = rope.axis;
+            p.grid_h = grid_h;
+            p.grid_w = grid_w;
             p.tokens_per_frame = T;
             p.prefix_tokens = prefix;
             p.hidden = D;

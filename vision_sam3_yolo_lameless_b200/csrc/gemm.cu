@@ -75,7 +75,7 @@ static int make_tmap_out(CUtensorMap* out, int epi, const GemmParams& p) {
     return 0;
 }
 
-template <int EPI, int CG, int STAGES = default_stages(CG)>
+template <int EPI, int CG, int STAGES = default_stages_epi(EPI, CG)>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                       cudaStream_t stream) {
     using Cfg = GemmCfg<EPI, CG, STAGES>;

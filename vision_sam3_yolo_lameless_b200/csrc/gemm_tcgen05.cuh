@@ -47,8 +47,8 @@ struct GemmParams {
     __nv_bfloat16* out_bf16;
     int ldo;
     // EPI_QKV
-    const float* rope_cos;  // [patches, 64] fp32, HF layout (angle j == angle j+32)
-    const float* rope_sin;
+    const float* rope_axis;  // [(grid_h + grid_w), 36] fp32: per-axis {cos[16], sin[16]} rows (y positions, then x positions)
+    int grid_h, grid_w;
     int tokens_per_frame, prefix_tokens, hidden;
     float q_scale;
     // EPI_PATCH
@@ -76,6 +76,10 @@ constexpr bool epi_tma_store(int epi) {
 }
 constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
+constexpr int kRopeRowFloats = 36;
+constexpr int kRopeTableBytes = 12 * 1024;   // up to 85 axis rows (grid_h + grid_w), e.g. 37 + 37 at 592 x 592
+// the QKV kernel trades one pipeline stage for the rotary table in shared memory
+constexpr int default_stages_epi(int epi, int cg) { return default_stages(cg) - (epi == EPI_QKV ? 1 : 0); }
 
 template <int EPI, int CG, int STAGES>
 struct GemmCfg {
@@ -84,7 +88,9 @@ struct GemmCfg {
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
     static constexpr int kEpiBytes = epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
-    static constexpr int kBarOff = kEpiOff + kEpiBytes;
+    static constexpr int kTableOff = kEpiOff + kEpiBytes;
+    static constexpr int kTableBytes = EPI == EPI_QKV ? kRopeTableBytes : 0;
+    static constexpr int kBarOff = kTableOff + kTableBytes;
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;       // barriers + tmem ptr + align slack
 };
 
@@ -194,6 +200,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         fence_barrier_init();
     } else if (warp == 2) {
         tmem_alloc<CG>(tmem_slot, 512);
+    }
+    if constexpr (EPI == EPI_QKV) {
+        // rotary per-axis table -> shared memory (read by every epilogue thread for every q / k chunk)
+        float* tab = reinterpret_cast<float*>(smem_raw + (smem_base + Cfg::kTableOff - smem_u32(smem_raw)));
+        const int nfl = (p.grid_h + p.grid_w) * kRopeRowFloats;
+        for (int i = threadIdx.x; i < nfl; i += kGemmThreads) tab[i] = __ldg(p.rope_axis + i);
     }
     tc_fence_before();
     if constexpr (CG > 1) cluster_sync_all(); else __syncthreads();
@@ -348,9 +360,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // one 64-column chunk = one head of q, k or v
                 const int tok = row_ok ? row % p.tokens_per_frame : 0;
                 const bool patch_row = tok >= p.prefix_tokens;
-                const size_t rope_row = static_cast<size_t>(patch_row ? tok - p.prefix_tokens : 0) * 64;
-                const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + rope_row);
-                const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + rope_row);
+                const int pidx = patch_row ? tok - p.prefix_tokens : 0;
+                const int py = pidx / p.grid_w, px = pidx - py * p.grid_w;
+                const float* tab = reinterpret_cast<const float*>(smem_raw + (smem_base + Cfg::kTableOff - smem_u32(smem_raw)));
+                const float4* ty = reinterpret_cast<const float4*>(tab + py * kRopeRowFloats);                 // cos[16] | sin[16]
+                const float4* tx = reinterpret_cast<const float4*>(tab + (p.grid_h + px) * kRopeRowFloats);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -377,10 +391,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         x2[4 * j4 + 3] = __uint_as_float(b[4 * j4 + 3]) + b2.w;
                     }
                     if (rot) {
+                        // element j of each half pairs with angle j: j < 16 -> y-angle j, j >= 16 -> x-angle j - 16
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 c4 = __ldg(cs + j4);
-                            const float4 s4 = __ldg(sn + j4);
+                            const float4 c4 = j4 < 4 ? ty[j4] : tx[j4 - 4];
+                            const float4 s4 = j4 < 4 ? ty[4 + j4] : tx[j4];
                             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
                             const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
