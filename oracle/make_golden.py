@@ -11,6 +11,7 @@ Fixtures (inputs are regenerated from seeds by the tests, only reference OUTPUTS
   clip_48x64_15fps.avi + video.json   extract_video_embeddings (main.py:117-163): sampled indices, times, embeddings
   process_video.json   process_video (main.py:188-282) results JSON + published NATS payloads, 3 videos, fake Qdrant/NATS
   reid_scenario.json   CowReIDMatcher.match_or_create transcript (matcher.py:151-201) over a scripted query sequence
+  knn_graph.json       GraphBuilder.compute_knn_edges (gnn-pipeline/app/main.py:55-100) edge list on 42 clustered nodes
 """
 from __future__ import annotations
 
@@ -62,6 +63,13 @@ def reid_queries(dim=768, seed=41):
            ("again_a", mix(base[0], 0.90)),          # high after two momentum updates
            ("again_b", mix(base[1], 0.97))]
     return seq
+
+
+def knn_embeddings(seed=61):
+    """42 nodes in 6 well-separated clusters (neighbour sets are unambiguous under bf16 gallery rounding)."""
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((6, 768))
+    return np.concatenate([c + 0.35 * rng.standard_normal((7, 768)) for c in centers])
 
 
 def write_clip(path: Path, n=45, h=48, w=64, fps=15, seed=51):
@@ -162,6 +170,14 @@ def main():
                "confidence_probe": {str(s): matcher._score_to_confidence(s) for s in
                                     (0.0, 0.6499, 0.65, 0.7499, 0.75, 0.8499, 0.85, 1.0)},
                "statistics": matcher.get_statistics()}, open(GOLDEN / "reid_scenario.json", "w"), indent=1)
+    # ---- kNN similarity graph (gnn-pipeline GraphBuilder.compute_knn_edges, extracted by AST and run unmodified) ----
+    from oracle import knn_ref
+    gb = knn_ref.reference_graph_builder()
+    emb = knn_embeddings()
+    ei, ew = gb(k_neighbors=5).compute_knn_edges(emb)
+    ei2, ew2 = gb(k_neighbors=5).compute_knn_edges(emb[:4])       # N <= k: k shrinks to N - 1
+    json.dump({"seed": 61, "edge_index": ei.tolist(), "edge_weights": ew.tolist(), "small_edge_index": ei2.tolist(),
+               "small_edge_weights": ew2.tolist()}, open(GOLDEN / "knn_graph.json", "w"))
     for f in sorted(GOLDEN.iterdir()):
         print(f"{f.name}: {f.stat().st_size} bytes")
 

@@ -165,3 +165,17 @@ def test_full_size_properties(engine_b):
     whole = eng.embed_frames(big)
     single = torch.cat([eng.embed_frames(big[j:j + 1]) for j in range(6)])
     assert torch.equal(whole, single)
+
+
+def test_knn_graph_vs_reference_golden(engine_b, golden):
+    """SURVEY 8(f) #1: the GNN service's kNN graph (gnn main.py:55-100) from one K4 launch (Q = N, self dropped)."""
+    from oracle.make_golden import knn_embeddings
+    from vision_sam3_yolo_lameless_b200.knn_graph import GraphBuilder
+    eng, _ = engine_b
+    want = json.load(open(golden / "knn_graph.json"))
+    from conftest import assert_knn_equivalent
+    emb = knn_embeddings()
+    ei, ew = GraphBuilder(eng, k_neighbors=5).compute_knn_edges(emb)
+    assert_knn_equivalent(ei, ew, want["edge_index"], want["edge_weights"], emb, 5)
+    ei2, ew2 = GraphBuilder(eng).compute_knn_edges(emb[:4])
+    assert_knn_equivalent(ei2, ew2, want["small_edge_index"], want["small_edge_weights"], emb[:4], 3)

@@ -207,3 +207,22 @@ def test_tracking_handler_flow(stub, tmp_path, golden):
     asyncio.run(h.process_dinov3_results({"results_path": "x"}))            # no video_id -> ignored
     asyncio.run(h.process_dinov3_results({"video_id": "c", "results_path": str(tmp_path / "missing.json")}))
     assert "c" not in h.video_embeddings
+
+
+def test_knn_graph_builder_matches_reference(stub, golden):
+    from oracle.make_golden import knn_embeddings
+    from vision_sam3_yolo_lameless_b200.knn_graph import GraphBuilder
+    want = json.load(open(golden / "knn_graph.json"))
+    gb = GraphBuilder(stub, k_neighbors=5)
+    from conftest import assert_knn_equivalent
+    emb = knn_embeddings()
+    ei, ew = gb.compute_knn_edges(emb)
+    assert ei.shape == (2, 210)
+    assert_knn_equivalent(ei, ew, want["edge_index"], want["edge_weights"], emb, 5)          # bf16 gallery rows
+    ei2, ew2 = gb.compute_knn_edges(emb[:4])
+    assert_knn_equivalent(ei2, ew2, want["small_edge_index"], want["small_edge_weights"], emb[:4], 3)
+    assert gb.compute_knn_edges(np.zeros((1, 768)))[0].shape == (2, 0)
+    with pytest.raises(ValueError):
+        gb.compute_knn_edges(knn_embeddings(), k=8)
+    with pytest.raises(RuntimeError):
+        GraphBuilder(None)

@@ -115,3 +115,15 @@ def test_topk_rule_ties_and_merge():
     assert mi.tolist() == [[1, 2, 4]]
     cm = reid_ref.clip_mean(np.arange(12, dtype=np.float32).reshape(6, 2), np.array([0, 2, 6]))
     np.testing.assert_allclose(cm, [[1, 2], [7, 8]])
+
+
+def test_knn_graph_restatement_matches_reference(golden):
+    from oracle import knn_ref
+    from oracle.make_golden import knn_embeddings
+    want = json.load(open(golden / "knn_graph.json"))
+    emb = knn_embeddings()
+    ei, ew = knn_ref.compute_knn_edges(emb, 5)
+    assert ei.tolist() == want["edge_index"]
+    np.testing.assert_allclose(ew, want["edge_weights"], atol=1e-12)
+    ei2, ew2 = knn_ref.compute_knn_edges(emb[:4], 5)
+    assert ei2.tolist() == want["small_edge_index"] and ei2.shape == (2, 12)

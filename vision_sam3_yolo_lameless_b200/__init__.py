@@ -9,8 +9,9 @@ from . import _lib
 from .engine import ClipEmbedEngine, VitConfig, pack_weights, set_cta_group
 from .extractor import DINOv3Pipeline, build_pipeline_from_hf
 from .gallery import GpuGallery, ScoredPoint
+from .knn_graph import GraphBuilder
 from .reid import CowIdentity, CowReIDMatcher, ReIDMatch, TrackingReIDHandler
 
 __all__ = ["_lib", "ClipEmbedEngine", "VitConfig", "pack_weights", "set_cta_group", "DINOv3Pipeline",
            "build_pipeline_from_hf", "GpuGallery", "ScoredPoint", "CowIdentity", "CowReIDMatcher", "ReIDMatch",
-           "TrackingReIDHandler"]
+           "TrackingReIDHandler", "GraphBuilder"]

@@ -125,6 +125,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if CRE_BOUNDED_WAIT
     // try_wait suspends in hardware for a bounded time; ~2^26 polls is seconds of wall clock,
     // far beyond any legitimate wait in these kernels.
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 26); ++it)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
