@@ -1,5 +1,6 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench, ncu launch list and a full capture of the first layer's kernels.
+# One gpurun call: GPU parity tests, bench, ncu launch list and a full capture of the first layer's kernels
+# (batch 1130 frames = the bench's launch size, so per-launch DRAM traffic is comparable with bench.py's roofline).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import os, torch; print('cpus', os.cpu_count(), 'threads', torch.get_num_threads())" >> gpurun_out/gpu.txt 2>&1
@@ -8,10 +9,10 @@ timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
 tail -15 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 3 --warmup 3 --breakdown > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -30 gpurun_out/bench.err; cat gpurun_out/bench.json
-SMALL="python bench.py --clips 2 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --gallery-rows 100000"
+SMALL="python bench.py --clips 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --gallery-rows 100000"
 timeout 300 $SMALL > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 timeout 300 $SMALL > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention|preprocess|layernorm|final_norm" -s 10 -c 10 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention|preprocess|layernorm|final_norm" -s 0 -c 11 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"

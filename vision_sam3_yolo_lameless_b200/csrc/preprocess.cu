@@ -44,7 +44,7 @@ __device__ __forceinline__ float byte_as_unit_float(uint32_t word, uint32_t sele
     return __uint_as_float(__byte_perm(word, 0x3F800000u, selector));
 }
 
-__global__ void __launch_bounds__(kPreThreads, 3) preprocess_kernel(const PreParams p) {
+__global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PreParams p) {
     extern __shared__ __align__(16) float vbuf[];  // [16][sstride]
     const int band = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
     const int px0 = band * kBandPatches;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kPreThreads, 3) preprocess_kernel(const PrePar
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc2[i] = pack2(0.0f, 0.0f);
             float wsum = 0.0f;
-#pragma unroll 3
+#pragma unroll 6
             for (int k = 0; k < cnt; ++k) {
                 const float wk = __ldg(wy + k);
                 const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(k) * p.row_pitch));
