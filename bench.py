@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--gallery-rows", type=int, default=100_000)
     ap.add_argument("--batch-frames", type=int, default=1130, help="frames per ViT launch sequence")
     ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
+    ap.add_argument("--ln-fold", type=int, default=-1, help="-1 = library default; 0 = separate LayerNorm launches")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -213,6 +214,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if args.cta_group:
         set_cta_group(args.cta_group)
+    if args.ln_fold >= 0:
+        _lib.set_tuning("ln_fold", args.ln_fold)
 
     model = common.hf_model()
     cfg = VitConfig.from_hf(model.config)

@@ -137,7 +137,9 @@ enum cre_gemm_epilogue {
     CRE_EPI_F32 = 1,   /* out_f32  = acc + bias                         */
     CRE_EPI_GELU = 3,  /* out_bf16 = gelu_erf(acc + bias)               */
     CRE_EPI_RESID = 4, /* out_f32 += scale * (acc + bias)   (in place)  */
-    CRE_EPI_NONE = 7   /* accumulators dropped: main-loop timing only   */
+    CRE_EPI_NONE = 7,  /* accumulators dropped: main-loop timing only   */
+    CRE_EPI_RESID_LN = 8, /* cre_gemm_ln only: x += scale * (acc + bias), bf16(x - pivot), LayerNorm statistics */
+    CRE_EPI_RESID_LN3 = 9 /* same results; one x tile in flight per warp, one pipeline stage more (long K) */
 };
 /* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0; n % 64 == 0 for the bf16-out
  * epilogues, n % 32 == 0 for the fp32-out ones; out_dev 16-byte aligned (written by TMA).
@@ -145,6 +147,22 @@ enum cre_gemm_epilogue {
 int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k,
                       int32_t epilogue, const float* bias_dev, const float* scale_dev, void* out_dev,
                       int32_t cta_group, void* stream);
+/* ---- LayerNorm folded into the GEMMs (what cre_vit_forward runs inside the blocks; HF:modeling_dinov3_vit.py:411-448
+ * norm1 -> attention, norm2 -> mlp).  LN(x) W^T + b = rstd * ((x - pivot) W'^T - (mean - pivot) c1) + c2 with
+ * W' = W * gamma, c1 = row sums of W', c2 = b + W beta.  A statistics row is 2 * (dim / 128) + 4 floats:
+ * [pivot, -, -, -, (mean_i, M2_i) of every 128-column slot]; dim = 768 | 1024.
+ *   cre_row_stats:       x f32 [rows, dim] -> out_xb bf16 [rows, dim] = x - mean, out_stats (pivot = mean).
+ *   cre_fold_ln_weights: w bf16 [n, k], gamma/beta f32 [k], bias f32 [n] or NULL -> out_w bf16 [n, k], out_c1/out_c2 f32 [n].
+ *   cre_gemm_ln:         epilogue CRE_EPI_BF16 | CRE_EPI_GELU: out bf16 [m, n] = (gelu)(LN-folded A B^T), A = the centred bf16
+ *                        rows, bias = c2, stats_in = their statistics rows (ln_dim = k);
+ *                        epilogue CRE_EPI_RESID_LN (n == ln_dim, n % 256 == 0): out f32 [m, n] (in place) += scale * (A B^T + bias),
+ *                        out_xb bf16 [m, n] = out - pivot (pivot = the row mean recorded in stats_in), stats_out = new rows. */
+int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_xb_dev, float* out_stats_dev, void* stream);
+int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
+                            int32_t k, void* out_w_dev, float* out_c1_dev, float* out_c2_dev, void* stream);
+int32_t cre_gemm_ln(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k, int32_t epilogue,
+                    const float* bias_dev, const float* c1_dev, const float* scale_dev, const float* stats_in_dev, int32_t ln_dim,
+                    float ln_eps, void* out_dev, void* out_xb_dev, float* stats_out_dev, int32_t cta_group, void* stream);
 /* out bf16 [rows, dim] = LayerNorm(x f32 [rows, dim]) * gamma + beta */
 int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const float* beta_dev, int32_t rows,
                            int32_t dim, float eps, void* out_dev, void* stream);
@@ -164,7 +182,7 @@ enum cre_kernel_id {
     CRE_K_PREPROCESS = 0, CRE_K_FILL_PREFIX = 1, CRE_K_GEMM_PATCH = 2, CRE_K_LAYERNORM = 3, CRE_K_GEMM_QKV = 4,
     CRE_K_ATTENTION = 5, CRE_K_GEMM_RESID = 6, CRE_K_GEMM_GELU = 7, CRE_K_FINAL_NORM_MEAN = 8, CRE_K_POOL_CLIPS = 9,
     CRE_K_SPLIT_HI_LO = 10, CRE_K_FILL_TOPK = 11, CRE_K_GEMM_TOPK = 12, CRE_K_MERGE_TOPK = 13, CRE_K_GEMM_PLAIN = 14,
-    CRE_K_GALLERY_UPDATE = 15, CRE_KERNEL_IDS = 16
+    CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_KERNEL_IDS = 18
 };
 int64_t cre_kernel_launches(void);
 int32_t cre_profile_start(int32_t max_launches);
@@ -175,7 +193,8 @@ int32_t cre_profile_stop(int32_t* ids_out, float* ms_out, double* work_out, int3
 int32_t cre_set_cta_group(int32_t cta_group);
 /* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..6:
  * TMA pipeline depth of the cre_gemm_bf16 building block), "attention_fast" (1 = persistent TMEM-resident kernel for
- * T <= 256, default; 0 = general kernel), "gemm_debug".  Unknown keys return -1. */
+ * T <= 256, default; 0 = general kernel), "ln_fold" (1 = LayerNorm folded into the GEMMs, default; 0 = separate LayerNorm
+ * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use CRE_EPI_RESID_LN3), "gemm_debug".  Unknown keys return -1. */
 int32_t cre_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus

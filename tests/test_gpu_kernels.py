@@ -58,6 +58,85 @@ def test_layernorm(engine_small, rows, dim):
     assert rel_err(engine_small.layernorm(x, g, b), ref) < 5e-3                                 # bf16 output
 
 
+def _stats_combine(stats, dim):
+    """numpy restatement of the consumer-side combination of a statistics row -> (pivot, mean, biased variance)."""
+    st = stats.double().cpu()
+    s = dim // 128
+    means, m2s = st[:, 4:4 + 2 * s:2], st[:, 5:5 + 2 * s:2]
+    mean = means.mean(dim=1)
+    m2 = m2s.sum(dim=1) + 128.0 * ((means - mean[:, None]) ** 2).sum(dim=1)
+    return st[:, 0], mean, m2 / dim
+
+
+@pytest.mark.parametrize("rows,dim", [(1003, 768), (77, 1024), (1, 768)])
+def test_row_stats(engine_small, rows, dim):
+    dev = engine_small.device
+    x = torch.randn(rows, dim, device=dev) * 3 + torch.randn(rows, 1, device=dev) * 5
+    xb, stats = engine_small.row_stats(x)
+    pivot, mean, var = _stats_combine(stats, dim)
+    xd = x.double().cpu()
+    assert (pivot - xd.mean(dim=1)).abs().max() < 1e-5 and (mean - xd.mean(dim=1)).abs().max() < 1e-5
+    assert ((var - xd.var(dim=1, unbiased=False)).abs() / xd.var(dim=1, unbiased=False)).max() < 1e-5
+    assert rel_err(xb, x - x.mean(dim=1, keepdim=True)) < 5e-3                                  # bf16 of the centred row
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,dim,epi", [(1000, 2304, 768, "bf16"), (515, 3072, 768, "gelu"), (300, 4096, 1024, "gelu"), (1, 64, 768, "bf16")])
+def test_gemm_layernorm_folded_consumer(engine_small, cg, m, n, dim, epi):
+    """LN(x) W^T + b through row_stats + fold_ln_weights + cre_gemm_ln == fp32 layer_norm + matmul, at the accuracy of the
+    unfolded bf16 path (bf16 LN output x bf16 weights), including rows with a large mean and outlier channels."""
+    eng, dev = engine_small, engine_small.device
+    g = torch.Generator(device=dev).manual_seed(m + n)
+    x = torch.randn(m, dim, device=dev, generator=g) * 2 + torch.randn(m, 1, device=dev, generator=g) * 4
+    x[:, 5] += 60.0                                                                             # a massive-activation channel
+    w = (torch.randn(n, dim, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    gamma, beta = torch.rand(dim, device=dev, generator=g) + 0.5, torch.randn(dim, device=dev, generator=g) * 0.3
+    bias = torch.randn(n, device=dev, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (dim,), gamma, beta, 1e-5) @ w.float().t() + bias
+    wf, c1, c2 = eng.fold_ln_weights(w, gamma, beta, bias)
+    assert rel_err(wf, w.float() * gamma) < 5e-3 and rel_err(c2, bias + w.float() @ beta) < 1e-5
+    assert rel_err(c1, wf.float().sum(dim=1)) < 1e-5
+    xb, stats = eng.row_stats(x)
+    e = _lib.EPI_BF16 if epi == "bf16" else _lib.EPI_GELU
+    out = eng.gemm_ln(xb, wf, e, stats, dim, bias=c2, c1=c1, cta_group=cg)
+    want = ref if epi == "bf16" else torch.nn.functional.gelu(ref)
+    unfolded = eng.gemm(eng.layernorm(x, gamma, beta), w, e, bias=bias, cta_group=cg)
+    assert rel_err(out, want) < max(8e-3, 2.0 * rel_err(unfolded, want))
+
+
+@pytest.mark.parametrize("epi", [_lib.EPI_RESID_LN, _lib.EPI_RESID_LN3])
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(1000, 768, 768), (515, 768, 3072), (300, 1024, 1024), (1, 768, 64), (40021, 768, 768)])
+def test_gemm_resid_layernorm_producer(engine_small, cg, epi, m, n, k):
+    """x += scale * (a W^T + b) with the LayerNorm statistics of the NEW x and bf16(x - pivot), pivot = the row mean recorded
+    in the incoming statistics; then the chain into a folded consumer reproduces LN(x_new) W2^T."""
+    eng, dev = engine_small, engine_small.device
+    g = torch.Generator(device=dev).manual_seed(m * 3 + k)
+    x0 = torch.randn(m, n, device=dev, generator=g) * 2 + torch.randn(m, 1, device=dev, generator=g) * 3
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(n, k, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    bias, scale = torch.randn(n, device=dev, generator=g), torch.rand(n, device=dev, generator=g) + 0.5
+    _, stats0 = eng.row_stats(x0)
+    ref = x0 + scale * (a.float() @ w.float().t() + bias)
+    x, xb, stats1 = eng.gemm_ln(a, w, epi, stats0, n, bias=bias, scale=scale, out=x0.clone(), cta_group=cg)
+    assert rel_err(x, ref) < 2e-5                                                               # fp32 accumulate + fp32 update
+    pivot, mean, var = _stats_combine(stats1, n)
+    rd = ref.double().cpu()
+    assert (pivot - x0.double().cpu().mean(dim=1)).abs().max() < 1e-4
+    assert (mean - rd.mean(dim=1)).abs().max() < 1e-4
+    assert ((var - rd.var(dim=1, unbiased=False)).abs() / rd.var(dim=1, unbiased=False)).max() < 1e-4
+    assert rel_err(xb, ref - x0.mean(dim=1, keepdim=True)) < 5e-3                               # bf16 of x - pivot
+    # chain: the folded consumer on (xb, stats1) == LN(x_new) W2^T + b2
+    n2 = 256
+    w2 = (torch.randn(n2, n, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    gamma, beta = torch.rand(n, device=dev, generator=g) + 0.5, torch.randn(n, device=dev, generator=g) * 0.3
+    b2 = torch.randn(n2, device=dev, generator=g)
+    wf, c1, c2 = eng.fold_ln_weights(w2, gamma, beta, b2)
+    out = eng.gemm_ln(xb, wf, _lib.EPI_BF16, stats1, n, bias=c2, c1=c1, cta_group=cg)
+    want = torch.nn.functional.layer_norm(ref, (n,), gamma, beta, 1e-5) @ w2.float().t() + b2
+    assert rel_err(out, want) < 8e-3
+
+
 @pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12)])
 def test_attention(engine_small, t, n, heads):
     dev = engine_small.device

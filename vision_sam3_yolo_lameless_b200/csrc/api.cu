@@ -111,8 +111,12 @@ struct Workspace {
     __nv_bfloat16* h;    // [M, D] LayerNorm output / attention output
     __nv_bfloat16* qkv;  // [M, 3D] q (pre-scaled, rotated) | k (rotated) | v
     __nv_bfloat16* mlp;  // [M, F]
+    __nv_bfloat16* xb;   // [M, D] bf16(x - row pivot): A operand of the LayerNorm-folded GEMMs
+    float* stats[2];     // [M, ln_stride] LayerNorm statistics rows (ping-pong between the two norms of a block)
     int64_t total;
 };
+inline int ln_slots(const cre_model_cfg* c) { return c->hidden / 128; }
+inline int ln_stride(const cre_model_cfg* c) { return 2 * ln_slots(c) + 4; }
 Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) {
     const int64_t T = static_cast<int64_t>(gh) * gw + 1 + c->registers;
     const int64_t M = frames * T, D = c->hidden, F = c->mlp;
@@ -124,6 +128,9 @@ Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) 
     w.h = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
     w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * 2));
     w.mlp = reinterpret_cast<__nv_bfloat16*>(take(M * F * 2));
+    w.xb = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+    w.stats[0] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
+    w.stats[1] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
     w.total = off;
     return w;
 }
@@ -165,11 +172,19 @@ void build_resize_table(int in, int out, std::vector<int32_t>& lo, std::vector<i
 
 }  // namespace
 
+// Linear weights with the preceding LayerNorm folded in (elementwise.cu fold_ln_weights_kernel), built at cre_create
+struct FoldedLinear {
+    __nv_bfloat16* w = nullptr;   // [out, in] = bf16(W * gamma)
+    float* c1 = nullptr;          // [out] row sums of w
+    float* c2 = nullptr;          // [out] bias + W beta
+};
 struct cre_ctx {
     cre_model_cfg cfg;
     const uint8_t* weights;
     int device;
     int num_sms;
+    uint8_t* fold_buf = nullptr;
+    std::vector<FoldedLinear> fold_qkv, fold_up;
     std::map<std::pair<int, int>, DevTable> resize_tables;
     std::map<std::pair<int, int>, RopeTable> rope_tables;
 
@@ -252,6 +267,40 @@ GemmParams base_params(int M, int N, int K) {
 }
 
 int g_default_cg = 2;  // CTA pairs: less smem traffic per FLOP, measured 3-5 % faster in the full step
+int g_resid_ln_deep = 2;   // bit 0: attention-out projection, bit 1: MLP down projection use EPI_RESID_LN3 (1 x tile, 5 stages)
+int g_ln_fold = 1;     // 1: LayerNorm folded into the GEMMs (no LayerNorm kernel in the blocks); 0: separate LayerNorm launches
+
+// LN1 -> q/k/v and LN2 -> up projections of every layer, folded once
+int build_folded_weights(cre_ctx* c) {
+    const cre_model_cfg& m = c->cfg;
+    const int64_t D = m.hidden, F = m.mlp;
+    auto bytes_of = [&](int64_t out) { return align_up(out * D * 2, kAlign) + 2 * align_up(out * 4, kAlign); };
+    const int64_t per_layer = bytes_of(3 * D) + bytes_of(F);
+    CRE_CUDA_OK(cudaDeviceSynchronize());   // the caller's upload of the packed blob (any stream) is complete
+    CRE_CUDA_OK(cudaMalloc(&c->fold_buf, per_layer * m.layers));
+    c->fold_qkv.resize(m.layers);
+    c->fold_up.resize(m.layers);
+    uint8_t* p = c->fold_buf;
+    auto take = [&](FoldedLinear& f, int64_t out) {
+        f.w = reinterpret_cast<__nv_bfloat16*>(p); p += align_up(out * D * 2, kAlign);
+        f.c1 = reinterpret_cast<float*>(p); p += align_up(out * 4, kAlign);
+        f.c2 = reinterpret_cast<float*>(p); p += align_up(out * 4, kAlign);
+    };
+    for (int l = 0; l < m.layers; ++l) {
+        take(c->fold_qkv[l], 3 * D);
+        take(c->fold_up[l], F);
+        int rc = launch_fold_ln_weights(c->w<__nv_bfloat16>(l, CRE_W_QKV), c->w<float>(l, CRE_LN1_G), c->w<float>(l, CRE_LN1_B),
+                                        c->w<float>(l, CRE_B_QKV), static_cast<int>(3 * D), static_cast<int>(D), c->fold_qkv[l].w,
+                                        c->fold_qkv[l].c1, c->fold_qkv[l].c2, nullptr);
+        if (rc) return rc;
+        rc = launch_fold_ln_weights(c->w<__nv_bfloat16>(l, CRE_W_UP), c->w<float>(l, CRE_LN2_G), c->w<float>(l, CRE_LN2_B),
+                                    c->w<float>(l, CRE_B_UP), static_cast<int>(F), static_cast<int>(D), c->fold_up[l].w,
+                                    c->fold_up[l].c1, c->fold_up[l].c2, nullptr);
+        if (rc) return rc;
+    }
+    CRE_CUDA_OK(cudaStreamSynchronize(nullptr));
+    return 0;
+}
 
 }  // namespace
 
@@ -296,6 +345,12 @@ int32_t cre_create(const cre_model_cfg* cfg, const void* packed_weights_dev, int
     c->weights = static_cast<const uint8_t*>(packed_weights_dev);
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    const int rc = build_folded_weights(c);   // the packed blob must already hold the weights (it does: see engine.py)
+    if (rc) {
+        cudaFree(c->fold_buf);
+        delete c;
+        return rc;
+    }
     *out = c;
     return 0;
 }
@@ -308,6 +363,7 @@ int32_t cre_destroy(cre_ctx* ctx) {
         cudaFree(kv.second.w);
     }
     for (auto& kv : ctx->rope_tables) cudaFree(kv.second.axis);
+    cudaFree(ctx->fold_buf);
     delete ctx;
     return 0;
 }
@@ -388,12 +444,20 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
         rc = launch_gemm(EPI_PATCH, cg, patches_dev, PK, ctx->w<void>(-1, CRE_W_PATCH), PK, p, ctx->num_sms, stream);
         if (rc) return rc;
     }
-    for (int l = 0; l < c.layers; ++l) {
-        rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN1_G), ctx->w<float>(l, CRE_LN1_B), M, D, c.ln_eps, ws.h, stream);
+    const bool fold = g_ln_fold != 0;
+    const int S = ln_slots(&c), SS = ln_stride(&c);
+    if (fold) {   // seed of the folded chain: statistics + centred bf16 copy of the embedded tokens
+        rc = launch_row_stats(ws.x, M, D, SS, ws.xb, ws.stats[0], stream);
         if (rc) return rc;
+    }
+    for (int l = 0; l < c.layers; ++l) {
+        if (!fold) {
+            rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN1_G), ctx->w<float>(l, CRE_LN1_B), M, D, c.ln_eps, ws.h, stream);
+            if (rc) return rc;
+        }
         {
             GemmParams p = base_params(M, 3 * D, D);
-            p.bias = ctx->w<float>(l, CRE_B_QKV);
+            p.bias = fold ? ctx->fold_qkv[l].c2 : ctx->w<float>(l, CRE_B_QKV);
             p.out_bf16 = ws.qkv;
             p.ldo = 3 * D;
             p.rope_axis = rope.axis;
@@ -403,7 +467,15 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             p.prefix_tokens = prefix;
             p.hidden = D;
             p.q_scale = 0.125f;  // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284)
-            rc = launch_gemm(EPI_QKV, cg, ws.h, D, ctx->w<void>(l, CRE_W_QKV), D, p, ctx->num_sms, stream);
+            if (fold) {
+                p.c1 = ctx->fold_qkv[l].c1;
+                p.ln_stats_in = ws.stats[0];
+                p.ln_slots = S;
+                p.ln_stride = SS;
+                p.ln_eps = c.ln_eps;
+            }
+            rc = launch_gemm(EPI_QKV, cg, fold ? ws.xb : ws.h, D, fold ? static_cast<const void*>(ctx->fold_qkv[l].w) : ctx->w<void>(l, CRE_W_QKV),
+                             D, p, ctx->num_sms, stream);
             if (rc) return rc;
         }
         {
@@ -419,32 +491,61 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             rc = launch_attention(a, stream);
             if (rc) return rc;
         }
-        {
+        {   // attention output projection: x += ls1 * (h Wo^T + b); folded: also bf16(x - pivot) and the LN2 statistics
             GemmParams p = base_params(M, D, D);
             p.bias = ctx->w<float>(l, CRE_B_O);
             p.scale = ctx->w<float>(l, CRE_LS1);
             p.out_f32 = ws.x;
             p.ldo = D;
-            rc = launch_gemm(EPI_RESID, cg, ws.h, D, ctx->w<void>(l, CRE_W_O), D, p, ctx->num_sms, stream);
+            if (fold) {
+                p.out_bf16 = ws.xb;
+                p.ldo2 = D;
+                p.ln_stats_in = ws.stats[0];
+                p.ln_stats_out = ws.stats[1];
+                p.ln_slots = S;
+                p.ln_stride = SS;
+            }
+            rc = launch_gemm(fold ? ((g_resid_ln_deep & 1) ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.h, D, ctx->w<void>(l, CRE_W_O), D, p,
+                             ctx->num_sms, stream);
             if (rc) return rc;
         }
-        rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN2_G), ctx->w<float>(l, CRE_LN2_B), M, D, c.ln_eps, ws.h, stream);
-        if (rc) return rc;
+        if (!fold) {
+            rc = launch_layernorm_bf16(ws.x, ctx->w<float>(l, CRE_LN2_G), ctx->w<float>(l, CRE_LN2_B), M, D, c.ln_eps, ws.h, stream);
+            if (rc) return rc;
+        }
         {
             GemmParams p = base_params(M, F, D);
-            p.bias = ctx->w<float>(l, CRE_B_UP);
+            p.bias = fold ? ctx->fold_up[l].c2 : ctx->w<float>(l, CRE_B_UP);
             p.out_bf16 = ws.mlp;
             p.ldo = F;
-            rc = launch_gemm(EPI_GELU, cg, ws.h, D, ctx->w<void>(l, CRE_W_UP), D, p, ctx->num_sms, stream);
+            if (fold) {
+                p.c1 = ctx->fold_up[l].c1;
+                p.ln_stats_in = ws.stats[1];
+                p.ln_slots = S;
+                p.ln_stride = SS;
+                p.ln_eps = c.ln_eps;
+            }
+            rc = launch_gemm(EPI_GELU, cg, fold ? ws.xb : ws.h, D, fold ? static_cast<const void*>(ctx->fold_up[l].w) : ctx->w<void>(l, CRE_W_UP),
+                             D, p, ctx->num_sms, stream);
             if (rc) return rc;
         }
-        {
+        {   // MLP down projection; the last block feeds the final norm (fp32 x only)
+            const bool ln_out = fold && l + 1 < c.layers;
             GemmParams p = base_params(M, D, F);
             p.bias = ctx->w<float>(l, CRE_B_DOWN);
             p.scale = ctx->w<float>(l, CRE_LS2);
             p.out_f32 = ws.x;
             p.ldo = D;
-            rc = launch_gemm(EPI_RESID, cg, ws.mlp, F, ctx->w<void>(l, CRE_W_DOWN), F, p, ctx->num_sms, stream);
+            if (ln_out) {
+                p.out_bf16 = ws.xb;
+                p.ldo2 = D;
+                p.ln_stats_in = ws.stats[1];
+                p.ln_stats_out = ws.stats[0];
+                p.ln_slots = S;
+                p.ln_stride = SS;
+            }
+            rc = launch_gemm(ln_out ? ((g_resid_ln_deep & 2) ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.mlp, F, ctx->w<void>(l, CRE_W_DOWN), F,
+                             p, ctx->num_sms, stream);
             if (rc) return rc;
         }
     }
@@ -544,6 +645,49 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
     return launch_gemm(epilogue, cta_group, a_dev, k, b_dev, k, p, ctx->num_sms, static_cast<cudaStream_t>(stream));
 }
 
+int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_xb_dev, float* out_stats_dev, void* stream) {
+    CRE_REQUIRE(x_dev != nullptr && out_xb_dev != nullptr && out_stats_dev != nullptr, "row_stats: NULL argument");
+    return launch_row_stats(x_dev, rows, dim, 2 * (dim / 128) + 4, static_cast<__nv_bfloat16*>(out_xb_dev), out_stats_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
+                            int32_t k, void* out_w_dev, float* out_c1_dev, float* out_c2_dev, void* stream) {
+    CRE_REQUIRE(w_dev != nullptr && gamma_dev != nullptr && beta_dev != nullptr && out_w_dev != nullptr && out_c1_dev != nullptr &&
+                    out_c2_dev != nullptr, "fold_ln_weights: NULL argument");
+    return launch_fold_ln_weights(static_cast<const __nv_bfloat16*>(w_dev), gamma_dev, beta_dev, bias_dev, n, k,
+                                  static_cast<__nv_bfloat16*>(out_w_dev), out_c1_dev, out_c2_dev, static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_gemm_ln(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k, int32_t epilogue,
+                    const float* bias_dev, const float* c1_dev, const float* scale_dev, const float* stats_in_dev, int32_t ln_dim,
+                    float ln_eps, void* out_dev, void* out_xb_dev, float* stats_out_dev, int32_t cta_group, void* stream) {
+    CRE_REQUIRE(ctx != nullptr && a_dev != nullptr && b_dev != nullptr && out_dev != nullptr && stats_in_dev != nullptr,
+                "gemm_ln: NULL argument");
+    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID_LN || epilogue == CRE_EPI_RESID_LN3,
+                "gemm_ln: epilogue %d is not exposed", epilogue);
+    CRE_REQUIRE(ln_dim > 0 && ln_dim % 128 == 0 && ln_dim / 128 <= 8, "gemm_ln: ln_dim=%d", ln_dim);
+    GemmParams p = base_params(m, n, k);
+    p.bias = bias_dev;
+    p.c1 = c1_dev;
+    p.scale = scale_dev;
+    p.ln_stats_in = stats_in_dev;
+    p.ln_stats_out = stats_out_dev;
+    p.ln_slots = ln_dim / 128;
+    p.ln_stride = 2 * p.ln_slots + 4;
+    p.ln_eps = ln_eps;
+    p.ldo = n;
+    if (epilogue == CRE_EPI_RESID_LN || epilogue == CRE_EPI_RESID_LN3) {
+        CRE_REQUIRE(out_xb_dev != nullptr && stats_out_dev != nullptr && n == ln_dim, "gemm_ln: RESID_LN needs out_xb, stats_out and n == ln_dim");
+        p.out_f32 = static_cast<float*>(out_dev);
+        p.out_bf16 = static_cast<__nv_bfloat16*>(out_xb_dev);
+        p.ldo2 = n;
+    } else {
+        p.out_bf16 = static_cast<__nv_bfloat16*>(out_dev);
+    }
+    return launch_gemm(epilogue, cta_group, a_dev, k, b_dev, k, p, ctx->num_sms, static_cast<cudaStream_t>(stream));
+}
+
 int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const float* beta_dev, int32_t rows, int32_t dim,
                            float eps, void* out_dev, void* stream) {
     CRE_REQUIRE(x_dev != nullptr && gamma_dev != nullptr && beta_dev != nullptr && out_dev != nullptr, "layernorm: NULL argument");
@@ -588,6 +732,14 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     }
     if (strcmp(key, "attention_debug") == 0) {
         set_attention_debug(value);
+        return 0;
+    }
+    if (strcmp(key, "resid_ln_deep") == 0) {
+        g_resid_ln_deep = value & 3;
+        return 0;
+    }
+    if (strcmp(key, "ln_fold") == 0) {
+        g_ln_fold = value != 0;
         return 0;
     }
     if (strcmp(key, "gemm_debug") == 0) {

@@ -68,6 +68,97 @@ int launch_layernorm_bf16(const float* x, const float* g, const float* b, int ro
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm folding.  LN(x) W^T = rstd * ((x - pivot) W'^T - (mean - pivot) c1) + c2 with
+// W' = W * gamma (per input column), c1[n] = sum_k W'[n, k], c2[n] = bias[n] + sum_k beta[k] W[n, k]: the GEMM reads the
+// bf16 residual stream (minus a per-row pivot ~ the row mean, so bf16 rounding is relative to the centred value exactly as
+// for a LayerNorm output) and its epilogue applies the row statistics.  Statistics row layout (fp32):
+// [pivot, -, -, -, (mean_i, M2_i) for every 128-column slot i].
+//
+// row_stats_kernel seeds the chain after the patch embedding: exact two-pass mean / M2 of each row, pivot = mean.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, int rows, int stride,
+                                                        __nv_bfloat16* __restrict__ xb, float* __restrict__ stats) {
+    constexpr int V = DIM / 128;
+    constexpr int S = DIM / 128;   // statistics slots
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * DIM);
+    float4 v[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i] = xr[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / DIM);
+    float q = 0.0f;
+    uint2* o = reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * DIM);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + c * c) + (d * d + e * e);
+        o[lane + 32 * i] = make_uint2(pack_bf16x2(a, c), pack_bf16x2(d, e));
+    }
+    const float m2 = warp_sum(q);
+    float* sr = stats + static_cast<size_t>(row) * stride;
+    if (lane == 0) sr[0] = mean;
+    if (lane < S) *reinterpret_cast<float2*>(sr + 4 + 2 * lane) = make_float2(mean, m2 * (1.0f / S));
+}
+
+int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, float* stats, cudaStream_t stream) {
+    CRE_REQUIRE(rows > 0, "row_stats: no rows");
+    CRE_REQUIRE(stride >= 2 * (dim / 128) + 4 && stride % 2 == 0, "row_stats: statistics stride %d too small for dim %d", stride, dim);
+    const int grid = (rows + 7) / 8;
+    LaunchScope scope(CRE_K_ROW_STATS, 6.0 * rows * dim, stream);
+    if (dim == 768) row_stats_kernel<768><<<grid, 256, 0, stream>>>(x, rows, stride, xb, stats);
+    else if (dim == 1024) row_stats_kernel<1024><<<grid, 256, 0, stream>>>(x, rows, stride, xb, stats);
+    else {
+        set_error("row_stats: unsupported dim %d (768 or 1024)", dim);
+        return -3;
+    }
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// One warp per output row n of a Linear that follows a LayerNorm: W' = bf16(W * gamma), c1 = row sum of the ROUNDED W'
+// (what the tensor core will multiply), c2 = bias + W beta.  Runs once per weight matrix at cre_create.
+__global__ void __launch_bounds__(256) fold_ln_weights_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ bias,
+                                                              int n_rows, int k, __nv_bfloat16* __restrict__ wf,
+                                                              float* __restrict__ c1, float* __restrict__ c2) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const __nv_bfloat16* wr = w + static_cast<size_t>(n) * k;
+    __nv_bfloat16* wo = wf + static_cast<size_t>(n) * k;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int j = lane; j < k; j += 32) {
+        const float wv = __bfloat162float(wr[j]);
+        const __nv_bfloat16 f = __float2bfloat16_rn(wv * gamma[j]);
+        wo[j] = f;
+        s1 += __bfloat162float(f);
+        s2 = fmaf(beta[j], wv, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        c1[n] = s1;
+        c2[n] = (bias != nullptr ? bias[n] : 0.0f) + s2;
+    }
+}
+
+int launch_fold_ln_weights(const __nv_bfloat16* w, const float* gamma, const float* beta, const float* bias, int n_rows, int k,
+                           __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream) {
+    CRE_REQUIRE(n_rows > 0 && k > 0, "fold_ln_weights: empty matrix");
+    LaunchScope scope(CRE_K_FOLD_LN, 4.0 * n_rows * k, stream);
+    fold_ln_weights_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(w, gamma, beta, bias, n_rows, k, wf, c1, c2);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Final LayerNorm + mean over all tokens of a frame (HF:modeling_dinov3_vit.py:547 self.norm, then
 // services/dinov3-pipeline/app/main.py:113 last_hidden_state.mean(dim=1)).  One CTA per frame,
 // warps stride over the frame's tokens and keep a per-warp partial sum in registers.

@@ -55,16 +55,14 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
 }
 
 // output tile map for the TMA-store epilogues: box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B swizzle
-static int make_tmap_out(CUtensorMap* out, int epi, const GemmParams& p) {
+static int make_tmap_out(CUtensorMap* out, bool bf16, void* base, int ldo, const GemmParams& p) {
     EncodeTiledFn fn = get_encode_fn();
     CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-    const bool bf16 = epi_out_bf16(epi);
-    void* base = bf16 ? static_cast<void*>(p.out_bf16) : static_cast<void*>(p.out_f32);
     const int esize = bf16 ? 2 : 4;
-    CRE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: output pointer must be 16-byte aligned");
-    CRE_REQUIRE((static_cast<int64_t>(p.ldo) * esize) % 16 == 0, "gemm: output row stride must be a multiple of 16 bytes");
+    CRE_REQUIRE(base != nullptr && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: output pointer must be non-NULL and 16-byte aligned");
+    CRE_REQUIRE((static_cast<int64_t>(ldo) * esize) % 16 == 0, "gemm: output row stride must be a multiple of 16 bytes");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.M)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.ldo) * esize};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldo) * esize};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
@@ -79,9 +77,14 @@ template <int EPI, int CG, int STAGES = default_stages_epi(EPI, CG)>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                       cudaStream_t stream) {
     using Cfg = GemmCfg<EPI, CG, STAGES>;
-    CUtensorMap tout = ta;   // placeholder for the epilogues that store directly
+    CUtensorMap tout = ta, tout2 = ta;   // placeholders for the epilogues that store directly
     if constexpr (epi_tma_store(EPI)) {
-        const int rc = make_tmap_out(&tout, EPI, p);
+        const bool bf16 = epi_out_bf16(EPI);
+        const int rc = make_tmap_out(&tout, bf16, bf16 ? static_cast<void*>(p.out_bf16) : static_cast<void*>(p.out_f32), p.ldo, p);
+        if (rc) return rc;
+    }
+    if constexpr (epi_resid_ln(EPI)) {
+        const int rc = make_tmap_out(&tout2, true, p.out_bf16, p.ldo2, p);
         if (rc) return rc;
     }
     static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline does not fit in shared memory");
@@ -109,12 +112,12 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    constexpr int kid = EPI == EPI_PATCH ? CRE_K_GEMM_PATCH : EPI == EPI_QKV ? CRE_K_GEMM_QKV : EPI == EPI_RESID ? CRE_K_GEMM_RESID
+    constexpr int kid = EPI == EPI_PATCH ? CRE_K_GEMM_PATCH : EPI == EPI_QKV ? CRE_K_GEMM_QKV : (EPI == EPI_RESID || epi_resid_ln(EPI)) ? CRE_K_GEMM_RESID
                       : EPI == EPI_GELU ? CRE_K_GEMM_GELU : EPI == EPI_TOPK ? CRE_K_GEMM_TOPK : CRE_K_GEMM_PLAIN;
     // work: FLOPs, except the gallery scan which is bound by reading the bf16 gallery once (bytes)
     const double work = EPI == EPI_TOPK ? 2.0 * p.N * p.b_k_extent : 2.0 * p.M * static_cast<double>(p.N) * p.K;
     LaunchScope scope(kid, work, stream);
-    CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p));
+    CRE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tout2, p));
     return 0;
 }
 
@@ -156,7 +159,15 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     CRE_REQUIRE(epi == EPI_TOPK || p.N % (epi_out_bf16(epi) ? 64 : 32) == 0, "gemm: N=%d must be a multiple of %d for this epilogue",
                 p.N, epi_out_bf16(epi) ? 64 : 32);
     CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
-    if (g_debug_mode != 0 && epi == EPI_NONE) {
+    if (epi_resid_ln(epi)) {
+        CRE_REQUIRE(p.N % kBlockN == 0 && p.N / 128 == p.ln_slots && p.ln_slots <= 8 && p.ln_stride >= 2 * p.ln_slots + kLnStatsPad,
+                    "gemm: RESID_LN needs N %% 256 == 0 and N / 128 = ln_slots <= 8 (N=%d slots=%d stride=%d)", p.N, p.ln_slots, p.ln_stride);
+        CRE_REQUIRE(p.ln_stats_in != nullptr && p.ln_stats_out != nullptr && p.bias != nullptr && p.scale != nullptr,
+                    "gemm: RESID_LN needs statistics in/out, bias and scale");
+    }
+    if (p.ln_stats_in != nullptr && !epi_resid_ln(epi))
+        CRE_REQUIRE(p.c1 != nullptr && p.bias != nullptr && p.ln_slots >= 1 && p.ln_slots <= 8, "gemm: folded LayerNorm needs c1, bias and 1..8 slots");
+    if (g_debug_mode != 0 && (epi == EPI_NONE || g_debug_mode >= 4)) {
         GemmParams q = p;
         q.debug_mode = g_debug_mode;
         const int saved = g_debug_mode;
@@ -164,6 +175,11 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         const int r = launch_gemm(epi, cg, a, lda, b, ldb, q, num_sms, stream);
         g_debug_mode = saved;
         return r;
+    }
+    if (epi == EPI_QKV && p.c1 == nullptr) {   // unfolded QKV: c1 is multiplied by 0
+        GemmParams q = p;
+        q.c1 = p.bias;
+        return launch_gemm(epi, cg, a, lda, b, ldb, q, num_sms, stream);
     }
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16(&ta, a, p.M, p.K, lda, kBlockM);
@@ -189,6 +205,8 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         CRE_CASE(EPI_QKV)
         CRE_CASE(EPI_GELU)
         CRE_CASE(EPI_RESID)
+        CRE_CASE(EPI_RESID_LN)
+        CRE_CASE(EPI_RESID_LN3)
         CRE_CASE(EPI_PATCH)
         CRE_CASE(EPI_NONE)
         case EPI_TOPK:

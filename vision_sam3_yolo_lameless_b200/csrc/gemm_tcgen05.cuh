@@ -34,7 +34,11 @@ enum GemmEpi : int {
     EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]   (patch rows -> token rows, direct stores)
     EPI_TOPK = 6,   // running per-row top-k over the columns this CTA visits  (gallery scan)
     EPI_NONE = 7,   // accumulators are dropped (main-loop tuning only)
+    EPI_RESID_LN = 8,  // v = x + scale * (acc + bias): x (TMA load -> store), bf16(v - pivot) and per-row LayerNorm partials
+    EPI_RESID_LN3 = 9, // same with ONE x tile per epilogue warp and one pipeline stage more (long-K GEMMs: a tile's main loop
+                       // is long enough to hide the x round trips; measured against three x tiles + one stage fewer: slower)
 };
+constexpr bool epi_resid_ln(int epi) { return epi == EPI_RESID_LN || epi == EPI_RESID_LN3; }
 
 constexpr int kTopKMax = 8;
 
@@ -46,6 +50,16 @@ struct GemmParams {
     float* out_f32;
     __nv_bfloat16* out_bf16;
     int ldo;
+    // LayerNorm folded into the GEMM (see "LayerNorm folding" below).  Consumer side (EPI_QKV / EPI_GELU / EPI_BF16 with
+    // ln_stats_in != nullptr): out = rstd * (acc - (mean - pivot) * c1[n]) + bias[n].  Producer side (EPI_RESID_LN): reads
+    // ln_stats_in (previous statistics of the row -> pivot), writes ln_stats_out, out_f32 (x) and out_bf16 (x - pivot).
+    const float* ln_stats_in;
+    float* ln_stats_out;
+    const float* c1;     // [N] column sums of the folded weight (consumer side)
+    int ln_slots;        // 128-column partials per row = 2 * hidden / 256
+    int ln_stride;       // floats per statistics row = 2 * ln_slots + 4
+    float ln_eps;
+    int ldo2;            // EPI_RESID_LN: row stride of out_bf16
     // EPI_QKV
     const float* rope_axis;  // [(grid_h + grid_w), 36] fp32: per-axis {cos[16], sin[16]} rows (y positions, then x positions)
     int grid_h, grid_w;
@@ -72,14 +86,21 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;  // one epilogue warp's staging tile: 32 rows x 128 bytes
 
 constexpr bool epi_tma_store(int epi) {
-    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID;
+    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID || epi_resid_ln(epi);
 }
 constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
 constexpr int kRopeRowFloats = 36;
 constexpr int kRopeTableBytes = 12 * 1024;   // up to 85 axis rows (grid_h + grid_w), e.g. 37 + 37 at 592 x 592
 // the QKV kernel trades one pipeline stage for the rotary table in shared memory
-constexpr int default_stages_epi(int epi, int cg) { return default_stages(cg) - (epi == EPI_QKV ? 1 : 0); }
+// EPI_RESID_LN keeps 2 (LN3: 1) x tiles + the bf16 tile, 4 KB each, per epilogue warp
+constexpr int ln_x_slots(int epi) { return epi == EPI_RESID_LN3 ? 1 : 2; }
+constexpr int ln_warp_bytes(int epi) { return (ln_x_slots(epi) + 1) * kEpiStageBytes; }
+constexpr int kLnStatsPad = 4;               // floats before the partials in one statistics row: [pivot, -, -, -]
+constexpr int default_stages_epi(int epi, int cg) {
+    return epi == EPI_RESID_LN ? (cg == 1 ? 2 : 4) : epi == EPI_RESID_LN3 ? (cg == 1 ? 3 : 5)
+                                                   : default_stages(cg) - (epi == EPI_QKV ? 1 : 0);
+}
 
 template <int EPI, int CG, int STAGES>
 struct GemmCfg {
@@ -87,11 +108,11 @@ struct GemmCfg {
     static constexpr int kSmemA = kBlockM * kBlockK * 2;          // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
-    static constexpr int kEpiBytes = epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
+    static constexpr int kEpiBytes = epi_resid_ln(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
     static constexpr int kTableOff = kEpiOff + kEpiBytes;
     static constexpr int kTableBytes = EPI == EPI_QKV ? kRopeTableBytes : 0;
     static constexpr int kBarOff = kTableOff + kTableBytes;
-    static constexpr int kSmemBytes = kBarOff + 256 + 1024;       // barriers + tmem ptr + align slack
+    static constexpr int kSmemBytes = kBarOff + 512 + 1024;       // barriers (+ x-tile barriers) + tmem ptr + align slack
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -153,6 +174,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                  "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+constexpr int kPrefetchKb = 8;
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -160,7 +187,8 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 template <int EPI, int CG, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+               const GemmParams p) {
     using Cfg = GemmCfg<EPI, CG, STAGES>;
     constexpr int kStages = Cfg::kStages;
 
@@ -187,6 +215,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if constexpr (epi_tma_store(EPI)) tma_prefetch_desc(&tmap_out);
+        if constexpr (epi_resid_ln(EPI)) tma_prefetch_desc(&tmap_out2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -197,6 +226,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(tmem_full_bar(s), 1);
             mbar_init(tmem_empty_bar(s), kEpiWarps * CG);
         }
+        if constexpr (epi_resid_ln(EPI))
+            for (int s = 0; s < 4 * kEpiWarps; ++s) mbar_init(bar_base + 256u + 8u * s, 1);
         fence_barrier_init();
     } else if (warp == 2) {
         tmem_alloc<CG>(tmem_slot, 512);
@@ -252,6 +283,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 const int ka = kb * kBlockK;
                 const int kbb = ka % p.b_k_extent;
+                if (p.debug_mode & 32) {
+                    // tuning: pull the A box kPrefetchKb k-blocks ahead (next tile's first boxes at the tail) into L2
+                    int pkb = kb + kPrefetchKb, prow = row0;
+                    if (pkb >= num_kb) {
+                        pkb -= num_kb;
+                        const int tn = t + t_step;
+                        prow = tn < t_end ? ((tn / num_nt) * CG + static_cast<int>(cta_rank)) * kBlockM : -1;
+                    }
+                    if (prow >= 0) tma_prefetch_2d(&tmap_a, pkb * kBlockK, prow);
+                }
                 tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA, ka, row0, kEvictNormal);
                 tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, kEvictLast);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -292,7 +333,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int half = (warp - 4) >> 2;      // which 128 accumulator columns
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         // this warp's staging tile (TMA-store epilogues): row r at r*128, 16-byte unit u at (u ^ (r & 7))
-        const uint32_t stage_u32 = smem_base + Cfg::kEpiOff + (warp - 4) * kEpiStageBytes;
+        constexpr int kWarpStage = epi_resid_ln(EPI) ? ln_warp_bytes(EPI) : kEpiStageBytes;
+        constexpr int XS = ln_x_slots(EPI);
+        const uint32_t stage_u32 = smem_base + Cfg::kEpiOff + (warp - 4) * kWarpStage;
         uint8_t* stage_row = smem_raw + (stage_u32 - smem_u32(smem_raw)) + lane * 128;
         const uint32_t r7 = lane & 7;
         auto stage_store = [&](int u, uint4 v) {
@@ -313,6 +356,56 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 bulk_commit();
             }
         };
+
+        // LayerNorm folding, consumer side: (rstd, -rstd * (mean - pivot)) of one row from its statistics row
+        // [pivot, -, -, -, (mean_i, M2_i) x ln_slots]; Chan's combination of the 128-column partials.
+        auto ln_row = [&](int r, bool ok, float& rstd, float& nrd) {
+            rstd = 1.0f;
+            nrd = 0.0f;
+            if (p.ln_stats_in == nullptr || !ok) return;
+            const float* so = p.ln_stats_in + static_cast<size_t>(r) * p.ln_stride;
+            const float pivot = so[0];
+            float mi[8];
+            float ms = 0.0f, m2 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                mi[i] = 0.0f;
+                if (i < p.ln_slots) {
+                    const float2 e = *reinterpret_cast<const float2*>(so + kLnStatsPad + 2 * i);
+                    mi[i] = e.x;
+                    ms += e.x;
+                    m2 += e.y;
+                }
+            }
+            const float inv_s = 1.0f / static_cast<float>(p.ln_slots);
+            const float mean = ms * inv_s;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < p.ln_slots) {
+                    const float d = mi[i] - mean;
+                    m2 = fmaf(128.0f * d, d, m2);
+                }
+            rstd = rsqrtf(m2 * inv_s * (1.0f / 128.0f) + p.ln_eps);
+            nrd = -rstd * (mean - pivot);
+        };
+
+        // EPI_RESID_LN: x-tile ring (XS 4 KB slots per warp, one mbarrier each), XS loads ahead of the chunk in hand
+        [[maybe_unused]] int xg = 0;         // running chunk counter of this warp: chunk xg lives in slot xg % XS
+        auto xbar = [&](int s) { return bar_base + 256u + 8u * static_cast<uint32_t>((warp - 4) * 4 + s); };
+        auto x_issue = [&](int s, int col, int rowb) {   // lane 0: arm the slot's barrier and fetch one 32 x 32 fp32 box of x
+            mbar_arrive_expect_tx(xbar(s), kEpiStageBytes);
+            tma_load_2d<1>(&tmap_out, xbar(s), stage_u32 + s * kEpiStageBytes, col, rowb, kEvictNormal);
+        };
+        if constexpr (epi_resid_ln(EPI)) {
+            if (lane == 0 && t_begin < t_end) {
+                const int mt0 = t_begin / num_nt, nt0 = t_begin % num_nt;
+                const int rb0 = (mt0 * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
+                const int nc0 = nt0 * kBlockN + half * 128;
+                x_issue(0, nc0, rb0);
+                if constexpr (XS > 1) x_issue(1, nc0 + 32, rb0);
+            }
+            __syncwarp();
+        }
 
         // EPI_TOPK running state
         float tk_s[kTopKMax];
@@ -365,6 +458,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float* tab = reinterpret_cast<const float*>(smem_raw + (smem_base + Cfg::kTableOff - smem_u32(smem_raw)));
                 const float4* ty = reinterpret_cast<const float4*>(tab + py * kRopeRowFloats);                 // cos[16] | sin[16]
                 const float4* tx = reinterpret_cast<const float4*>(tab + (p.grid_h + px) * kRopeRowFloats);
+                float rstd, nrd;
+                ln_row(row, row_ok, rstd, nrd);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -381,14 +476,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
                         const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
-                        x1[4 * j4] = __uint_as_float(a[4 * j4]) + b1.x;
-                        x1[4 * j4 + 1] = __uint_as_float(a[4 * j4 + 1]) + b1.y;
-                        x1[4 * j4 + 2] = __uint_as_float(a[4 * j4 + 2]) + b1.z;
-                        x1[4 * j4 + 3] = __uint_as_float(a[4 * j4 + 3]) + b1.w;
-                        x2[4 * j4] = __uint_as_float(b[4 * j4]) + b2.x;
-                        x2[4 * j4 + 1] = __uint_as_float(b[4 * j4 + 1]) + b2.y;
-                        x2[4 * j4 + 2] = __uint_as_float(b[4 * j4 + 2]) + b2.z;
-                        x2[4 * j4 + 3] = __uint_as_float(b[4 * j4 + 3]) + b2.w;
+                        const float4 k1 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0) + j4);
+                        const float4 k2 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0 + 32) + j4);
+                        x1[4 * j4] = fmaf(rstd, __uint_as_float(a[4 * j4]), fmaf(nrd, k1.x, b1.x));
+                        x1[4 * j4 + 1] = fmaf(rstd, __uint_as_float(a[4 * j4 + 1]), fmaf(nrd, k1.y, b1.y));
+                        x1[4 * j4 + 2] = fmaf(rstd, __uint_as_float(a[4 * j4 + 2]), fmaf(nrd, k1.z, b1.z));
+                        x1[4 * j4 + 3] = fmaf(rstd, __uint_as_float(a[4 * j4 + 3]), fmaf(nrd, k1.w, b1.w));
+                        x2[4 * j4] = fmaf(rstd, __uint_as_float(b[4 * j4]), fmaf(nrd, k2.x, b2.x));
+                        x2[4 * j4 + 1] = fmaf(rstd, __uint_as_float(b[4 * j4 + 1]), fmaf(nrd, k2.y, b2.y));
+                        x2[4 * j4 + 2] = fmaf(rstd, __uint_as_float(b[4 * j4 + 2]), fmaf(nrd, k2.z, b2.z));
+                        x2[4 * j4 + 3] = fmaf(rstd, __uint_as_float(b[4 * j4 + 3]), fmaf(nrd, k2.w, b2.w));
                     }
                     if (rot) {
                         // element j of each half pairs with angle j: j < 16 -> y-angle j, j >= 16 -> x-angle j - 16
@@ -423,14 +520,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             } else if constexpr (epi_tma_store(EPI) && epi_out_bf16(EPI)) {
                 // EPI_BF16 / EPI_GELU: 64-column chunks, bf16 out
+                float rstd, nrd;
+                ln_row(row, row_ok, rstd, nrd);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
                     if (n0 >= p.N) break;
+                    if (p.debug_mode & 4) break;          // tuning: accumulators are never read
                     uint32_t a[32], b[32];
                     tmem_ld32(taddr + hh * 64, a);
                     tmem_ld32(taddr + hh * 64 + 32, b);
                     tmem_ld_wait();
+                    if (p.debug_mode & 8) {               // tuning: TMEM read only
+                        uint32_t acc_or = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc_or |= a[j] | b[j];
+                        if (acc_or == 0x7fc12345u) p.out_bf16[0] = __float2bfloat16(0.f);
+                        continue;
+                    }
                     uint32_t o[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -438,11 +545,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         if (p.bias != nullptr) {
                             b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
                             b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
+                            if (p.ln_stats_in != nullptr) {
+                                const float4 k1 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0) + j4);
+                                const float4 k2 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0 + 32) + j4);
+                                b1.x = fmaf(nrd, k1.x, b1.x); b1.y = fmaf(nrd, k1.y, b1.y); b1.z = fmaf(nrd, k1.z, b1.z); b1.w = fmaf(nrd, k1.w, b1.w);
+                                b2.x = fmaf(nrd, k2.x, b2.x); b2.y = fmaf(nrd, k2.y, b2.y); b2.z = fmaf(nrd, k2.z, b2.z); b2.w = fmaf(nrd, k2.w, b2.w);
+                            }
                         }
-                        float v0 = __uint_as_float(a[4 * j4]) + b1.x, v1 = __uint_as_float(a[4 * j4 + 1]) + b1.y;
-                        float v2 = __uint_as_float(a[4 * j4 + 2]) + b1.z, v3 = __uint_as_float(a[4 * j4 + 3]) + b1.w;
-                        float w0 = __uint_as_float(b[4 * j4]) + b2.x, w1 = __uint_as_float(b[4 * j4 + 1]) + b2.y;
-                        float w2 = __uint_as_float(b[4 * j4 + 2]) + b2.z, w3 = __uint_as_float(b[4 * j4 + 3]) + b2.w;
+                        float v0 = fmaf(rstd, __uint_as_float(a[4 * j4]), b1.x), v1 = fmaf(rstd, __uint_as_float(a[4 * j4 + 1]), b1.y);
+                        float v2 = fmaf(rstd, __uint_as_float(a[4 * j4 + 2]), b1.z), v3 = fmaf(rstd, __uint_as_float(a[4 * j4 + 3]), b1.w);
+                        float w0 = fmaf(rstd, __uint_as_float(b[4 * j4]), b2.x), w1 = fmaf(rstd, __uint_as_float(b[4 * j4 + 1]), b2.y);
+                        float w2 = fmaf(rstd, __uint_as_float(b[4 * j4 + 2]), b2.z), w3 = fmaf(rstd, __uint_as_float(b[4 * j4 + 3]), b2.w);
                         if constexpr (EPI == EPI_GELU) {
                             gelu2(v0, v1); gelu2(v2, v3); gelu2(w0, w1); gelu2(w2, w3);
                         }
@@ -454,7 +567,102 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     stage_begin();
 #pragma unroll
                     for (int u = 0; u < 8; ++u) stage_store(u, make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]));
+                    if (p.debug_mode & 16) continue;      // tuning: staged, never stored
                     stage_commit(n0, row_base);
+                }
+            } else if constexpr (epi_resid_ln(EPI)) {
+                // v = x + scale * (acc + bias) per 32-column chunk: x arrives by TMA in this warp's slot ring, v goes
+                // back through the same slot (TMA store), bf16(v - pivot) through the 64-column tile (TMA store every
+                // second chunk), and the row's (mean, M2) over this warp's 128 columns is merged chunk by chunk.
+                const int slot_id = nt * 2 + half;
+                float pivot = 0.0f;
+                if (row_ok) {   // pivot = the row's mean at the previous LayerNorm (any value near the mean would do)
+                    const float* so = p.ln_stats_in + static_cast<size_t>(row) * p.ln_stride + kLnStatsPad;
+                    float ms = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < p.ln_slots) ms += so[2 * i];
+                    pivot = ms / static_cast<float>(p.ln_slots);
+                }
+                float mean_r = 0.0f, m2_r = 0.0f;
+                uint8_t* orow = stage_row + XS * kEpiStageBytes;
+                // lane 0: fetch the x tile XS chunks ahead (this tile, or the head of this worker's next tile) into `slot`
+                auto x_ahead = [&](int c, int slot) {
+                    int c2 = c + XS, nrow = row_base, ncol = ncol0;
+                    if (c2 >= 4) {
+                        const int tn = t + t_step;
+                        if (tn >= t_end) return;
+                        c2 -= 4;
+                        const int nmt = tn / num_nt, nnt = tn % num_nt;
+                        nrow = (nmt * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
+                        ncol = nnt * kBlockN + half * 128;
+                    }
+                    x_issue(slot, ncol + c2 * 32, nrow);
+                };
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c, ++xg) {
+                    const int n0 = ncol0 + c * 32;
+                    const int s = xg % XS;
+                    const int ob = c & 1;   // which half of the bf16 tile
+                    uint32_t a[32];
+                    tmem_ld32(taddr + c * 32, a);
+                    mbar_wait(xbar(s), static_cast<uint32_t>(xg / XS) & 1u);
+                    tmem_ld_wait();
+                    uint8_t* xrow = stage_row + s * kEpiStageBytes;
+                    float v[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xrow + ((static_cast<uint32_t>(u) ^ r7) << 4));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + u);
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + u);
+                        v[4 * u] = fmaf(sc.x, __uint_as_float(a[4 * u]) + b4.x, xv.x);
+                        v[4 * u + 1] = fmaf(sc.y, __uint_as_float(a[4 * u + 1]) + b4.y, xv.y);
+                        v[4 * u + 2] = fmaf(sc.z, __uint_as_float(a[4 * u + 2]) + b4.z, xv.z);
+                        v[4 * u + 3] = fmaf(sc.w, __uint_as_float(a[4 * u + 3]) + b4.w, xv.w);
+                    }
+                    // chunk statistics (two passes over registers), then Chan's merge with the running pair
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+                    const float mc = ((s0 + s1) + (s2 + s3)) * (1.0f / 32.0f);
+                    float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float d0 = v[j] - mc, d1 = v[j + 1] - mc;
+                        q0 = fmaf(d0, d0, q0);
+                        q1 = fmaf(d1, d1, q1);
+                    }
+                    const float delta = mc - mean_r;
+                    const float inv = 1.0f / static_cast<float>(c + 1);
+                    mean_r = fmaf(delta, inv, mean_r);
+                    m2_r += (q0 + q1) + delta * delta * (32.0f * static_cast<float>(c) * inv);
+                    // every earlier store of this warp has drained its smem tiles: the bf16 tile may be overwritten
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<float4*>(xrow + ((static_cast<uint32_t>(u) ^ r7) << 4)) =
+                            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(ob * 4 + j) ^ r7) << 4)) =
+                            make_uint4(pack_bf16x2(v[8 * j] - pivot, v[8 * j + 1] - pivot), pack_bf16x2(v[8 * j + 2] - pivot, v[8 * j + 3] - pivot),
+                                       pack_bf16x2(v[8 * j + 4] - pivot, v[8 * j + 5] - pivot), pack_bf16x2(v[8 * j + 6] - pivot, v[8 * j + 7] - pivot));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, stage_u32 + s * kEpiStageBytes, n0, row_base);
+                        if (ob == 1) tma_store_2d(&tmap_out2, stage_u32 + XS * kEpiStageBytes, n0 - 32, row_base);
+                        bulk_commit();
+                        bulk_wait_read0();   // the chunk XS ahead reuses THIS slot once its store has drained
+                        x_ahead(c, s);
+                    }
+                    __syncwarp();
+                }
+                if (row_ok) {
+                    float* sn = p.ln_stats_out + static_cast<size_t>(row) * p.ln_stride;
+                    *reinterpret_cast<float2*>(sn + kLnStatsPad + 2 * slot_id) = make_float2(mean_r, m2_r);
+                    if (slot_id == 0) sn[0] = pivot;
                 }
             } else if constexpr (epi_tma_store(EPI)) {
                 // EPI_F32 / EPI_RESID: 32-column chunks, fp32 out (store / reduce-add)

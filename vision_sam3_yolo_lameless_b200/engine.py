@@ -366,6 +366,44 @@ class ClipEmbedEngine:
                                           _ptr(scale), out.data_ptr(), cta_group, self._stream()), "cre_gemm_bf16")
         return out
 
+    def row_stats(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """f32 [rows, dim] -> (bf16 [rows, dim] = x - row mean, f32 statistics rows [rows, 2 * dim / 128 + 4])."""
+        rows, dim = x.shape
+        xb = torch.empty((rows, dim), dtype=torch.bfloat16, device=self.device)
+        stats = torch.zeros((rows, 2 * (dim // 128) + 4), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cre_row_stats(x.data_ptr(), rows, dim, xb.data_ptr(), stats.data_ptr(), self._stream()), "cre_row_stats")
+        return xb, stats
+
+    def fold_ln_weights(self, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        """bf16 W [n, k] + LayerNorm (gamma, beta) [k] + bias [n] -> (bf16 W * gamma, c1 = its row sums, c2 = bias + W beta)."""
+        n, k = w.shape
+        wf = torch.empty_like(w)
+        c1 = torch.empty(n, dtype=torch.float32, device=self.device)
+        c2 = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cre_fold_ln_weights(w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(bias), n, k, wf.data_ptr(),
+                                                c1.data_ptr(), c2.data_ptr(), self._stream()), "cre_fold_ln_weights")
+        return wf, c1, c2
+
+    def gemm_ln(self, a: torch.Tensor, b: torch.Tensor, epilogue: int, stats_in: torch.Tensor, ln_dim: int, bias=None, c1=None,
+                scale=None, out: Optional[torch.Tensor] = None, eps: float = 1e-5, cta_group: int = 2):
+        """LayerNorm-folded GEMM building block (include/cre.h cre_gemm_ln).  EPI_BF16 / EPI_GELU: returns bf16 [m, n].
+        EPI_RESID_LN: `out` f32 [m, n] is updated in place; returns (out, bf16 out - pivot, new statistics rows)."""
+        m, k = a.shape
+        n = b.shape[0]
+        if epilogue in (_lib.EPI_RESID_LN, _lib.EPI_RESID_LN3):
+            xb = torch.empty((m, n), dtype=torch.bfloat16, device=self.device)
+            stats_out = torch.zeros_like(stats_in)
+            _lib.check(self.lib.cre_gemm_ln(self._ctx, a.data_ptr(), b.data_ptr(), m, n, k, epilogue, _ptr(bias), None, _ptr(scale),
+                                            stats_in.data_ptr(), ln_dim, eps, out.data_ptr(), xb.data_ptr(), stats_out.data_ptr(),
+                                            cta_group, self._stream()), "cre_gemm_ln")
+            return out, xb, stats_out
+        if out is None:
+            out = torch.zeros((m, n), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.cre_gemm_ln(self._ctx, a.data_ptr(), b.data_ptr(), m, n, k, epilogue, _ptr(bias), _ptr(c1), None,
+                                        stats_in.data_ptr(), ln_dim, eps, out.data_ptr(), None, None, cta_group, self._stream()),
+                   "cre_gemm_ln")
+        return out
+
     def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
         rows, dim = x.shape
         out = torch.empty((rows, dim), dtype=torch.bfloat16, device=self.device)
