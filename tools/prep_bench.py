@@ -9,8 +9,13 @@ from gemm_tune import timeit
 
 model = common.hf_model(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=600)
+from vision_sam3_yolo_lameless_b200 import _lib
+modes = [int(a) for a in sys.argv[1:]] or [1, 0]       # preprocess_tma values: 1 = TMA-staged, 0 = direct-load kernel; +2 / +4 = debug bits
 for (n, h, w) in [(600, 1080, 1920), (600, 720, 1280), (600, 224, 224)]:
     fr = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=eng.device)
-    ms = timeit(lambda: eng.preprocess(fr), iters=10)
-    b = n * (h * w * 3 + 196 * 1536)
-    print(f"preprocess {n}x{h}x{w}: {ms:.3f} ms  {ms / n * 1e3:.2f} us/frame  {b / ms / 1e6:.0f} GB/s", flush=True)
+    for mode in modes:
+        _lib.set_tuning("preprocess_tma", mode)
+        ms = timeit(lambda: eng.preprocess(fr), iters=10)
+        b = n * (h * w * 3 + 196 * 1536)
+        print(f"preprocess[mode {mode}] {n}x{h}x{w}: {ms:.3f} ms  {ms / n * 1e3:.2f} us/frame  {b / ms / 1e6:.0f} GB/s", flush=True)
+_lib.set_tuning("preprocess_tma", 1)

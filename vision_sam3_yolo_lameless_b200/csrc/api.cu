@@ -734,6 +734,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_attention_debug(value);
         return 0;
     }
+    if (strcmp(key, "preprocess_tma") == 0) {
+        set_preprocess_tma(value);
+        return 0;
+    }
     if (strcmp(key, "resid_ln_deep") == 0) {
         g_resid_ln_deep = value & 3;
         return 0;

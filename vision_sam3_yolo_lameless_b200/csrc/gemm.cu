@@ -54,6 +54,25 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
     return 0;
 }
 
+int make_tmap_u8_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t row_pitch,
+                    int64_t frame_pitch, int box_cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_pitch % 16 == 0 && frame_pitch % 16 == 0,
+                "TMA frame tensor needs 16-byte aligned base and pitches");
+    CRE_REQUIRE(box_cols >= 16 && box_cols <= 256 && box_cols % 16 == 0 && box_rows >= 1 && box_rows <= 256, "TMA box %dx%d out of range",
+                box_rows, box_cols);
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(frames)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch), static_cast<cuuint64_t>(frame_pitch)};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (frames) failed with CUresult %d (cols=%lld rows=%lld frames=%lld pitch=%lld/%lld)",
+                (int)r, (long long)cols, (long long)rows, (long long)frames, (long long)row_pitch, (long long)frame_pitch);
+    return 0;
+}
+
 // output tile map for the TMA-store epilogues: box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B swizzle
 static int make_tmap_out(CUtensorMap* out, bool bf16, void* base, int ldo, const GemmParams& p) {
     EncodeTiledFn fn = get_encode_fn();

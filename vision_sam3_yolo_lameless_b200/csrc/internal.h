@@ -39,6 +39,12 @@ int profile_stop(int32_t* ids, float* ms, double* work, int cap);
 // [box_rows x 64] box and 128-byte swizzle.  Returns 0 / negative error code.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
+// uint8 tensor [frames, rows, cols] (strides in bytes, multiples of 16) -> TMA descriptor with a [1, box_rows, box_cols] box,
+// no swizzle, zero fill out of bounds
+int make_tmap_u8_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t row_pitch,
+                    int64_t frame_pitch, int box_cols, int box_rows);
+void set_preprocess_tma(int on);
+
 struct GemmParams;
 // epi is a cre::GemmEpi value; cg = 1 | 2
 int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int64_t ldb, const GemmParams& p,

@@ -143,6 +143,245 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
     }
 }
 
+// =====================================================================================================================
+// TMA-staged, warp-specialised variant (16-byte aligned frames and pitches; the tile must fit shared memory twice).
+// Persistent: one CTA per SM walks tiles (frame, patch row, patch) in raster order.
+//
+//   warp 20 (one lane)  tile scheduler + TMA producer: the raw uint8 rows the tile's 16 output rows depend on -- rows_tile rows
+//                       x nbox 256-byte boxes -- land in a 2-deep ring; no thread ever waits on a global load of pixels.
+//   warps 0..15         pass 1, warp r = output row r of the patch, lane = 16-byte column group: vertical taps from shared
+//                       memory (same arithmetic and order as preprocess_kernel: results are bit-identical) -> vbuf ring.
+//   warps 16..19        pass 2: horizontal taps + normalise + bf16 + patch-order stores, two pixels per thread.
+//
+// The three roles are connected by mbarriers only (raw full/empty, vbuf full/empty): no __syncthreads in the tile loop.
+// =====================================================================================================================
+constexpr int kPtRowWarps = 16, kPtColWarps = 4;
+constexpr int kPtThreads = (kPtRowWarps + kPtColWarps + 1) * 32;
+constexpr int kPtParamInts = 8;   // per tile: frame, py, px, b0, y_first, nvec
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(kEvictFirst)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kPtThreads, 1)
+preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles, int debug) {
+    extern __shared__ uint8_t smem_raw_[];
+    const uint32_t base_u32 = (smem_u32(smem_raw_) + 127u) & ~127u;
+    uint8_t* base = smem_raw_ + (base_u32 - smem_u32(smem_raw_));
+    const int raw_bytes = nbox * rows_tile * 256;
+    const int vb_floats = 16 * p.sstride;
+    float* vb0 = reinterpret_cast<float*>(base + 2 * raw_bytes);
+    int* params = reinterpret_cast<int*>(base + 2 * raw_bytes + 2 * vb_floats * 4);          // [4][kPtParamInts]
+    const uint32_t bar0 = base_u32 + 2 * raw_bytes + 2 * vb_floats * 4 + 4 * kPtParamInts * 4;
+    // resize tables, copied once per CTA: every tap weight / window lookup in the tile loop is a shared-memory read
+    const int oh = p.gh * 16, ow = p.gw * 16;
+    float* s_yw = reinterpret_cast<float*>(base + 2 * raw_bytes + 2 * vb_floats * 4 + 4 * kPtParamInts * 4 + 64);
+    float* s_xw = s_yw + oh * p.ykmax;
+    int* s_ylo = reinterpret_cast<int*>(s_xw + ow * p.xkmax);
+    int* s_ycnt = s_ylo + oh;
+    int* s_xlo = s_ycnt + oh;
+    int* s_xcnt = s_xlo + ow;
+    for (int i = threadIdx.x; i < oh * p.ykmax; i += kPtThreads) s_yw[i] = __ldg(p.yw + i);
+    for (int i = threadIdx.x; i < ow * p.xkmax; i += kPtThreads) s_xw[i] = __ldg(p.xw + i);
+    for (int i = threadIdx.x; i < oh; i += kPtThreads) { s_ylo[i] = __ldg(p.ylo + i); s_ycnt[i] = __ldg(p.ycnt + i); }
+    for (int i = threadIdx.x; i < ow; i += kPtThreads) { s_xlo[i] = __ldg(p.xlo + i); s_xcnt[i] = __ldg(p.xcnt + i); }
+    auto raw_full = [&](int b) { return bar0 + 8u * b; };
+    auto raw_empty = [&](int b) { return bar0 + 16u + 8u * b; };
+    auto vb_full = [&](int b) { return bar0 + 32u + 8u * b; };
+    auto vb_empty = [&](int b) { return bar0 + 48u + 8u * b; };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int per_frame = p.gh * p.gw;
+    const int step = gridDim.x;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(raw_full(b), 1);
+            mbar_init(raw_empty(b), kPtRowWarps);
+            mbar_init(vb_full(b), kPtRowWarps);
+            mbar_init(vb_empty(b), kPtColWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kPtRowWarps + kPtColWarps) {
+        // =============================== scheduler + TMA producer ===============================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+                const int buf = it & 1;
+                if (it >= 2) mbar_wait(raw_empty(buf), static_cast<uint32_t>((it >> 1) - 1) & 1u);
+                const int frame = tile / per_frame, rem = tile - frame * per_frame;
+                const int py = rem / p.gw, px = rem - py * p.gw;
+                const int ox0 = px * 16;
+                const int x_lo = s_xlo[ox0];
+                const int x_hi = s_xlo[ox0 + 15] + s_xcnt[ox0 + 15];
+                const int b0 = (x_lo * 3) & ~15;
+                const int y_first = s_ylo[py * 16];
+                int* pr = params + (it & 3) * kPtParamInts;
+                pr[0] = frame; pr[1] = py; pr[2] = px; pr[3] = b0; pr[4] = y_first; pr[5] = (x_hi * 3 - b0 + 15) >> 4;
+                if (debug & 2) { mbar_arrive(raw_full(buf)); continue; }   // tuning: no loads
+                mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
+                for (int j = 0; j < nbox; ++j)
+                    tma_load_3d(&tmap, raw_full(buf), base_u32 + buf * raw_bytes + j * rows_tile * 256, b0 + j * 256, y_first, frame);
+            }
+        }
+    } else if (warp < kPtRowWarps) {
+        // =============================== pass 1: vertical filter, warp = output row ===============================
+        const int r = warp;
+        const int rot = (lane >> 1) & 3;   // store-order rotation: the four 16-byte stores of a lane hit all bank groups evenly
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+            mbar_wait(raw_full(buf), ph);
+            const int* pr = params + (it & 3) * kPtParamInts;
+            const int py = pr[1], y_first = pr[4], nvec = pr[5];
+            if (it >= 2) mbar_wait(vb_empty(buf), ph ^ 1u);
+            const uint8_t* raw = base + buf * raw_bytes;
+            float* vrow = vb0 + buf * vb_floats + static_cast<size_t>(r) * p.sstride;
+            const int oy = py * 16 + r;
+            const int y0 = s_ylo[oy] - y_first, cnt = s_ycnt[oy];
+            const float* wy = s_yw + oy * p.ykmax;
+            for (int v = lane; v < nvec && !(debug & 1); v += 32) {
+                const uint8_t* src = raw + (v >> 4) * (rows_tile * 256) + y0 * 256 + (v & 15) * 16;
+                uint64_t acc2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc2[i] = pack2(0.0f, 0.0f);
+                float wsum = 0.0f;
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const float wk = wy[k];
+                    const uint4 q = *reinterpret_cast<const uint4*>(src + k * 256);
+                    const uint64_t w2 = pack2(wk, wk);
+                    wsum += wk;
+                    const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc2[2 * i] = fma2(pack2(byte_as_unit_float(wds[i], 0x7604u), byte_as_unit_float(wds[i], 0x7614u)), w2, acc2[2 * i]);
+                        acc2[2 * i + 1] = fma2(pack2(byte_as_unit_float(wds[i], 0x7624u), byte_as_unit_float(wds[i], 0x7634u)), w2, acc2[2 * i + 1]);
+                    }
+                }
+                // (acc - wsum) * 2^15 as one packed FMA: the scaling is exact, so this rounds exactly like the subtraction
+                const float nws = -wsum * 32768.0f;
+                const uint64_t k15 = pack2(32768.0f, 32768.0f), nws2 = pack2(nws, nws);
+                float4 f[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unpack2(fma2(acc2[2 * i], k15, nws2), f[i].x, f[i].y);
+                    unpack2(fma2(acc2[2 * i + 1], k15, nws2), f[i].z, f[i].w);
+                }
+                // rotate the store order by `rot` (two select stages) -- lane l writes unit (i + rot) & 3 in store i
+                float4 g[4], h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a = f[i], b = f[(i + 1) & 3];
+                    g[i] = (rot & 1) ? b : a;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a = g[i], b = g[(i + 2) & 3];
+                    h[i] = (rot & 2) ? b : a;
+                }
+                float4* dst = reinterpret_cast<float4*>(vrow + v * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[(i + rot) & 3] = h[i];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(raw_empty(buf));
+                mbar_arrive(vb_full(buf));
+            }
+        }
+    } else {
+        // =============================== pass 2: horizontal filter + normalise + patchify ===============================
+        const int t = tid - kPtRowWarps * 32;   // 0..127: pixels t and t + 128 of the 16 x 16 patch
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+            const int buf = it & 1;
+            mbar_wait(vb_full(buf), static_cast<uint32_t>(it >> 1) & 1u);
+            const int* pr = params + (it & 3) * kPtParamInts;
+            const int frame = pr[0], py = pr[1], px = pr[2], b0 = pr[3];
+            const float* vbuf = vb0 + buf * vb_floats;
+            const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px;
+#pragma unroll
+            for (int half = 0; half < 2 && !(debug & 1); ++half) {
+                const int pix = t + half * 128;
+                const int ky = pix >> 4, kx = pix & 15;
+                const int ox = px * 16 + kx;
+                const int x0 = s_xlo[ox], cnt = s_xcnt[ox];
+                const float* wx = s_xw + ox * p.xkmax;
+                const float* src = vbuf + static_cast<size_t>(ky) * p.sstride + (x0 * 3 - b0);
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const float w = wx[k];
+                    s0 = fmaf(w, src[3 * k], s0);
+                    s1 = fmaf(w, src[3 * k + 1], s1);
+                    s2 = fmaf(w, src[3 * k + 2], s2);
+                }
+                const float sm[3] = {s0, s1, s2};   // memory channel order
+                __nv_bfloat16* o = p.out + patch * 768 + ky * 16 + kx;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = p.bgr ? 2 - j : j;  // output (RGB) channel of memory channel j
+                    o[c * 256] = __float2bfloat16_rn((sm[j] * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(vb_empty(buf));
+        }
+    }
+}
+
+static int g_pre_tma = 1, g_pre_debug = 0;
+void set_preprocess_tma(int on) { g_pre_tma = on & 1; g_pre_debug = on >> 1; }
+
+// returns 1 if the TMA variant was launched, 0 if the input does not qualify, negative on error
+static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStream_t stream) {
+    if (!g_pre_tma || !p.vec) return 0;
+    // tile extent: input rows / bytes one 16 x 16 output patch depends on
+    const double sy = static_cast<double>(a.ty.in) / a.ty.out, sx = static_cast<double>(a.tx.in) / a.tx.out;
+    const double supy = sy >= 1.0 ? sy : 1.0, supx = sx >= 1.0 ? sx : 1.0;
+    int rows_tile = static_cast<int>(16 * sy + 2 * supy + 4);
+    if (rows_tile > a.h) rows_tile = a.h;
+    const int span_px = static_cast<int>(16 * sx + 2 * supx + 4);
+    const int nvec_max = (span_px * 3 + 15 + 15) / 16;
+    const int nbox = (nvec_max * 16 + 255) / 256;
+    if (rows_tile > 256) return 0;
+    // small tiles are bound by the per-tile hand-offs, not by bytes: measured cross-over near a 4x vertical reduction
+    if (sy < 4.0 && !(g_pre_debug & 4)) return 0;
+    p.sstride = nvec_max * 16 + 4;
+    const size_t smem = 2 * static_cast<size_t>(nbox) * rows_tile * 256 + 2 * static_cast<size_t>(16) * p.sstride * 4 +
+                        4 * kPtParamInts * 4 + 64 + 128 +
+                        (static_cast<size_t>(a.gh) * 16 * (a.ty.kmax + 2) + static_cast<size_t>(a.gw) * 16 * (a.tx.kmax + 2)) * 4;
+    if (smem > 227 * 1024) return 0;
+    CUtensorMap tmap;
+    int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows_tile);
+    if (rc) return rc;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CRE_CUDA_OK(cudaFuncSetAttribute(preprocess_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        smem_set = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles64 = static_cast<int64_t>(a.n) * a.gh * a.gw;
+    if (tiles64 > 0x7fffffff) return 0;
+    const int tiles = static_cast<int>(tiles64);
+    const int grid = tiles < sms ? tiles : sms;
+    LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
+    preprocess_tma_kernel<<<grid, kPtThreads, smem, stream>>>(tmap, p, rows_tile, nbox, tiles, g_pre_debug);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.n > 0 && a.gh > 0 && a.gw > 0, "preprocess: empty problem");
     CRE_REQUIRE(a.gh * 16 <= a.ty.out && a.gw * 16 <= a.tx.out, "preprocess: patch grid exceeds the resized image");
@@ -170,6 +409,10 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     p.xw = a.tx.w;
     p.xkmax = a.tx.kmax;
     p.vec = ((reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && a.row_pitch % 16 == 0 && a.frame_pitch % 16 == 0) ? 1 : 0;
+    {
+        const int rc = try_launch_preprocess_tma(a, p, stream);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     // widest band: (band output pixels) * scale + 2 * support, rounded up generously
     const double scale = static_cast<double>(a.tx.in) / a.tx.out;
     const double support = scale >= 1.0 ? scale : 1.0;
