@@ -152,14 +152,16 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
  * W' = W * gamma, c1 = row sums of W', c2 = b + W beta.  A statistics row is 2 * (dim / 128) + 4 floats:
  * [pivot, -, -, -, (mean_i, M2_i) of every 128-column slot]; dim = 768 | 1024.
  *   cre_row_stats:       x f32 [rows, dim] -> out_xb bf16 [rows, dim] = x - mean, out_stats (pivot = mean).
- *   cre_fold_ln_weights: w bf16 [n, k], gamma/beta f32 [k], bias f32 [n] or NULL -> out_w bf16 [n, k], out_c1/out_c2 f32 [n].
+ *   cre_fold_ln_weights: w bf16 [n, k], gamma/beta f32 [k], bias f32 [n] or NULL -> out_w bf16 [n, k], out_c1/out_c2 f32 [n];
+ *                        rows [0, scaled_rows) of all three outputs are multiplied by row_scale (head_dim^-0.5 on the q rows).
  *   cre_gemm_ln:         epilogue CRE_EPI_BF16 | CRE_EPI_GELU: out bf16 [m, n] = (gelu)(LN-folded A B^T), A = the centred bf16
  *                        rows, bias = c2, stats_in = their statistics rows (ln_dim = k);
  *                        epilogue CRE_EPI_RESID_LN (n == ln_dim, n % 256 == 0): out f32 [m, n] (in place) += scale * (A B^T + bias),
  *                        out_xb bf16 [m, n] = out - pivot (pivot = the row mean recorded in stats_in), stats_out = new rows. */
 int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_xb_dev, float* out_stats_dev, void* stream);
 int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
-                            int32_t k, void* out_w_dev, float* out_c1_dev, float* out_c2_dev, void* stream);
+                            int32_t k, int32_t scaled_rows, float row_scale, void* out_w_dev, float* out_c1_dev, float* out_c2_dev,
+                            void* stream);
 int32_t cre_gemm_ln(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t m, int32_t n, int32_t k, int32_t epilogue,
                     const float* bias_dev, const float* c1_dev, const float* scale_dev, const float* stats_in_dev, int32_t ln_dim,
                     float ln_eps, void* out_dev, void* out_xb_dev, float* stats_out_dev, int32_t cta_group, void* stream);

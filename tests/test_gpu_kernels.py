@@ -96,6 +96,10 @@ def test_gemm_layernorm_folded_consumer(engine_small, cg, m, n, dim, epi):
     wf, c1, c2 = eng.fold_ln_weights(w, gamma, beta, bias)
     assert rel_err(wf, w.float() * gamma) < 5e-3 and rel_err(c2, bias + w.float() @ beta) < 1e-5
     assert rel_err(c1, wf.float().sum(dim=1)) < 1e-5
+    ws, c1s, c2s = eng.fold_ln_weights(w, gamma, beta, bias, scaled_rows=min(n, 32), row_scale=0.125)   # q rows: exact 2^-3
+    rs = torch.ones(n, device=dev)
+    rs[:32] = 0.125
+    assert torch.equal(ws.float(), wf.float() * rs[:, None]) and torch.equal(c1s, c1 * rs) and torch.equal(c2s, c2 * rs)
     xb, stats = eng.row_stats(x)
     e = _lib.EPI_BF16 if epi == "bf16" else _lib.EPI_GELU
     out = eng.gemm_ln(xb, wf, e, stats, dim, bias=c2, c1=c1, cta_group=cg)

@@ -74,7 +74,7 @@ PROTOTYPES = {
     "cre_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "cre_layernorm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "cre_row_stats": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
-    "cre_fold_ln_weights": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cre_fold_ln_weights": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "cre_gemm_ln": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cre_set_cta_group": (_i32, [_i32]),

@@ -24,9 +24,9 @@ struct DevTable {
     float* w = nullptr;
     int kmax = 0, in = 0, out = 0;
 };
-constexpr int kRopeRowFloats = 36;   // 16 cos + 16 sin per axis position, padded to 36 floats (bank spreading in smem)
+// kRopeRowFloats (gemm_tcgen05.cuh): cos[16] | sin[16] | -sin[16] | pad per axis position
 struct RopeTable {
-    float* axis = nullptr;   // [(gh + gw), 36]: rows 0..gh-1 = y positions, rows gh.. = x positions; {cos[16], sin[16], pad[4]}
+    float* axis = nullptr;   // [(gh + gw), kRopeRowFloats]: rows 0..gh-1 = y positions, rows gh.. = x positions
 };
 
 bool cfg_ok(const cre_model_cfg* c) {
@@ -231,6 +231,8 @@ int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
         *t = it->second;
         return 0;
     }
+    CRE_REQUIRE((gh + gw) * kRopeRowFloats * 4 <= kRopeTableBytes, "rotary table for a %dx%d patch grid exceeds the kernel's %d bytes",
+                gh, gw, kRopeTableBytes);
     // The HF table is cos/sin of [y*f0..f15, x*f0..f15] tiled twice: per token only the 16 y-angles of its patch row and
     // the 16 x-angles of its patch column are distinct, so one small per-axis table serves every token.
     std::vector<float> tab(static_cast<size_t>(gh + gw) * kRopeRowFloats, 0.0f);
@@ -245,6 +247,7 @@ int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
             const float ang = two_pi * coord * inv_freq[k];
             row[k] = cosf(ang);
             row[16 + k] = sinf(ang);
+            row[32 + k] = -row[16 + k];
         }
     }
     RopeTable r;
@@ -267,6 +270,7 @@ GemmParams base_params(int M, int N, int K) {
 }
 
 int g_default_cg = 2;  // CTA pairs: less smem traffic per FLOP, measured 3-5 % faster in the full step
+constexpr float kQScale = 0.125f;   // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284); folded into the q rows
 int g_resid_ln_deep = 2;   // bit 0: attention-out projection, bit 1: MLP down projection use EPI_RESID_LN3 (1 x tile, 5 stages)
 int g_ln_fold = 1;     // 1: LayerNorm folded into the GEMMs (no LayerNorm kernel in the blocks); 0: separate LayerNorm launches
 
@@ -290,11 +294,11 @@ int build_folded_weights(cre_ctx* c) {
         take(c->fold_qkv[l], 3 * D);
         take(c->fold_up[l], F);
         int rc = launch_fold_ln_weights(c->w<__nv_bfloat16>(l, CRE_W_QKV), c->w<float>(l, CRE_LN1_G), c->w<float>(l, CRE_LN1_B),
-                                        c->w<float>(l, CRE_B_QKV), static_cast<int>(3 * D), static_cast<int>(D), c->fold_qkv[l].w,
-                                        c->fold_qkv[l].c1, c->fold_qkv[l].c2, nullptr);
+                                        c->w<float>(l, CRE_B_QKV), static_cast<int>(3 * D), static_cast<int>(D), static_cast<int>(D), kQScale,
+                                        c->fold_qkv[l].w, c->fold_qkv[l].c1, c->fold_qkv[l].c2, nullptr);
         if (rc) return rc;
         rc = launch_fold_ln_weights(c->w<__nv_bfloat16>(l, CRE_W_UP), c->w<float>(l, CRE_LN2_G), c->w<float>(l, CRE_LN2_B),
-                                    c->w<float>(l, CRE_B_UP), static_cast<int>(F), static_cast<int>(D), c->fold_up[l].w,
+                                    c->w<float>(l, CRE_B_UP), static_cast<int>(F), static_cast<int>(D), 0, 1.0f, c->fold_up[l].w,
                                     c->fold_up[l].c1, c->fold_up[l].c2, nullptr);
         if (rc) return rc;
     }
@@ -466,7 +470,7 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             p.tokens_per_frame = T;
             p.prefix_tokens = prefix;
             p.hidden = D;
-            p.q_scale = 0.125f;  // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284)
+            p.q_scale = fold ? 1.0f : kQScale;   // the folded q rows are pre-scaled
             if (fold) {
                 p.c1 = ctx->fold_qkv[l].c1;
                 p.ln_stats_in = ws.stats[0];
@@ -652,10 +656,11 @@ int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_x
 }
 
 int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
-                            int32_t k, void* out_w_dev, float* out_c1_dev, float* out_c2_dev, void* stream) {
+                            int32_t k, int32_t scaled_rows, float row_scale, void* out_w_dev, float* out_c1_dev, float* out_c2_dev,
+                            void* stream) {
     CRE_REQUIRE(w_dev != nullptr && gamma_dev != nullptr && beta_dev != nullptr && out_w_dev != nullptr && out_c1_dev != nullptr &&
                     out_c2_dev != nullptr, "fold_ln_weights: NULL argument");
-    return launch_fold_ln_weights(static_cast<const __nv_bfloat16*>(w_dev), gamma_dev, beta_dev, bias_dev, n, k,
+    return launch_fold_ln_weights(static_cast<const __nv_bfloat16*>(w_dev), gamma_dev, beta_dev, bias_dev, n, k, scaled_rows, row_scale,
                                   static_cast<__nv_bfloat16*>(out_w_dev), out_c1_dev, out_c2_dev, static_cast<cudaStream_t>(stream));
 }
 

@@ -123,20 +123,23 @@ int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat1
 }
 
 // One warp per output row n of a Linear that follows a LayerNorm: W' = bf16(W * gamma), c1 = row sum of the ROUNDED W'
-// (what the tensor core will multiply), c2 = bias + W beta.  Runs once per weight matrix at cre_create.
+// (what the tensor core will multiply), c2 = bias + W beta.  Rows [0, scaled_rows) are additionally multiplied by row_scale
+// (the attention's head_dim^-0.5 on the q rows; a power of two, so exact).  Runs once per weight matrix at cre_create.
 __global__ void __launch_bounds__(256) fold_ln_weights_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ bias,
-                                                              int n_rows, int k, __nv_bfloat16* __restrict__ wf,
+                                                              int n_rows, int k, int scaled_rows, float row_scale,
+                                                              __nv_bfloat16* __restrict__ wf,
                                                               float* __restrict__ c1, float* __restrict__ c2) {
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= n_rows) return;
     const int lane = threadIdx.x & 31;
     const __nv_bfloat16* wr = w + static_cast<size_t>(n) * k;
     __nv_bfloat16* wo = wf + static_cast<size_t>(n) * k;
+    const float rs = n < scaled_rows ? row_scale : 1.0f;
     float s1 = 0.0f, s2 = 0.0f;
     for (int j = lane; j < k; j += 32) {
         const float wv = __bfloat162float(wr[j]);
-        const __nv_bfloat16 f = __float2bfloat16_rn(wv * gamma[j]);
+        const __nv_bfloat16 f = __float2bfloat16_rn(wv * gamma[j] * rs);
         wo[j] = f;
         s1 += __bfloat162float(f);
         s2 = fmaf(beta[j], wv, s2);
@@ -145,15 +148,15 @@ __global__ void __launch_bounds__(256) fold_ln_weights_kernel(const __nv_bfloat1
     s2 = warp_sum(s2);
     if (lane == 0) {
         c1[n] = s1;
-        c2[n] = (bias != nullptr ? bias[n] : 0.0f) + s2;
+        c2[n] = ((bias != nullptr ? bias[n] : 0.0f) + s2) * rs;
     }
 }
 
 int launch_fold_ln_weights(const __nv_bfloat16* w, const float* gamma, const float* beta, const float* bias, int n_rows, int k,
-                           __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream) {
+                           int scaled_rows, float row_scale, __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream) {
     CRE_REQUIRE(n_rows > 0 && k > 0, "fold_ln_weights: empty matrix");
     LaunchScope scope(CRE_K_FOLD_LN, 4.0 * n_rows * k, stream);
-    fold_ln_weights_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(w, gamma, beta, bias, n_rows, k, wf, c1, c2);
+    fold_ln_weights_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(w, gamma, beta, bias, n_rows, k, scaled_rows, row_scale, wf, c1, c2);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }

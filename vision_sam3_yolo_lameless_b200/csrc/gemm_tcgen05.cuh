@@ -61,7 +61,7 @@ struct GemmParams {
     float ln_eps;
     int ldo2;            // EPI_RESID_LN: row stride of out_bf16
     // EPI_QKV
-    const float* rope_axis;  // [(grid_h + grid_w), 36] fp32: per-axis {cos[16], sin[16]} rows (y positions, then x positions)
+    const float* rope_axis;  // [(grid_h + grid_w), 52] fp32: per-axis {cos[16], sin[16], -sin[16]} rows (y positions, then x positions)
     int grid_h, grid_w;
     int tokens_per_frame, prefix_tokens, hidden;
     float q_scale;
@@ -90,8 +90,8 @@ constexpr bool epi_tma_store(int epi) {
 }
 constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
-constexpr int kRopeRowFloats = 36;
-constexpr int kRopeTableBytes = 12 * 1024;   // up to 85 axis rows (grid_h + grid_w), e.g. 37 + 37 at 592 x 592
+constexpr int kRopeRowFloats = 52;           // per axis position: cos[16] | sin[16] | -sin[16] | pad[4] (208 B: odd multiple of 16)
+constexpr int kRopeTableBytes = 16 * 1024;   // up to 78 axis rows (grid_h + grid_w), e.g. 37 + 37 at 592 x 592
 // the QKV kernel trades one pipeline stage for the rotary table in shared memory
 // EPI_RESID_LN keeps 2 (LN3: 1) x tiles + the bf16 tile, 4 KB each, per epilogue warp
 constexpr int ln_x_slots(int epi) { return epi == EPI_RESID_LN3 ? 1 : 2; }
@@ -329,6 +329,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===============================
+        // Vector-register copies of the per-column parameter pointers.  They are warp-uniform, and the compiler would otherwise
+        // address every LDG through uniform registers at the price of two R2UR per load (10 % of the QKV kernel's instructions).
+        uint32_t vzero;
+        asm volatile("mov.u32 %0, 0;" : "=r"(vzero));
+        const float* bias_v = p.bias + vzero;
+        const float* scale_v = p.scale + vzero;
+        const float* c1_v = (p.ln_stats_in != nullptr && p.c1 != nullptr ? p.c1 : p.bias) + vzero;   // unfolded: multiplied by nrd = 0
         const int quarter = warp & 3;          // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;      // which 128 accumulator columns
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
@@ -460,6 +467,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float4* tx = reinterpret_cast<const float4*>(tab + (p.grid_h + px) * kRopeRowFloats);
                 float rstd, nrd;
                 ln_row(row, row_ok, rstd, nrd);
+                const uint64_t rstd2 = pack2(rstd, rstd), nrd2 = pack2(nrd, nrd);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -469,52 +477,58 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tmem_ld32(taddr + hh * 64 + 32, b);
                     const int which = n0 / p.hidden;  // 0 = q, 1 = k, 2 = v
                     const bool rot = which < 2 && patch_row;
-                    const float qs = which == 0 ? p.q_scale : 1.0f;
                     tmem_ld_wait();
-                    float x1[32], x2[32];
+                    // packed column pairs: X1[i] = columns (2i, 2i+1) of the head's first half, X2[i] of its second half
+                    uint64_t X1[16], X2[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
-                        const float4 k1 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0) + j4);
-                        const float4 k2 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0 + 32) + j4);
-                        x1[4 * j4] = fmaf(rstd, __uint_as_float(a[4 * j4]), fmaf(nrd, k1.x, b1.x));
-                        x1[4 * j4 + 1] = fmaf(rstd, __uint_as_float(a[4 * j4 + 1]), fmaf(nrd, k1.y, b1.y));
-                        x1[4 * j4 + 2] = fmaf(rstd, __uint_as_float(a[4 * j4 + 2]), fmaf(nrd, k1.z, b1.z));
-                        x1[4 * j4 + 3] = fmaf(rstd, __uint_as_float(a[4 * j4 + 3]), fmaf(nrd, k1.w, b1.w));
-                        x2[4 * j4] = fmaf(rstd, __uint_as_float(b[4 * j4]), fmaf(nrd, k2.x, b2.x));
-                        x2[4 * j4 + 1] = fmaf(rstd, __uint_as_float(b[4 * j4 + 1]), fmaf(nrd, k2.y, b2.y));
-                        x2[4 * j4 + 2] = fmaf(rstd, __uint_as_float(b[4 * j4 + 2]), fmaf(nrd, k2.z, b2.z));
-                        x2[4 * j4 + 3] = fmaf(rstd, __uint_as_float(b[4 * j4 + 3]), fmaf(nrd, k2.w, b2.w));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + j4);
+                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(bias_v + n0 + 32) + j4);
+                        const float4 k1 = __ldg(reinterpret_cast<const float4*>(c1_v + n0) + j4);
+                        const float4 k2 = __ldg(reinterpret_cast<const float4*>(c1_v + n0 + 32) + j4);
+                        // rstd * acc + (nrd * c1 + c2), two columns per FFMA2
+                        X1[2 * j4] = fma2(rstd2, pack2(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1])),
+                                          fma2(nrd2, pack2(k1.x, k1.y), pack2(b1.x, b1.y)));
+                        X1[2 * j4 + 1] = fma2(rstd2, pack2(__uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3])),
+                                              fma2(nrd2, pack2(k1.z, k1.w), pack2(b1.z, b1.w)));
+                        X2[2 * j4] = fma2(rstd2, pack2(__uint_as_float(b[4 * j4]), __uint_as_float(b[4 * j4 + 1])),
+                                          fma2(nrd2, pack2(k2.x, k2.y), pack2(b2.x, b2.y)));
+                        X2[2 * j4 + 1] = fma2(rstd2, pack2(__uint_as_float(b[4 * j4 + 2]), __uint_as_float(b[4 * j4 + 3])),
+                                              fma2(nrd2, pack2(k2.z, k2.w), pack2(b2.z, b2.w)));
                     }
                     if (rot) {
-                        // element j of each half pairs with angle j: j < 16 -> y-angle j, j >= 16 -> x-angle j - 16
+                        // element j of each half pairs with angle j: j < 16 -> y-angle j, j >= 16 -> x-angle j - 16;
+                        // (u, v) -> (u cos - v sin, v cos + u sin)  =  q*cos + rotate_half(q)*sin
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 c4 = j4 < 4 ? ty[j4] : tx[j4 - 4];
-                            const float4 s4 = j4 < 4 ? ty[4 + j4] : tx[j4];
-                            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                            const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int j = j4 * 4 + e;
-                                const float u = x1[j], v = x2[j];
-                                x1[j] = u * cc[e] - v * ss[e];   // q*cos + rotate_half(q)*sin, first half
-                                x2[j] = v * cc[e] + u * ss[e];   // second half
-                            }
+                            const float4* t4 = j4 < 4 ? ty + j4 : tx + (j4 - 4);
+                            const float4 c4 = t4[0], s4 = t4[4], n4 = t4[8];
+                            const uint64_t u0 = X1[2 * j4], u1 = X1[2 * j4 + 1], v0 = X2[2 * j4], v1 = X2[2 * j4 + 1];
+                            X1[2 * j4] = fma2(v0, pack2(n4.x, n4.y), mul2(u0, pack2(c4.x, c4.y)));
+                            X1[2 * j4 + 1] = fma2(v1, pack2(n4.z, n4.w), mul2(u1, pack2(c4.z, c4.w)));
+                            X2[2 * j4] = fma2(u0, pack2(s4.x, s4.y), mul2(v0, pack2(c4.x, c4.y)));
+                            X2[2 * j4 + 1] = fma2(u1, pack2(s4.z, s4.w), mul2(v1, pack2(c4.z, c4.w)));
                         }
+                    }
+                    if (which == 0 && p.q_scale != 1.0f) {   // unfolded weights only: the folded q rows carry head_dim^-0.5 already
+                        const uint64_t qs2 = pack2(p.q_scale, p.q_scale);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { X1[i] = mul2(X1[i], qs2); X2[i] = mul2(X2[i], qs2); }
+                    }
+                    uint32_t o1[16], o2[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float lo, hi;
+                        unpack2(X1[i], lo, hi);
+                        o1[i] = pack_bf16x2(lo, hi);
+                        unpack2(X2[i], lo, hi);
+                        o2[i] = pack_bf16x2(lo, hi);
                     }
                     stage_begin();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        stage_store(j, make_uint4(pack_bf16x2(x1[8 * j] * qs, x1[8 * j + 1] * qs),
-                                                  pack_bf16x2(x1[8 * j + 2] * qs, x1[8 * j + 3] * qs),
-                                                  pack_bf16x2(x1[8 * j + 4] * qs, x1[8 * j + 5] * qs),
-                                                  pack_bf16x2(x1[8 * j + 6] * qs, x1[8 * j + 7] * qs)));
-                        stage_store(j + 4, make_uint4(pack_bf16x2(x2[8 * j] * qs, x2[8 * j + 1] * qs),
-                                                      pack_bf16x2(x2[8 * j + 2] * qs, x2[8 * j + 3] * qs),
-                                                      pack_bf16x2(x2[8 * j + 4] * qs, x2[8 * j + 5] * qs),
-                                                      pack_bf16x2(x2[8 * j + 6] * qs, x2[8 * j + 7] * qs)));
+                        stage_store(j, make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]));
+                        stage_store(j + 4, make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]));
                     }
                     stage_commit(n0, row_base);
                 }
@@ -522,6 +536,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // EPI_BF16 / EPI_GELU: 64-column chunks, bf16 out
                 float rstd, nrd;
                 ln_row(row, row_ok, rstd, nrd);
+                const uint64_t rstd2 = pack2(rstd, rstd), nrd2 = pack2(nrd, nrd);
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
@@ -541,21 +556,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint32_t o[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+                        uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;   // nrd * c1 + c2 for 8 columns (packed pairs)
                         if (p.bias != nullptr) {
-                            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-                            b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
-                            if (p.ln_stats_in != nullptr) {
-                                const float4 k1 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0) + j4);
-                                const float4 k2 = __ldg(reinterpret_cast<const float4*>(p.c1 + n0 + 32) + j4);
-                                b1.x = fmaf(nrd, k1.x, b1.x); b1.y = fmaf(nrd, k1.y, b1.y); b1.z = fmaf(nrd, k1.z, b1.z); b1.w = fmaf(nrd, k1.w, b1.w);
-                                b2.x = fmaf(nrd, k2.x, b2.x); b2.y = fmaf(nrd, k2.y, b2.y); b2.z = fmaf(nrd, k2.z, b2.z); b2.w = fmaf(nrd, k2.w, b2.w);
-                            }
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + j4);
+                            const float4 b2 = __ldg(reinterpret_cast<const float4*>(bias_v + n0 + 32) + j4);
+                            const float4 k1 = __ldg(reinterpret_cast<const float4*>(c1_v + n0) + j4);
+                            const float4 k2 = __ldg(reinterpret_cast<const float4*>(c1_v + n0 + 32) + j4);
+                            t0 = fma2(nrd2, pack2(k1.x, k1.y), pack2(b1.x, b1.y));
+                            t1 = fma2(nrd2, pack2(k1.z, k1.w), pack2(b1.z, b1.w));
+                            t2 = fma2(nrd2, pack2(k2.x, k2.y), pack2(b2.x, b2.y));
+                            t3 = fma2(nrd2, pack2(k2.z, k2.w), pack2(b2.z, b2.w));
                         }
-                        float v0 = fmaf(rstd, __uint_as_float(a[4 * j4]), b1.x), v1 = fmaf(rstd, __uint_as_float(a[4 * j4 + 1]), b1.y);
-                        float v2 = fmaf(rstd, __uint_as_float(a[4 * j4 + 2]), b1.z), v3 = fmaf(rstd, __uint_as_float(a[4 * j4 + 3]), b1.w);
-                        float w0 = fmaf(rstd, __uint_as_float(b[4 * j4]), b2.x), w1 = fmaf(rstd, __uint_as_float(b[4 * j4 + 1]), b2.y);
-                        float w2 = fmaf(rstd, __uint_as_float(b[4 * j4 + 2]), b2.z), w3 = fmaf(rstd, __uint_as_float(b[4 * j4 + 3]), b2.w);
+                        float v0, v1, v2, v3, w0, w1, w2, w3;
+                        unpack2(fma2(rstd2, pack2(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1])), t0), v0, v1);
+                        unpack2(fma2(rstd2, pack2(__uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3])), t1), v2, v3);
+                        unpack2(fma2(rstd2, pack2(__uint_as_float(b[4 * j4]), __uint_as_float(b[4 * j4 + 1])), t2), w0, w1);
+                        unpack2(fma2(rstd2, pack2(__uint_as_float(b[4 * j4 + 2]), __uint_as_float(b[4 * j4 + 3])), t3), w2, w3);
                         if constexpr (EPI == EPI_GELU) {
                             gelu2(v0, v1); gelu2(v2, v3); gelu2(w0, w1); gelu2(w2, w3);
                         }
@@ -613,8 +629,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const float4 xv = *reinterpret_cast<const float4*>(xrow + ((static_cast<uint32_t>(u) ^ r7) << 4));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + u);
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + u);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + u);
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale_v + n0) + u);
                         v[4 * u] = fmaf(sc.x, __uint_as_float(a[4 * u]) + b4.x, xv.x);
                         v[4 * u + 1] = fmaf(sc.y, __uint_as_float(a[4 * u + 1]) + b4.y, xv.y);
                         v[4 * u + 2] = fmaf(sc.z, __uint_as_float(a[4 * u + 2]) + b4.z, xv.z);
@@ -677,13 +693,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + j4);
                         x[4 * j4] = __uint_as_float(a[4 * j4]) + b4.x;
                         x[4 * j4 + 1] = __uint_as_float(a[4 * j4 + 1]) + b4.y;
                         x[4 * j4 + 2] = __uint_as_float(a[4 * j4 + 2]) + b4.z;
                         x[4 * j4 + 3] = __uint_as_float(a[4 * j4 + 3]) + b4.w;
                         if constexpr (EPI == EPI_RESID) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + j4);
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale_v + n0) + j4);
                             x[4 * j4] *= sc.x; x[4 * j4 + 1] *= sc.y; x[4 * j4 + 2] *= sc.z; x[4 * j4 + 3] *= sc.w;
                         }
                     }
@@ -735,7 +751,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     } else {  // EPI_PATCH
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + j4);
                             x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
                         }
                         if (row_ok) {

@@ -64,7 +64,7 @@ int launch_layernorm_bf16(const float* x, const float* g, const float* b, int ro
 // LayerNorm folding: seed statistics + centred bf16 copy of x; weight folding at context creation (elementwise.cu)
 int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, float* stats, cudaStream_t stream);
 int launch_fold_ln_weights(const __nv_bfloat16* w, const float* gamma, const float* beta, const float* bias, int n_rows, int k,
-                           __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream);
+                           int scaled_rows, float row_scale, __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream);
 // final LayerNorm + mean over the t tokens of each frame; tokens_out optional
 int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
                            float* frame_emb, float* tokens_out, cudaStream_t stream);

@@ -374,13 +374,15 @@ class ClipEmbedEngine:
         _lib.check(self.lib.cre_row_stats(x.data_ptr(), rows, dim, xb.data_ptr(), stats.data_ptr(), self._stream()), "cre_row_stats")
         return xb, stats
 
-    def fold_ln_weights(self, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    def fold_ln_weights(self, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                        scaled_rows: int = 0, row_scale: float = 1.0):
         """bf16 W [n, k] + LayerNorm (gamma, beta) [k] + bias [n] -> (bf16 W * gamma, c1 = its row sums, c2 = bias + W beta)."""
         n, k = w.shape
         wf = torch.empty_like(w)
         c1 = torch.empty(n, dtype=torch.float32, device=self.device)
         c2 = torch.empty(n, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.cre_fold_ln_weights(w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(bias), n, k, wf.data_ptr(),
+        _lib.check(self.lib.cre_fold_ln_weights(w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(bias), n, k, int(scaled_rows), float(row_scale),
+                                                wf.data_ptr(),
                                                 c1.data_ptr(), c2.data_ptr(), self._stream()), "cre_fold_ln_weights")
         return wf, c1, c2
 
