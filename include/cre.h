@@ -95,6 +95,18 @@ int32_t cre_preprocess_patchify(cre_ctx* ctx, const uint8_t* frames_dev, int32_t
                                 int32_t resize_w, const float mean[3], const float std_[3],
                                 void* out_patches_dev, void* stream);
 
+/* K1 on regions of interest (per-track crops, SURVEY.md section 8(f) #3: services/tracking-service/app/main.py:332-334 "in
+ * production, you'd extract per-track embeddings").  rois_dev: int32 [n_rois, 5] = {frame, x0, y0, x1, y1} (pixel box, x1 / y1
+ * exclusive, inside the frame, at least 1 x 1).  ROI r is processed exactly like the image frames[frame][y0:y1, x0:x1] would be
+ * by cre_preprocess_patchify (the HF processor resizes every crop to resize_h x resize_w) and lands in patch rows
+ * [r * P, (r + 1) * P).  The per-ROI antialias tables are built on the device into scratch_dev
+ * (cre_roi_scratch_bytes(n_rois, h, w, resize_h, resize_w) bytes, 256-byte aligned). */
+int64_t cre_roi_scratch_bytes(int32_t n_rois, int32_t h, int32_t w, int32_t resize_h, int32_t resize_w);
+int32_t cre_preprocess_patchify_roi(cre_ctx* ctx, const uint8_t* frames_dev, int32_t n_frames, int32_t h, int32_t w,
+                                    int64_t row_pitch, int64_t frame_pitch, int32_t bgr, const int32_t* rois_dev, int32_t n_rois,
+                                    int32_t resize_h, int32_t resize_w, const float mean[3], const float std_[3],
+                                    void* scratch_dev, int64_t scratch_bytes, void* out_patches_dev, void* stream);
+
 /* K2 + K3a. bf16 patch rows [n * grid_h * grid_w, 3*256] -> ViT forward -> final LayerNorm ->
  * mean over ALL tokens (cls + registers + patches) -> out_frame_emb_dev f32 [n, hidden].
  * If out_tokens_dev != NULL the final-normed hidden state f32 [n, T, hidden] is also written. */
@@ -184,7 +196,7 @@ enum cre_kernel_id {
     CRE_K_PREPROCESS = 0, CRE_K_FILL_PREFIX = 1, CRE_K_GEMM_PATCH = 2, CRE_K_LAYERNORM = 3, CRE_K_GEMM_QKV = 4,
     CRE_K_ATTENTION = 5, CRE_K_GEMM_RESID = 6, CRE_K_GEMM_GELU = 7, CRE_K_FINAL_NORM_MEAN = 8, CRE_K_POOL_CLIPS = 9,
     CRE_K_SPLIT_HI_LO = 10, CRE_K_FILL_TOPK = 11, CRE_K_GEMM_TOPK = 12, CRE_K_MERGE_TOPK = 13, CRE_K_GEMM_PLAIN = 14,
-    CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_KERNEL_IDS = 18
+    CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_K_ROI_TABLES = 18, CRE_KERNEL_IDS = 19
 };
 int64_t cre_kernel_launches(void);
 int32_t cre_profile_start(int32_t max_launches);

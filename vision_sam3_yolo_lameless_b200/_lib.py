@@ -25,7 +25,7 @@ BF16_KINDS = {W_PATCH, W_QKV, W_O, W_UP, W_DOWN}
 # enum cre_kernel_id
 KERNEL_NAMES = ["preprocess", "fill_prefix", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu",
                 "final_norm_mean", "pool_clips", "split_hi_lo", "fill_topk", "gemm_topk", "merge_topk", "gemm_plain",
-                "gallery_update", "row_stats", "fold_ln_weights"]
+                "gallery_update", "row_stats", "fold_ln_weights", "roi_tables"]
 # kernels whose `work` is FLOPs (tensor-bound); the others report bytes (HBM-bound)
 FLOP_KERNELS = {"gemm_patch", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu", "gemm_plain"}
 
@@ -65,6 +65,8 @@ PROTOTYPES = {
     "cre_destroy": (_i32, [_vp]),
     "cre_workspace_bytes": (_i64, [_cfgp, _i32, _i32, _i32]),
     "cre_preprocess_patchify": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _f3, _f3, _vp, _vp]),
+    "cre_roi_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    "cre_preprocess_patchify_roi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _i32, _i32, _i32, _f3, _f3, _vp, _i64, _vp, _vp]),
     "cre_vit_forward": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "cre_pool_clips": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "cre_gallery_scratch_bytes": (_i64, [_i32, _i32, _i32]),

@@ -414,6 +414,83 @@ int32_t cre_preprocess_patchify(cre_ctx* ctx, const uint8_t* frames_dev, int32_t
     return launch_preprocess(a, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// widest tap count any crop of an `in`-pixel axis can need when resized to `out` (build_resize_table's kmax for the whole axis)
+int roi_kmax(int in, int out) {
+    const float scale = static_cast<float>(in) / static_cast<float>(out);
+    return static_cast<int>(ceilf(scale >= 1.0f ? scale : 1.0f)) * 2 + 1;
+}
+struct RoiScratch {
+    int32_t *ylo, *ycnt, *xlo, *xcnt;
+    float *yw, *xw;
+    int ykmax, xkmax;
+    int64_t total;
+};
+RoiScratch carve_roi(int n_rois, int h, int w, int oh, int ow, void* base) {
+    RoiScratch r;
+    r.ykmax = roi_kmax(h, oh);
+    r.xkmax = roi_kmax(w, ow);
+    uint8_t* p = static_cast<uint8_t*>(base);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { uint8_t* q = p + off; off += align_up(bytes, kAlign); return q; };
+    r.ylo = reinterpret_cast<int32_t*>(take(4LL * n_rois * oh));
+    r.ycnt = reinterpret_cast<int32_t*>(take(4LL * n_rois * oh));
+    r.xlo = reinterpret_cast<int32_t*>(take(4LL * n_rois * ow));
+    r.xcnt = reinterpret_cast<int32_t*>(take(4LL * n_rois * ow));
+    r.yw = reinterpret_cast<float*>(take(4LL * n_rois * oh * r.ykmax));
+    r.xw = reinterpret_cast<float*>(take(4LL * n_rois * ow * r.xkmax));
+    r.total = off;
+    return r;
+}
+}  // namespace
+
+int64_t cre_roi_scratch_bytes(int32_t n_rois, int32_t h, int32_t w, int32_t resize_h, int32_t resize_w) {
+    if (n_rois <= 0 || h <= 0 || w <= 0 || resize_h < 16 || resize_w < 16) {
+        set_error("roi_scratch_bytes: n_rois=%d %dx%d -> %dx%d", n_rois, h, w, resize_h, resize_w);
+        return -1;
+    }
+    return carve_roi(n_rois, h, w, resize_h / 16 * 16, resize_w / 16 * 16, nullptr).total;
+}
+
+int32_t cre_preprocess_patchify_roi(cre_ctx* ctx, const uint8_t* frames_dev, int32_t n_frames, int32_t h, int32_t w,
+                                    int64_t row_pitch, int64_t frame_pitch, int32_t bgr, const int32_t* rois_dev, int32_t n_rois,
+                                    int32_t resize_h, int32_t resize_w, const float mean[3], const float std_[3], void* scratch_dev,
+                                    int64_t scratch_bytes, void* out_patches_dev, void* stream_) {
+    CRE_REQUIRE(ctx != nullptr && frames_dev != nullptr && rois_dev != nullptr && scratch_dev != nullptr && out_patches_dev != nullptr,
+                "preprocess_roi: NULL argument");
+    CRE_REQUIRE(n_frames > 0 && n_rois > 0 && h > 0 && w > 0 && resize_h >= 16 && resize_w >= 16,
+                "preprocess_roi: bad sizes frames=%d rois=%d %dx%d -> %dx%d", n_frames, n_rois, h, w, resize_h, resize_w);
+    CRE_REQUIRE(ctx->cfg.patch == 16, "preprocess_roi: patch size must be 16");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 255) == 0, "preprocess_roi: scratch must be 256-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int gh = resize_h / 16, gw = resize_w / 16;
+    RoiScratch sc = carve_roi(n_rois, h, w, gh * 16, gw * 16, scratch_dev);
+    CRE_REQUIRE(scratch_bytes >= sc.total, "preprocess_roi: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)sc.total);
+    int rc = launch_build_roi_tables(rois_dev, n_rois, gh * 16, gw * 16, sc.ykmax, sc.xkmax, sc.ylo, sc.ycnt, sc.yw, sc.xlo, sc.xcnt, sc.xw,
+                                     stream);
+    if (rc) return rc;
+    PreprocArgs a;
+    a.frames = frames_dev;
+    a.n = n_frames;
+    a.h = h;
+    a.w = w;
+    a.row_pitch = row_pitch;
+    a.frame_pitch = frame_pitch;
+    a.bgr = bgr;
+    a.gh = gh;
+    a.gw = gw;
+    for (int i = 0; i < 3; ++i) {
+        a.mean[i] = mean[i];
+        a.inv_std[i] = 1.0f / std_[i];
+    }
+    a.out = static_cast<__nv_bfloat16*>(out_patches_dev);
+    a.ty = {sc.ylo, sc.ycnt, sc.yw, sc.ykmax, h, gh * 16};      // in / out: the widest crop sizes the shared-memory band
+    a.tx = {sc.xlo, sc.xcnt, sc.xw, sc.xkmax, w, gw * 16};
+    a.rois = rois_dev;
+    a.n_rois = n_rois;
+    return launch_preprocess(a, stream);
+}
+
 int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_t grid_h, int32_t grid_w,
                         void* workspace_dev, int64_t workspace_bytes, float* out_frame_emb_dev, float* out_tokens_dev,
                         void* stream_) {

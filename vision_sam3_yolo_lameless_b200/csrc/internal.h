@@ -96,7 +96,11 @@ struct PreprocArgs {
     float mean[3], inv_std[3];
     __nv_bfloat16* out;
     ResizeTable ty, tx;
+    const int32_t* rois = nullptr;   // [n_rois, 5] = {frame, x0, y0, x1, y1}; ty / tx then hold one table block per ROI
+    int n_rois = 0;
 };
+int launch_build_roi_tables(const int32_t* rois, int n_rois, int oh, int ow, int ykmax, int xkmax, int32_t* ylo, int32_t* ycnt,
+                            float* yw, int32_t* xlo, int32_t* xcnt, float* xw, cudaStream_t stream);
 int launch_preprocess(const PreprocArgs& a, cudaStream_t stream);
 
 }  // namespace cre

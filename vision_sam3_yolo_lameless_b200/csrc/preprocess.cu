@@ -35,6 +35,9 @@ struct PreParams {
     int ykmax, xkmax;
     int sstride;  // floats per vertically-filtered row in shared memory
     int vec;      // 1: 16-byte aligned rows, vector loads allowed
+    // region-of-interest mode (cre_preprocess_patchify_roi): blockIdx.z = ROI, rois[5 * z] = {frame, x0, y0, x1, y1}; the six
+    // tables above then hold one block per ROI (oh / ow entries, oh * ykmax / ow * xkmax weights), built by build_roi_tables_kernel
+    const int32_t* rois;
 };
 
 // byte j of `word` -> the float 1 + b * 2^-15 (bits 0x3F80bb00) with ONE byte-permute: no shift / mask / int->float
@@ -46,25 +49,38 @@ __device__ __forceinline__ float byte_as_unit_float(uint32_t word, uint32_t sele
 
 __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PreParams p) {
     extern __shared__ __align__(16) float vbuf[];  // [16][sstride]
-    const int band = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
+    const int band = blockIdx.x, py = blockIdx.y;
+    int frame = blockIdx.z, cx0 = 0, cy0 = 0;   // crop origin inside the frame (ROI mode)
+    const int32_t *t_ylo = p.ylo, *t_ycnt = p.ycnt, *t_xlo = p.xlo, *t_xcnt = p.xcnt;
+    const float *t_yw = p.yw, *t_xw = p.xw;
+    if (p.rois != nullptr) {
+        const int32_t* roi = p.rois + 5 * blockIdx.z;
+        frame = roi[0];
+        cx0 = roi[1];
+        cy0 = roi[2];
+        const size_t oh = static_cast<size_t>(p.gh) * 16, ow = static_cast<size_t>(p.gw) * 16;
+        t_ylo += blockIdx.z * oh; t_ycnt += blockIdx.z * oh; t_yw += blockIdx.z * oh * p.ykmax;
+        t_xlo += blockIdx.z * ow; t_xcnt += blockIdx.z * ow; t_xw += blockIdx.z * ow * p.xkmax;
+    }
     const int px0 = band * kBandPatches;
     const int npatch = min(kBandPatches, p.gw - px0);
     const int ox0 = px0 * 16, ox1 = ox0 + npatch * 16;  // output column range [ox0, ox1)
-    const int x_lo = p.xlo[ox0];
-    const int x_hi = p.xlo[ox1 - 1] + p.xcnt[ox1 - 1];
-    const int b0 = p.vec ? ((x_lo * 3) & ~15) : x_lo * 3;  // first byte column staged
+    const int x_lo = t_xlo[ox0];
+    const int x_hi = t_xlo[ox1 - 1] + t_xcnt[ox1 - 1];
+    // first byte column staged, relative to the crop origin; 16-byte aligned in the FRAME row when vector loads are allowed
+    const int b0 = p.vec ? ((((cx0 + x_lo) * 3) & ~15) - cx0 * 3) : x_lo * 3;
     const int nbytes = x_hi * 3 - b0;
     const int nvec = (nbytes + 15) >> 4;
-    const int row_bytes = p.w * 3;
-    const uint8_t* fbase = p.frames + static_cast<int64_t>(frame) * p.frame_pitch;
+    const int row_bytes = (p.w - cx0) * 3;      // readable bytes of a frame row from the crop origin on
+    const uint8_t* fbase = p.frames + static_cast<int64_t>(frame) * p.frame_pitch + static_cast<int64_t>(cy0) * p.row_pitch + cx0 * 3;
     const int nthreads = blockDim.x;
 
     // ---- pass 1: vertical filter (each item = one output row x one 16-byte column group) ----
     for (int item = threadIdx.x; item < 16 * nvec; item += nthreads) {
         const int r = item / nvec, v = item - r * nvec;
         const int oy = py * 16 + r;
-        const int y0 = p.ylo[oy], cnt = p.ycnt[oy];
-        const float* wy = p.yw + static_cast<size_t>(oy) * p.ykmax;
+        const int y0 = t_ylo[oy], cnt = t_ycnt[oy];
+        const float* wy = t_yw + static_cast<size_t>(oy) * p.ykmax;
         const int col = b0 + v * 16;
         float acc[16];
         const uint8_t* src = fbase + static_cast<int64_t>(y0) * p.row_pitch + col;
@@ -121,19 +137,19 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
     for (int t = threadIdx.x; t < nout; t += nthreads) {
         const int pl = t >> 8, ky = (t >> 4) & 15, kx = t & 15;
         const int ox = (px0 + pl) * 16 + kx;
-        const int x0 = __ldg(p.xlo + ox), cnt = __ldg(p.xcnt + ox);
-        const float* wx = p.xw + static_cast<size_t>(ox) * p.xkmax;
+        const int x0 = t_xlo[ox], cnt = t_xcnt[ox];
+        const float* wx = t_xw + static_cast<size_t>(ox) * p.xkmax;
         const float* src = vbuf + static_cast<size_t>(ky) * p.sstride + (x0 * 3 - b0);
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 4
         for (int k = 0; k < cnt; ++k) {
-            const float w = __ldg(wx + k);
+            const float w = wx[k];
             s0 = fmaf(w, src[3 * k], s0);
             s1 = fmaf(w, src[3 * k + 1], s1);
             s2 = fmaf(w, src[3 * k + 2], s2);
         }
         const float sm[3] = {s0, s1, s2};   // memory channel order
-        const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px0 + pl;
+        const size_t patch = (static_cast<size_t>(blockIdx.z) * p.gh + py) * p.gw + px0 + pl;
         __nv_bfloat16* o = p.out + patch * 768 + ky * 16 + kx;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -141,6 +157,57 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
             o[c * 256] = __float2bfloat16_rn((sm[j] * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c]);
         }
     }
+}
+
+// Separable antialias tables for every region of interest: the arithmetic of build_resize_table (api.cu; aten
+// _compute_indices_min_size_weights_aa, triangle filter) in the same operation order, without FMA contraction, so that a ROI
+// covering the whole frame reproduces the cached full-frame tables bit for bit.  One thread per (ROI, output index) of both axes.
+__global__ void build_roi_tables_kernel(const int32_t* __restrict__ rois, int n_rois, int oh, int ow, int ykmax, int xkmax,
+                                        int32_t* __restrict__ ylo, int32_t* __restrict__ ycnt, float* __restrict__ yw,
+                                        int32_t* __restrict__ xlo, int32_t* __restrict__ xcnt, float* __restrict__ xw) {
+    const int per = oh + ow;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= static_cast<int64_t>(n_rois) * per) return;
+    const int r = static_cast<int>(gid / per), e = static_cast<int>(gid % per);
+    const bool is_y = e < oh;
+    const int i = is_y ? e : e - oh;
+    const int32_t* roi = rois + 5 * r;
+    const int in = is_y ? roi[4] - roi[2] : roi[3] - roi[1];
+    const int out = is_y ? oh : ow, kmax = is_y ? ykmax : xkmax;
+    const float scale = __fdiv_rn(static_cast<float>(in), static_cast<float>(out));
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? __fdiv_rn(1.0f, scale) : 1.0f;
+    const float center = __fmul_rn(scale, __fadd_rn(static_cast<float>(i), 0.5f));
+    int xmin = static_cast<int>(__fadd_rn(__fsub_rn(center, support), 0.5f));
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(__fadd_rn(__fadd_rn(center, support), 0.5f));
+    if (xmax > in) xmax = in;
+    const int xsize = xmax - xmin;
+    float* wi = (is_y ? yw : xw) + (static_cast<size_t>(r) * out + i) * kmax;
+    float total = 0.0f;
+    for (int j = 0; j < kmax; ++j) {
+        float v = 0.0f;
+        if (j < xsize) {
+            const float x = fabsf(__fmul_rn(__fadd_rn(__fsub_rn(static_cast<float>(j + xmin), center), 0.5f), invscale));
+            v = x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f;
+            total = __fadd_rn(total, v);
+        }
+        wi[j] = v;
+    }
+    if (total != 0.0f)
+        for (int j = 0; j < xsize && j < kmax; ++j) wi[j] = __fdiv_rn(wi[j], total);
+    (is_y ? ylo : xlo)[static_cast<size_t>(r) * out + i] = xmin;
+    (is_y ? ycnt : xcnt)[static_cast<size_t>(r) * out + i] = xsize < kmax ? xsize : kmax;
+}
+
+int launch_build_roi_tables(const int32_t* rois, int n_rois, int oh, int ow, int ykmax, int xkmax, int32_t* ylo, int32_t* ycnt,
+                            float* yw, int32_t* xlo, int32_t* xcnt, float* xw, cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(n_rois) * (oh + ow);
+    LaunchScope scope(CRE_K_ROI_TABLES, 4.0 * total * (ykmax + xkmax), stream);
+    build_roi_tables_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(rois, n_rois, oh, ow, ykmax, xkmax, ylo, ycnt,
+                                                                                             yw, xlo, xcnt, xw);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 // =====================================================================================================================
@@ -409,7 +476,8 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     p.xw = a.tx.w;
     p.xkmax = a.tx.kmax;
     p.vec = ((reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && a.row_pitch % 16 == 0 && a.frame_pitch % 16 == 0) ? 1 : 0;
-    {
+    p.rois = a.rois;
+    if (a.rois == nullptr) {
         const int rc = try_launch_preprocess_tma(a, p, stream);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
@@ -417,7 +485,7 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     const double scale = static_cast<double>(a.tx.in) / a.tx.out;
     const double support = scale >= 1.0 ? scale : 1.0;
     const int span_px = static_cast<int>(kBandPatches * 16 * scale + 2 * support + 4);
-    int sstride = ((span_px * 3 + 15 + 15) / 16) * 16 + 16;
+    int sstride = ((span_px * 3 + 15 + 15) / 16) * 16 + 16 + (a.rois != nullptr ? 16 : 0);   // ROI: the crop origin shifts the alignment
     sstride += 4;  // de-phase the 16 rows across shared-memory banks
     p.sstride = sstride;
     const size_t smem = static_cast<size_t>(16) * sstride * sizeof(float);
@@ -427,12 +495,13 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
         CRE_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         smem_set = smem;
     }
-    dim3 grid((a.gw + kBandPatches - 1) / kBandPatches, a.gh, a.n);
+    dim3 grid((a.gw + kBandPatches - 1) / kBandPatches, a.gh, a.rois != nullptr ? a.n_rois : a.n);
     // two balanced rounds of the vertical pass: 16 rows x nvec column groups over the block
     const int nvec_max = (span_px * 3 + 15 + 15) / 16;
     int threads = ((16 * nvec_max + 1) / 2 + 31) / 32 * 32;
     threads = threads < 128 ? 128 : (threads > kPreThreads ? kPreThreads : threads);
-    LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
+    LaunchScope scope(CRE_K_PREPROCESS, a.rois != nullptr ? static_cast<double>(a.n_rois) * 1536.0 * a.gh * a.gw
+                                                          : static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
     preprocess_kernel<<<grid, threads, smem, stream>>>(p);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;

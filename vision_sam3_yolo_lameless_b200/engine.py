@@ -216,6 +216,43 @@ class ClipEmbedEngine:
             "cre_preprocess_patchify")
         return out
 
+    def preprocess_rois(self, frames: torch.Tensor, rois, bgr: bool = True) -> torch.Tensor:
+        """uint8 [n, H, W, 3] on the device + boxes [(frame, x0, y0, x1, y1), ...] -> bf16 patch rows [n_rois * P, 768]: every box is
+        cropped and resized exactly as the image frames[frame][y0:y1, x0:x1] would be (K1 in region-of-interest mode)."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
+            raise ValueError("frames must be a CUDA uint8 tensor [n, H, W, 3]")
+        if frames.stride(3) != 1 or frames.stride(2) != 3:
+            frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        boxes = np.asarray(rois, dtype=np.int64).reshape(-1, 5)
+        if boxes.shape[0] == 0:
+            raise ValueError("no regions of interest")
+        if boxes.shape[0] > self.max_frames:
+            raise ValueError(f"{boxes.shape[0]} regions > max_frames={self.max_frames}")
+        f, x0, y0, x1, y1 = boxes.T
+        if ((f < 0) | (f >= n) | (x0 < 0) | (y0 < 0) | (x1 > w) | (y1 > h) | (x1 <= x0) | (y1 <= y0)).any():
+            raise ValueError("regions must be non-empty boxes inside their frame: (frame, x0, y0, x1, y1), x1 / y1 exclusive")
+        rois_dev = torch.from_numpy(boxes.astype(np.int32)).to(self.device)
+        need = _lib.check_size(self.lib.cre_roi_scratch_bytes(boxes.shape[0], h, w, self.resize[0], self.resize[1]), "cre_roi_scratch_bytes")
+        if getattr(self, "_roi_scratch", None) is None or self._roi_scratch.numel() < need:
+            self._roi_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = self.patches[: boxes.shape[0] * self.grid[0] * self.grid[1]]
+        _lib.check(self.lib.cre_preprocess_patchify_roi(
+            self._ctx, frames.data_ptr(), n, h, w, frames.stride(1), frames.stride(0), 1 if bgr else 0, rois_dev.data_ptr(),
+            boxes.shape[0], self.resize[0], self.resize[1], self._mean, self._std, self._roi_scratch.data_ptr(),
+            self._roi_scratch.numel(), out.data_ptr(), self._stream()), "cre_preprocess_patchify_roi")
+        return out
+
+    def embed_rois(self, frames: torch.Tensor, rois, bgr: bool = True) -> torch.Tensor:
+        """Per-box embeddings f32 [n_rois, D] (crop -> HF-processor resize -> ViT -> token mean), chunked by max_frames."""
+        boxes = np.asarray(rois, dtype=np.int64).reshape(-1, 5)
+        out = torch.empty((boxes.shape[0], self.cfg.hidden), dtype=torch.float32, device=self.device)
+        for s in range(0, boxes.shape[0], self.max_frames):
+            chunk = boxes[s:s + self.max_frames]
+            patches = self.preprocess_rois(frames, chunk, bgr=bgr)
+            self.forward_patches(patches, chunk.shape[0], out=out[s:s + chunk.shape[0]])
+        return out
+
     def forward_patches(self, patches: torch.Tensor, n: int, want_tokens: bool = False,
                         out: Optional[torch.Tensor] = None):
         """bf16 patch rows -> f32 frame embeddings [n, D] (final LayerNorm + mean over all tokens)."""
