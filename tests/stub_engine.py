@@ -24,6 +24,12 @@ class StubEngine:
 
     embed_frames = embed_host_frames
 
+    def embed_rois(self, frames, rois, bgr=True):
+        frames = frames.numpy() if isinstance(frames, torch.Tensor) else np.asarray(frames)
+        self.calls.append(("rois", len(rois)))
+        out = [self.embed_host_frames(frames[f:f + 1, y0:y1, x0:x1], bgr=bgr)[0] for f, x0, y0, x1, y1 in np.asarray(rois)]
+        return torch.stack(out)
+
     def pool_clips(self, frame_emb, clip_offsets):
         offs = np.asarray(clip_offsets)
         mean = reid_ref.clip_mean(frame_emb.numpy(), offs)

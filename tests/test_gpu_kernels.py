@@ -186,6 +186,31 @@ def test_preprocess_plain_bilinear_would_fail(engine_small):
     assert np.abs(out - preprocess_ref.patchify(plain.numpy())).max() > 0.5
 
 
+def test_preprocess_rois_vs_oracle(engine_small):
+    """K1 in region-of-interest mode == the oracle on the numpy crop; a ROI covering the whole frame reproduces the full-frame
+    call bit for bit (the device-built tables equal the cached host tables)."""
+    eng, dev = engine_small, engine_small.device
+    fr = common.smooth_frames(2, 720, 1280, seed=12)
+    fr[1] = common.noise_frames(1, 720, 1280, seed=13)[0]
+    frd = torch.from_numpy(fr).to(dev)
+    rois = [(0, 100, 50, 500, 400), (1, 0, 0, 1280, 720), (1, 601, 333, 777, 700), (0, 1000, 500, 1280, 720), (0, 37, 411, 150, 500),
+            (1, 3, 7, 4, 8), (0, 0, 0, 1280, 720)]
+    out = eng.preprocess_rois(frd, rois).clone().view(len(rois), 196, 768)
+    for i, (f, x0, y0, x1, y1) in enumerate(rois):
+        ref = preprocess_ref.patchify(preprocess_ref.preprocess(np.ascontiguousarray(fr[f:f + 1, y0:y1, x0:x1]), bgr=True))
+        err = (out[i].float().cpu() - torch.from_numpy(ref)).abs().max().item()
+        assert err < 1.2e-2, (i, err)
+    whole = eng.preprocess(frd).view(2, 196, 768)
+    assert torch.equal(out[1], whole[1]) and torch.equal(out[6], whole[0])
+    unaligned = torch.zeros(fr.size + 1, dtype=torch.uint8, device=dev)       # scalar-load path, same bits
+    unaligned[1:] = frd.reshape(-1)
+    assert torch.equal(eng.preprocess_rois(unaligned[1:].view(2, 720, 1280, 3), rois).view(len(rois), 196, 768), out)
+    with pytest.raises(ValueError):
+        eng.preprocess_rois(frd, [(0, 10, 10, 10, 50)])
+    with pytest.raises(ValueError):
+        eng.preprocess_rois(frd, [(2, 0, 0, 10, 10)])
+
+
 def test_preprocess_pitched_and_unaligned_input(engine_small):
     """Row pitch > 3*w and a base pointer that is not 16-byte aligned (scalar-load path) give identical results."""
     dev = engine_small.device

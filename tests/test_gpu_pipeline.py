@@ -184,3 +184,25 @@ def test_knn_graph_vs_reference_golden(engine_b, golden):
     assert_knn_equivalent(ei, ew, want["edge_index"], want["edge_weights"], emb, 5)
     ei2, ew2 = GraphBuilder(eng).compute_knn_edges(emb[:4])
     assert_knn_equivalent(ei2, ew2, want["small_edge_index"], want["small_edge_weights"], emb[:4], 3)
+
+
+def test_track_crop_embeddings_vs_reference_golden(engine_b, golden, tmp_path):
+    """per-box embeddings through K1's region-of-interest mode match the REFERENCE's extract_embedding on the numpy
+    crop (tests/golden/roi_crops.npz), and extract_track_embeddings averages a track's boxes like a clip."""
+    from oracle.make_golden_roi import ROI_CASES, ROI_FRAMES
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    eng, _ = engine_b
+    want = np.load(golden / "roi_crops.npz")
+    kind, n, h, w, seed = ROI_FRAMES
+    fr = frames_for(kind, n, h, w, seed)
+    rois = [(f, x0, y0, x1, y1) for _, f, x0, y0, x1, y1 in ROI_CASES]
+    emb = eng.embed_rois(torch.from_numpy(fr).to(eng.device), rois).cpu().numpy()
+    for i, (name, *_rest) in enumerate(ROI_CASES):
+        assert common.cosine(emb[i], want["emb_" + name]) >= COS_GATE, name
+        assert np.abs(emb[i] - want["emb_" + name]).max() < 2e-2, name
+    pipe = DINOv3Pipeline(eng, config=SUBJECTS, results_dir=tmp_path)
+    recs = [{"frame": f, "track_id": 1 if i < 3 else 2, "bbox": [x0, y0, x1, y1]} for i, (f, x0, y0, x1, y1) in enumerate(rois)]
+    tracks = pipe.extract_track_embeddings(fr, recs)
+    assert common.cosine(tracks[1], emb[:3].mean(0)) > 0.999999 and common.cosine(tracks[2], emb[3:].mean(0)) > 0.999999
+    # the crop path and the whole-image path agree on the same pixels
+    assert common.cosine(emb[1], pipe.extract_embedding(fr[0])) > 0.99999

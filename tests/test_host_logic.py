@@ -226,3 +226,35 @@ def test_knn_graph_builder_matches_reference(stub, golden):
         gb.compute_knn_edges(knn_embeddings(), k=8)
     with pytest.raises(RuntimeError):
         GraphBuilder(None)
+
+
+def test_track_boxes_and_per_track_reid(stub, tmp_path):
+    """boxes from the tracking service's frame records are floored / ceiled / clamped, every track gets the
+    mean embedding of ITS crops, and the handler re-identifies a track on that embedding when one was supplied."""
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    recs = [{"frame": 0, "track_id": 7, "bbox": [10.2, 5.9, 60.1, 40.0]}, {"frame": 1, "track_id": 7, "bbox": [-4.0, 0.0, 30.5, 20.5]},
+            {"frame": 1, "track_id": 9, "bbox": [50.0, 30.0, 200.0, 90.0]}, {"frame": 1, "track_id": 3, "bbox": [70.0, 10.0, 70.0, 50.0]},
+            {"frame": 5, "track_id": 9, "bbox": [0, 0, 10, 10]}]
+    boxes = DINOv3Pipeline.track_boxes(recs, height=64, width=96)
+    assert boxes[7] == [(0, 10, 5, 61, 40), (1, 0, 0, 31, 21)] and boxes[9][0] == (1, 50, 30, 96, 64) and 3 not in boxes
+    pipe = DINOv3Pipeline(stub, results_dir=tmp_path)
+    fr = common.smooth_frames(2, 64, 96, seed=5)
+    emb = pipe.extract_track_embeddings(fr, recs)                      # the frame-5 record has no frame: dropped
+    assert sorted(emb) == [7, 9] and emb[7].shape == (768,)
+    want7 = np.mean([pipe.extract_embedding(fr[0, 5:40, 10:61]), pipe.extract_embedding(fr[1, 0:21, 0:31])], axis=0)
+    np.testing.assert_allclose(emb[7], want7, atol=1e-5)
+    np.testing.assert_allclose(emb[9], pipe.extract_embedding(fr[1, 30:64, 50:96]), atol=1e-5)
+    assert pipe.extract_track_embeddings(fr, []) == {}
+
+    nats = fake_services.FakeNats()
+    m = CowReIDMatcher(engine=stub)
+    asyncio.run(m.connect())
+    h = TrackingReIDHandler(m, nats, tmp_path)
+    h.pending_tracks["v"] = [{"track_id": 7, "start_frame": 0, "end_frame": 1}, {"track_id": 9, "start_frame": 1, "end_frame": 1},
+                             {"track_id": 11, "start_frame": 0, "end_frame": 0}]
+    h.track_embeddings["v"] = {7: emb[7], 9: -emb[7]}                  # opposite directions -> two identities
+    asyncio.run(h._perform_reid("v", emb[7]))                          # track 11 falls back to the video embedding (= track 7's)
+    _, msg = nats.published[-1]
+    assert [(r["track_id"], r["cow_id"], r["is_new"]) for r in msg["matches"]] == [(7, "COW-0001", True), (9, "COW-0002", True),
+                                                                                  (11, "COW-0001", False)]
+    assert "v" not in h.track_embeddings

@@ -127,3 +127,19 @@ def test_knn_graph_restatement_matches_reference(golden):
     np.testing.assert_allclose(ew, want["edge_weights"], atol=1e-12)
     ei2, ew2 = knn_ref.compute_knn_edges(emb[:4], 5)
     assert ei2.tolist() == want["small_edge_index"] and ei2.shape == (2, 12)
+
+
+def test_crop_path_matches_reference_on_crops(golden, model_b):
+    """Per-track crops: the oracle applied to frame[y0:y1, x0:x1] reproduces the reference's extract_embedding on
+    that crop (tests/golden/roi_crops.npz, oracle/make_golden_roi.py) and the HF processor's pixel_values."""
+    from oracle.make_golden_roi import ROI_CASES, ROI_FRAMES
+    want = np.load(golden / "roi_crops.npz")
+    kind, n, h, w, seed = ROI_FRAMES
+    fr = frames_for(kind, n, h, w, seed)
+    sd = model_b.state_dict()
+    for name, f, x0, y0, x1, y1 in ROI_CASES:
+        pv = preprocess_ref.preprocess(np.ascontiguousarray(fr[f:f + 1, y0:y1, x0:x1]), bgr=True)
+        if "pix_" + name in want:
+            np.testing.assert_allclose(pv[0], want["pix_" + name].astype(np.float32), atol=2e-3, rtol=0)   # stored as fp16
+        got = vit_ref.frame_embeddings(sd, torch.from_numpy(pv), heads=12, layers=12).numpy()[0]
+        np.testing.assert_allclose(got, want["emb_" + name], atol=2e-4, rtol=0, err_msg=name)

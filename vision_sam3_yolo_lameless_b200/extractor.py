@@ -17,7 +17,7 @@ from __future__ import annotations
 import json
 import os
 from pathlib import Path
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -105,6 +105,47 @@ class DINOv3Pipeline:
             scores, idx = self.engine.gallery_topk(unit, self.gallery.matrix[: len(self.gallery)], k=top_k)
             return mean.cpu().numpy(), unit.cpu().numpy(), scores.cpu().numpy(), idx.cpu().numpy()
         return mean.cpu().numpy(), unit.cpu().numpy()
+
+    # -- per-track crops (new; tracking main.py:332-334 "in production, you'd extract per-track embeddings") --------
+    @staticmethod
+    def track_boxes(frame_tracks, height: int, width: int, frame_index=None) -> Dict[int, List[Tuple[int, int, int, int, int]]]:
+        """``frame_tracks`` = the tracking service's per-frame records ({"frame", "track_id", "bbox": [x1, y1, x2, y2]},
+        tracking main.py:180-187) -> {track_id: [(row, x0, y0, x1, y1), ...]} with integer pixel boxes (floor / ceil, clamped
+        to the frame, empty boxes dropped).  ``frame_index`` maps a video frame number to its row in the frame array
+        (default: identity)."""
+        out: Dict[int, List[Tuple[int, int, int, int, int]]] = {}
+        for rec in frame_tracks:
+            f = int(rec["frame"])
+            row = f if frame_index is None else frame_index.get(f)
+            if row is None:
+                continue
+            x1, y1, x2, y2 = (float(v) for v in rec["bbox"][:4])
+            x0, y0 = max(0, int(np.floor(x1))), max(0, int(np.floor(y1)))
+            xe, ye = min(width, int(np.ceil(x2))), min(height, int(np.ceil(y2)))
+            if xe > x0 and ye > y0:
+                out.setdefault(int(rec["track_id"]), []).append((row, x0, y0, xe, ye))
+        return out
+
+    def extract_track_embeddings(self, frames, frame_tracks, frame_index=None, bgr: bool = True) -> Dict[int, np.ndarray]:
+        """One embedding per track: every box of the track is cropped from its frame, embedded exactly as
+        ``extract_embedding(frame[y0:y1, x0:x1])`` would (K1 in region-of-interest mode: the frames are uploaded once, no
+        crop is materialised), and the track's embeddings are averaged like a clip (main.py:204-208).
+        frames: uint8 [n, H, W, 3] host array or CUDA tensor; returns {track_id: float32 [D]}."""
+        dev_frames = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
+        dev_frames = dev_frames.to(self.engine.device)
+        n, h, w, _ = dev_frames.shape
+        boxes = self.track_boxes(frame_tracks, h, w, frame_index)
+        boxes = {t: [b for b in bs if 0 <= b[0] < n] for t, bs in boxes.items()}
+        boxes = {t: bs for t, bs in boxes.items() if bs}
+        if not boxes:
+            return {}
+        ids = sorted(boxes)
+        rois = np.array([b for t in ids for b in boxes[t]], dtype=np.int64)
+        offsets = np.cumsum([0] + [len(boxes[t]) for t in ids]).astype(np.int32)
+        emb = self.engine.embed_rois(dev_frames, rois, bgr=bgr)
+        mean, _ = self.engine.pool_clips(emb, torch.as_tensor(offsets))
+        mean = mean.cpu().numpy()
+        return {t: mean[i] for i, t in enumerate(ids)}
 
     # -- main.py:95-115 ---------------------------------------------------------------------------
     def extract_embedding(self, image: np.ndarray) -> np.ndarray:

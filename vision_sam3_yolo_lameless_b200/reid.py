@@ -208,6 +208,9 @@ class TrackingReIDHandler:
         self.save_track = save_track
         self.video_embeddings: Dict[str, np.ndarray] = {}
         self.pending_tracks: Dict[str, List[Dict]] = {}
+        # opt-in: {video_id: {track_id: embedding}} from DINOv3Pipeline.extract_track_embeddings; a track found
+        # here is re-identified on ITS crops' embedding instead of the whole-video embedding the reference reuses for every track
+        self.track_embeddings: Dict[str, Dict[int, np.ndarray]] = {}
 
     # -- tracking main.py:268-320 ------------------------------------------------------------------
     async def process_dinov3_results(self, message: dict):
@@ -250,9 +253,10 @@ class TrackingReIDHandler:
             return
         print(f"Performing Re-ID for {len(tracks)} tracks in {video_id}")
         reid_results = []
+        per_track = self.track_embeddings.pop(video_id, {})
         for track in tracks:
             match = self.reid_matcher.match_or_create(
-                embedding=embedding, video_id=video_id, track_id=track["track_id"],
+                embedding=per_track.get(track["track_id"], embedding), video_id=video_id, track_id=track["track_id"],
                 metadata={"start_frame": track["start_frame"], "end_frame": track["end_frame"]})
             reid_results.append({
                 "track_id": track["track_id"], "cow_id": match.cow_id, "identity_id": str(match.identity_id),
