@@ -169,22 +169,38 @@ class DINOv3Pipeline:
         fps = int(cap.get(cv2.CAP_PROP_FPS))
         total_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
         frame_interval = self.frame_interval if self.frame_interval is not None else max(1, fps)
-        picked: List[np.ndarray] = []
+        # Same sampling rule as the reference (every frame is visited, frame_count % interval == 0 is kept), but a skipped frame
+        # is only grab()bed -- no BGR conversion, no copy -- and a kept frame is retrieve()d straight into one pinned staging
+        # array, so the sampled frames go host -> device with no intermediate list / np.stack.
         picked_idx: List[int] = []
+        staging = None          # uint8 [capacity, H, W, 3]; pinned when CUDA is present
         frame_count = 0
         while True:
-            ret, frame = cap.read()
-            if not ret:
+            if not cap.grab():
                 break
             if frame_count % frame_interval == 0:
-                picked.append(frame)
+                n = len(picked_idx)
+                if staging is not None and n < staging.shape[0]:
+                    ret, frame = cap.retrieve(staging[n].numpy())
+                else:
+                    ret, frame = cap.retrieve()
+                if not ret:
+                    break
+                if staging is None or n >= staging.shape[0] or frame.shape != tuple(staging.shape[1:]):
+                    want = max(2 * n, (max(total_frames, frame_count + 1) + frame_interval - 1) // frame_interval + 1)
+                    grown = torch.empty((want,) + frame.shape, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+                    if staging is not None and n:
+                        grown[:n].copy_(staging[:n])
+                    staging = grown
+                if frame.ctypes.data != staging[n].data_ptr():      # cv2 allocated its own array (first frame, growth)
+                    staging[n].copy_(torch.from_numpy(frame))
                 picked_idx.append(frame_count)
             frame_count += 1
         cap.release()
 
         embeddings = []
-        if picked:
-            embs = self.embed_frames(np.stack(picked), bgr=True)
+        if picked_idx:
+            embs = self.engine.embed_host_frames(staging[: len(picked_idx)], bgr=True).cpu().numpy()
             for idx, e in zip(picked_idx, embs):
                 embeddings.append({"frame": idx, "time": idx / fps if fps > 0 else 0, "embedding": e.tolist()})
         canonical_frames = []
