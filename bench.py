@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--gallery-rows", type=int, default=100_000)
     ap.add_argument("--batch-frames", type=int, default=1130, help="frames per ViT launch sequence")
+    ap.add_argument("--resize", type=int, default=224, help="model input size (configs[2]: 518 or 592 with --height/--width equal to it)")
     ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
     ap.add_argument("--ln-fold", type=int, default=-1, help="-1 = library default; 0 = separate LayerNorm launches")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
@@ -181,14 +182,14 @@ def run_reference(args, rank: int):
 
 
 def workload_config(args, world):
-    return {"workload": f"configs[1]: ViT-B/16 embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
+    return {"workload": f"{'configs[1]' if args.resize == 224 else 'configs[2]'}: ViT-B/16 embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
                         f"({args.clips * args.frames_per_clip} frames) decoded as {args.width}x{args.height} uint8 incl. fused "
                         f"resize/normalize, + cosine top-5 re-ID against a {args.gallery_rows}-row gallery; per rank",
             "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip, "frame_hw": [args.height, args.width],
-            "gallery_rows": args.gallery_rows, "top_k": 5, "batch_frames": args.batch_frames,
+            "gallery_rows": args.gallery_rows, "top_k": 5, "batch_frames": args.batch_frames, "model_input": args.resize,
             "parallelism": f"dp{world} clips + row-sharded gallery",
             "l2": "inputs (59.7 GB of frames per step) are far larger than L2; no flush needed",
-            "flops": GFLOP_PER_FRAME_NOTE}
+            "flops": GFLOP_PER_FRAME_NOTE if args.resize == 224 else f"2MNK per GEMM + 4T^2D attention per layer, T={(args.resize // 16) ** 2 + 5}"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -219,7 +220,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     model = common.hf_model()
     cfg = VitConfig.from_hf(model.config)
-    eng = ClipEmbedEngine(cfg, model.state_dict(), device=local_rank, max_frames=args.batch_frames)
+    eng = ClipEmbedEngine(cfg, model.state_dict(), device=local_rank, max_frames=args.batch_frames, resize=(args.resize, args.resize))
+    grid = args.resize // 16
     del model
     h, w, fpc, clips = args.height, args.width, args.frames_per_clip, args.clips
     frames_total = clips * fpc
@@ -379,8 +381,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
             "clips_per_s": value / fpc,
-            "vit_tflops": value * cfg.flops_per_frame(14, 14) / 1e12,
-            "vit_frac_of_bf16_burst_peak": value / world * cfg.flops_per_frame(14, 14) / 1e12 / 1623.1,
+            "vit_tflops": value * cfg.flops_per_frame(grid, grid) / 1e12,
+            "vit_frac_of_bf16_burst_peak": value / world * cfg.flops_per_frame(grid, grid) / 1e12 / 1623.1,
             "resident_frames": resident,
             "roofline": roofline, "kernels": {n: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in k.items()}
                                               for n, k in kernels.items()},

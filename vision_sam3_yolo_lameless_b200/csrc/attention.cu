@@ -22,11 +22,13 @@
 
 namespace cre {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;                // two threads per query row: each exponentiates half of a key block
+constexpr int kAttnKbMax = 192;                  // keys per block: S [0, 192) + O [192, 256) = 256 TMEM columns -> two CTAs per SM
 constexpr int kAttnQBytes = 128 * 128;           // 128 rows x 64 bf16
-constexpr int kAttnKPBytes = 4 * 128 * 128;      // K block (<= 256 x 128 B) aliased with P (4 chunks of 128 x 128 B)
-constexpr int kAttnVBytes = 256 * 128;           // V block: <= 256 keys x 64 dims
-constexpr int kAttnSmemBytes = kAttnQBytes + kAttnKPBytes + kAttnVBytes + 128;   // x2 CTAs (+1 KB reserved each) fits one SM
+constexpr int kAttnKBytes = kAttnKbMax * 128;    // K block
+constexpr int kAttnPBytes = 3 * 128 * 128;       // P: 3 chunks of 128 rows x 64 keys (bf16, K-major 128B swizzle)
+constexpr int kAttnVBytes = kAttnKbMax * 128;    // V block: <= 192 keys x 64 dims
+constexpr int kAttnSmemBytes = kAttnQBytes + kAttnKBytes + kAttnPBytes + kAttnVBytes + 128;   // x2 CTAs (+1 KB reserved each) fits one SM
 
 struct AttnParams {
     int t, heads, kb, nblocks;
@@ -104,6 +106,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t 
     return umma_idesc_bf16(m, n) | (1u << 16);                // B operand is MN-major
 }
 
+// General kernel (any T; used for T > 256, i.e. the 518 x 518 / 592 x 592 inputs).  One CTA = one 128-row query tile of one
+// (frame, head); keys are visited in blocks of KB <= 192.  Like the fast path below it is a SINGLE-pass softmax with a fixed
+// stabiliser: m = the row's maximum over the first 32 keys (CLS, registers, first patches), exponents clamped at +120 -- softmax
+// is shift invariant, so any m works as long as exp2 neither overflows nor flushes the row's largest term; only rows where some
+// score exceeds that 32-key maximum by > 83 nats are altered.  With m fixed, nothing is ever rescaled: O accumulates in its own
+// TMEM columns across all key blocks (read back once), and a block costs one TMEM pass over S instead of two passes plus an O
+// read.  K has its own buffer (not aliased with P), so the K tile of the next block streams in while this block exponentiates.
+// TMEM (S 192 + O 64 columns per tile) caps the SM at two resident query tiles, so every row is served by TWO threads (warps w
+// and w + 4 share a TMEM lane quarter and split the block's 16-key chunks): 16 softmax warps per SM instead of 8.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                  const AttnParams p) {
@@ -111,18 +122,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();  // 128B swizzle atoms need 1024-byte alignment
     const uint32_t s_q = smem_base;
-    const uint32_t s_kp = s_q + kAttnQBytes;
-    const uint32_t s_v = s_kp + kAttnKPBytes;
+    const uint32_t s_k = s_q + kAttnQBytes;
+    const uint32_t s_p = s_k + kAttnKBytes;
+    const uint32_t s_v = s_p + kAttnPBytes;
     const uint32_t bar_q = s_v + kAttnVBytes;
-    const uint32_t bar_kv = bar_q + 8;
-    const uint32_t bar_s = bar_q + 16;
-    const uint32_t bar_o = bar_q + 24;
-    const uint32_t tmem_slot = bar_q + 32;
+    const uint32_t bar_k = bar_q + 8;
+    const uint32_t bar_v = bar_q + 16;
+    const uint32_t bar_s = bar_q + 24;
+    const uint32_t bar_o = bar_q + 32;
+    const uint32_t tmem_slot = bar_q + 40;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    uint8_t* p_gen = smem_raw + (s_kp - smem_u32(smem_raw));  // generic pointer to the K/P region
+    uint8_t* p_gen = smem_raw + (s_p - smem_u32(smem_raw));  // generic pointer to the P region
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int quarter = warp & 3, side = warp >> 2;        // TMEM lane quarter; which half of every key block
+    const int row = quarter * 32 + (tid & 31);             // query row inside the tile
     const int mtile = blockIdx.x, head = blockIdx.y, frame = blockIdx.z;
     const int T = p.t, KB = p.kb;
 
@@ -130,7 +145,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
         mbar_init(bar_q, 1);
-        mbar_init(bar_kv, 1);
+        mbar_init(bar_k, 1);
+        mbar_init(bar_v, 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_o, 1);
         fence_barrier_init();
@@ -140,157 +156,185 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_o = tmem_base + kAttnKbMax;   // O accumulator columns [192, 256)
 
     const int q_row0 = frame * T + mtile * 128;
     if (tid == 0) {
         mbar_arrive_expect_tx(bar_q, kAttnQBytes);
         tma_load_2d<1>(&tmap_q, bar_q, s_q, head * 64, q_row0, kEvictFirst);
+        mbar_arrive_expect_tx(bar_k, KB * 128);
+        tma_load_2d<1>(&tmap_kv, bar_k, s_k, p.k_col0 + head * 64, frame * T, kEvictNormal);
+        mbar_arrive_expect_tx(bar_v, KB * 128);
+        tma_load_2d<1>(&tmap_kv, bar_v, s_v, p.v_col0 + head * 64, frame * T, kEvictNormal);
     }
 
-    const int tok = mtile * 128 + tid;  // this thread's query token
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int tok = mtile * 128 + row;  // this thread's query token
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
+    const uint64_t l2e2 = pack2(kLog2e, kLog2e);
+    uint64_t neg_m2 = pack2(0.0f, 0.0f);
+    uint64_t l2 = pack2(0.0f, 0.0f);
 
-    float o_acc[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) o_acc[j] = 0.0f;
-    float m_run = -INFINITY, l_run = 0.0f;
-
-    const uint32_t r7 = tid & 7;
-    uint8_t* p_row = p_gen + (tid >> 3) * 1024 + r7 * 128;
+    const uint32_t r7 = row & 7;
+    uint8_t* p_row = p_gen + (row >> 3) * 1024 + r7 * 128;
     const int nchunk16 = KB >> 4;
+    const int c_lo = side == 0 ? 0 : (nchunk16 + 1) >> 1, c_hi = side == 0 ? (nchunk16 + 1) >> 1 : nchunk16;   // this thread's chunks
+
+    // thread 0: S = Q K^T of one key block into TMEM columns [0, KB)
+    auto issue_s = [&](uint32_t k_phase) {
+        mbar_wait(bar_k, k_phase);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, KB);
+        const uint64_t dq = umma_desc_k_sw128(s_q);
+        const uint64_t dk = umma_desc_k_sw128(s_k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+        umma_commit<1>(bar_s);
+    };
+    if (tid == 0) {
+        mbar_wait(bar_q, 0);
+        issue_s(0);
+    }
 
     for (int kb = 0; kb < p.nblocks; ++kb) {
         const int key0 = kb * KB;
         const uint32_t ph = kb & 1;
         const int valid = min(KB, T - key0);      // keys of this frame inside the block (>= 1)
-        if (tid == 0) {
-            mbar_arrive_expect_tx(bar_kv, 2 * KB * 128);
-            tma_load_2d<1>(&tmap_kv, bar_kv, s_kp, p.k_col0 + head * 64, frame * T + key0, kEvictNormal);
-            tma_load_2d<1>(&tmap_kv, bar_kv, s_v, p.v_col0 + head * 64, frame * T + key0, kEvictNormal);
-            if (kb == 0) mbar_wait(bar_q, 0);
-            mbar_wait(bar_kv, ph);
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16(128, KB);
-            const uint64_t dq = umma_desc_k_sw128(s_q);
-            const uint64_t dk = umma_desc_k_sw128(s_kp);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-            umma_commit<1>(bar_s);
-        }
+        // S(kb) complete; the tensor core runs in order, so P V of the previous block is complete too: P may be overwritten
         mbar_wait(bar_s, ph);
         __syncwarp();
         tc_fence_after();
-
-        // ---- pass 1: row maximum over the valid keys of this block ----
-        float m_blk = -INFINITY;
+        // S is in TMEM: the K buffer is free -> stream the next block's K in behind the exponentials
+        if (tid == 0 && kb + 1 < p.nblocks) {
+            mbar_arrive_expect_tx(bar_k, KB * 128);
+            tma_load_2d<1>(&tmap_kv, bar_k, s_k, p.k_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+        }
         const int nfull = valid >> 4, rem = valid & 15;
-        for (int c = 0; c < nfull; ++c) {
-            uint32_t v[16];
-            tmem_ld16(t_row + c * 16, v);
-            tmem_ld_wait();
-            float a = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-            float b = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
-#pragma unroll
-            for (int j = 4; j < 16; j += 4) {
-                a = fmaxf(a, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-                b = fmaxf(b, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-            }
-            m_blk = fmaxf(m_blk, fmaxf(a, b));
-        }
-        if (rem != 0) {
-            uint32_t v[16];
-            tmem_ld16(t_row + nfull * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < rem) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-        }
-        const float m_new = fmaxf(m_run, m_blk);
-        const float alpha = ex2_approx((m_run - m_new) * kLog2e);  // 0 on the first block (m_run = -inf)
-        const uint64_t neg_m2 = pack2(-m_new * kLog2e, -m_new * kLog2e);
-        const uint64_t l2e2 = pack2(kLog2e, kLog2e);
-
-        // ---- pass 2: P = exp2(S*log2e - m), row sum, bf16 P into the swizzled K-major smem tile ----
-        uint64_t l2 = pack2(0.0f, 0.0f);
-        for (int c = 0; c < nchunk16; ++c) {
-            uint32_t pk[8];
-            if (c < nfull || (c == nfull && rem != 0)) {
+        if (kb == 0) {
+            // fixed stabiliser: maximum over the first min(32, valid) keys of the frame
+            float m = -INFINITY;
+            const int npre = min(32, valid);
+            for (int c = 0; c * 16 < npre; ++c) {
                 uint32_t v[16];
                 tmem_ld16(t_row + c * 16, v);
                 tmem_ld_wait();
-                float e[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float x0, x1;
-                    unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
-                    e[j] = ex2_approx(x0);
-                    e[j + 1] = ex2_approx(x1);
-                }
-                if (c == nfull) {   // partial chunk: keys >= valid belong to another frame
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j >= rem) e[j] = 0.0f;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    l2 = add2(l2, pack2(e[j], e[j + 1]));
-                    pk[j >> 1] = pack_bf16x2_pos(e[j], e[j + 1]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pk[j] = 0u;
+                for (int j = 0; j < 16; ++j)
+                    if (c * 16 + j < npre) m = fmaxf(m, __uint_as_float(v[j]));
             }
-            const int chunk = c >> 2;                       // 64-key smem chunk
+            neg_m2 = pack2(-m * kLog2e, -m * kLog2e);
+        }
+
+        // ---- P = exp2(S*log2e - m*log2e), row sum, bf16 P into the swizzled K-major smem tile; the TMEM read of chunk c + 1 is
+        //      in flight while chunk c is exponentiated ----
+        const int nk = nfull + (rem != 0 ? 1 : 0);          // chunks holding at least one valid key
+        auto softmax_chunk = [&](int c, const uint32_t (&v)[16]) {
+            uint32_t pk[8];
+            float e[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                float x0, x1;
+                unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
+                x0 = fminf(x0, 120.0f);
+                x1 = fminf(x1, 120.0f);
+                e[j] = ex2_approx(x0);          // all on the MUFU: this kernel is bound by issue slots, not by the XU pipe
+                e[j + 1] = ex2_approx(x1);
+            }
+            if (c == nfull) {   // partial chunk: keys >= valid belong to another frame
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j >= rem) e[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                l2 = add2(l2, pack2(e[j], e[j + 1]));
+                pk[j >> 1] = pack_bf16x2_pos(e[j], e[j + 1]);
+            }
             const uint32_t u0 = (static_cast<uint32_t>(c) & 3u) << 1;  // first 16-byte unit inside the 128-byte row
-            uint8_t* base = p_row + chunk * (128 * 128);
+            uint8_t* base = p_row + (c >> 2) * (128 * 128);            // 64-key smem chunk
             *reinterpret_cast<uint4*>(base + ((u0 ^ r7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(base + (((u0 + 1) ^ r7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        };
+        {
+            const int hi = min(c_hi, nk);                   // this thread's chunks that hold valid keys: [c_lo, hi)
+            uint32_t va[16], vb[16];
+            int c = c_lo;
+            if (c < hi) {
+                tmem_ld16(t_row + c * 16, va);
+                tmem_ld_wait();
+            }
+            for (; c + 2 <= hi; c += 2) {
+                tmem_ld16(t_row + (c + 1) * 16, vb);
+                softmax_chunk(c, va);
+                tmem_ld_wait();
+                if (c + 2 < hi) tmem_ld16(t_row + (c + 2) * 16, va);
+                softmax_chunk(c + 1, vb);
+                tmem_ld_wait();
+            }
+            if (c < hi) softmax_chunk(c, va);
+            for (int z = max(nk, c_lo); z < c_hi; ++z) {    // chunks past the frame's last key: P = 0
+                const uint32_t u0 = (static_cast<uint32_t>(z) & 3u) << 1;
+                uint8_t* base = p_row + (z >> 2) * (128 * 128);
+                *reinterpret_cast<uint4*>(base + ((u0 ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(base + (((u0 + 1) ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
-        float l_lo, l_hi;
-        unpack2(l2, l_lo, l_hi);
-        const float l_blk = l_lo + l_hi;
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
 
         if (tid == 0) {
             tc_fence_after();
+            mbar_wait(bar_v, ph);
             const uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
             for (int ks = 0; ks < nchunk16; ++ks) {
-                const uint64_t dp = umma_desc_k_sw128(s_kp + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
+                const uint64_t dp = umma_desc_k_sw128(s_p + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
                 const uint64_t dv = umma_desc_mn_sw128(s_v + ks * 2048);   // 16 keys = two 8-row atoms
-                umma_bf16<1>(tmem_base, dp, dv, idesc, ks != 0);
+                umma_bf16<1>(tmem_o, dp, dv, idesc, (kb | ks) != 0);
             }
             umma_commit<1>(bar_o);
+            if (kb + 1 < p.nblocks) {
+                // every thread has read S(kb) (the __syncthreads above): queue the next S right behind P V, then refill V once
+                // P V has retired
+                issue_s(ph ^ 1u);
+                mbar_wait(bar_o, ph);
+                mbar_arrive_expect_tx(bar_v, KB * 128);
+                tma_load_2d<1>(&tmap_kv, bar_v, s_v, p.v_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+            }
         }
-        mbar_wait(bar_o, ph);
-        __syncwarp();
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_row + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o_acc[c + j] = fmaf(o_acc[c + j], alpha, __uint_as_float(v[j]));
-        }
-        l_run = fmaf(l_run, alpha, l_blk);
-        m_run = m_new;
-        tc_fence_before();
-        __syncthreads();  // TMEM and the K/P region are reused by the next key block
     }
 
-    if (tok < T) {
-        const float inv = 1.0f / l_run;
-        uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + tok) * p.ld_out + head * 64);
+    // ---- O / l -> bf16 ----
+    mbar_wait(bar_o, static_cast<uint32_t>(p.nblocks - 1) & 1u);
+    __syncwarp();
+    tc_fence_after();
+    // the two threads of a row exchange their partial row sums through the (now idle) P region
+    float l_lo, l_hi;
+    unpack2(l2, l_lo, l_hi);
+    float* l_x = reinterpret_cast<float*>(p_gen);
+    l_x[side * 128 + row] = l_lo + l_hi;
+    __syncthreads();
+    const float inv = 1.0f / (l_x[row] + l_x[128 + row]);
+    uint32_t o[32];                                         // this thread's half of the 64 output dims
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            o[j] = make_uint4(pack_bf16x2(o_acc[8 * j] * inv, o_acc[8 * j + 1] * inv),
-                              pack_bf16x2(o_acc[8 * j + 2] * inv, o_acc[8 * j + 3] * inv),
-                              pack_bf16x2(o_acc[8 * j + 4] * inv, o_acc[8 * j + 5] * inv),
-                              pack_bf16x2(o_acc[8 * j + 6] * inv, o_acc[8 * j + 7] * inv));
+    for (int c = 0; c < 32; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + kAttnKbMax + side * 32 + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[c + j] = v[j];
     }
+    tmem_ld_wait();
+    if (tok < T) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + tok) * p.ld_out + head * 64 + side * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+    }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, 256);
@@ -613,13 +657,15 @@ void set_attention_fast(int on) { g_attn_fast = on; }
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.n > 0 && a.t > 0 && a.heads > 0, "attention: empty problem");
     CRE_REQUIRE(a.ld % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0, "attention: ld / column offsets must be multiples of 8");
-    const int nblocks = (a.t + 255) / 256;
+    const bool fast = a.t <= 256 && g_attn_fast;
+    const int kb_cap = fast ? 256 : kAttnKbMax;
+    const int nblocks = (a.t + kb_cap - 1) / kb_cap;
     int kb = (a.t + nblocks - 1) / nblocks;
     kb = (kb + 15) & ~15;
-    CRE_REQUIRE(kb >= 16 && kb <= 256, "attention: key block %d out of range", kb);
+    CRE_REQUIRE(kb >= 16 && kb <= kb_cap, "attention: key block %d out of range", kb);
     const int64_t rows = static_cast<int64_t>(a.n) * a.t;
     CUtensorMap tq, tkv;
-    if (nblocks == 1 && g_attn_fast) {
+    if (fast) {
         int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 256);
         if (rc) return rc;
         rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
