@@ -32,9 +32,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "DINOv3 ViT-B/16 clip-embedding + re-ID throughput"
+METRIC = "DINOv3 ViT-B/16 frames/s at 1/2/4/8 B200 (% bf16 tensor peak) vs host CPU"   # BASELINE.json "metric"
 UNIT = "frames/s"
-GFLOP_PER_FRAME_NOTE = "35.864 GFLOP/frame (2MNK per GEMM + 4T^2D attention per layer, T=201)"
 
 
 def parse_args():
@@ -49,6 +48,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--gallery-rows", type=int, default=100_000)
     ap.add_argument("--batch-frames", type=int, default=1130, help="frames per ViT launch sequence")
+    ap.add_argument("--model", choices=["vitb16", "vitl16"], default="vitb16", help="vitl16 = BASELINE.json configs[4] (D 1024, 24 layers)")
     ap.add_argument("--resize", type=int, default=224, help="model input size (configs[2]: 518 or 592 with --height/--width equal to it)")
     ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
     ap.add_argument("--ln-fold", type=int, default=-1, help="-1 = library default; 0 = separate LayerNorm launches")
@@ -121,9 +121,10 @@ def cpu_reference_sample(args, seconds: float, frames_cap: int = 10_000):
     import numpy as np
     import torch
 
-    from oracle import common, pipeline_ref
+    from oracle import pipeline_ref
+    from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 
-    pipe = pipeline_ref.ReferencePipelineCPU(common.hf_model())
+    pipe = pipeline_ref.ReferencePipelineCPU(random_init_vit(args.model))
     rng = np.random.default_rng(0)
     frames = rng.integers(0, 256, size=(4, args.height, args.width, 3), dtype=np.uint8)
     pipe.extract_embedding(frames[0])                      # warm-up (thread pools, allocator)
@@ -146,13 +147,14 @@ def run_reference(args, rank: int):
     import numpy as np
     import torch
 
-    from oracle import common, pipeline_ref, reid_ref
+    from oracle import pipeline_ref, reid_ref
+    from vision_sam3_yolo_lameless_b200.synthetic import VIT_SHAPES, random_init_vit
 
-    pipe = pipeline_ref.ReferencePipelineCPU(common.hf_model())
+    pipe = pipeline_ref.ReferencePipelineCPU(random_init_vit(args.model))
     rng = np.random.default_rng(0)
     sample = 8                                             # frames per step: 1 clip sampled at 8 frames
     frames = rng.integers(0, 256, size=(sample, args.height, args.width, 3), dtype=np.uint8)
-    gal = reid_ref.l2_normalise(np.random.default_rng(7).standard_normal((args.gallery_rows, 768))).astype(np.float32)
+    gal = reid_ref.l2_normalise(np.random.default_rng(7).standard_normal((args.gallery_rows, VIT_SHAPES[args.model][0]))).astype(np.float32)
 
     def step():
         emb = np.stack([pipe.extract_embedding(f) for f in frames])
@@ -182,14 +184,22 @@ def run_reference(args, rank: int):
 
 
 def workload_config(args, world):
-    return {"workload": f"{'configs[1]' if args.resize == 224 else 'configs[2]'}: ViT-B/16 embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
+    from vision_sam3_yolo_lameless_b200.synthetic import vit_flops_per_frame
+
+    tokens = (args.resize // 16) ** 2 + 5
+    which = "configs[4]" if args.model == "vitl16" else "configs[1]" if args.resize == 224 else "configs[2]"
+    name = "ViT-L/16" if args.model == "vitl16" else "ViT-B/16"
+    gf = vit_flops_per_frame(args.model, tokens, tokens - 5) / 1e9
+    step_bytes = args.clips * args.frames_per_clip * args.height * args.width * 3
+    return {"workload": f"{which}: {name} embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
                         f"({args.clips * args.frames_per_clip} frames) decoded as {args.width}x{args.height} uint8 incl. fused "
                         f"resize/normalize, + cosine top-5 re-ID against a {args.gallery_rows}-row gallery; per rank",
-            "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip, "frame_hw": [args.height, args.width],
-            "gallery_rows": args.gallery_rows, "top_k": 5, "batch_frames": args.batch_frames, "model_input": args.resize,
+            "model": args.model, "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip,
+            "frame_hw": [args.height, args.width], "gallery_rows": args.gallery_rows, "top_k": 5,
+            "batch_frames": args.batch_frames, "model_input": args.resize,
             "parallelism": f"dp{world} clips + row-sharded gallery",
-            "l2": "inputs (59.7 GB of frames per step) are far larger than L2; no flush needed",
-            "flops": GFLOP_PER_FRAME_NOTE if args.resize == 224 else f"2MNK per GEMM + 4T^2D attention per layer, T={(args.resize // 16) ** 2 + 5}"}
+            "l2": f"inputs ({step_bytes / 1e9:.1f} GB of frames per step and rank) are far larger than L2 (126 MB); no flush needed",
+            "flops": f"{gf:.3f} GFLOP/frame (2MNK per GEMM + 4T^2D attention per layer, T={tokens})"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -200,11 +210,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
-    from oracle import common                        # seeded random-init weights only (test/bench infrastructure)
     from vision_sam3_yolo_lameless_b200 import _lib
     from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig, set_cta_group
     from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
     from vision_sam3_yolo_lameless_b200.sharded import ShardedReID, shard_range
+    from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit      # the CUDA arm never touches oracle/
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -218,7 +228,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if args.ln_fold >= 0:
         _lib.set_tuning("ln_fold", args.ln_fold)
 
-    model = common.hf_model()
+    model = random_init_vit(args.model)
     cfg = VitConfig.from_hf(model.config)
     eng = ClipEmbedEngine(cfg, model.state_dict(), device=local_rank, max_frames=args.batch_frames, resize=(args.resize, args.resize))
     grid = args.resize // 16
@@ -321,6 +331,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "launches": g_l, "avg_launch_us": g_ms / g_l * 1e3, "flops_per_launch": g_work / g_l,
                     "share_of_step": g_ms / tot,
                     "how": "CUDA events around every launch (cre_profile_start/stop) in one instrumented step after the timed region"}
+        # the ViT forward alone (north_star's tensor-peak target is quoted "on the ViT-B/16 forward"): every launch between the
+        # patch rows and the frame embeddings, i.e. the instrumented step minus K1, pooling and re-ID
+        fwd_names = [n for n in kernels if n in _lib.FLOP_KERNELS or n in ("row_stats", "layernorm", "final_norm_mean", "fill_prefix")]
+        fwd_ms = sum(kernels[n]["ms"] for n in fwd_names)
+        fwd_tf = frames_total * cfg.flops_per_frame(grid, grid) / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
+        roofline["vit_forward"] = {"tflops": fwd_tf, "frac_of_burst_peak": fwd_tf / peaks.get("bf16_tflops", 1623.1) if fwd_tf else None,
+                                   "frac_of_sustained_peak": fwd_tf / tf_peak if fwd_tf else None, "ms": fwd_ms,
+                                   "how": "sum of the CUDA-event durations of the forward's launches in the instrumented step"}
         if args.breakdown:
             for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]):
                 perf = f"{k.get('tflops', 0):8.1f} TF/s" if "tflops" in k else f"{k.get('gbs', 0):8.1f} GB/s"

@@ -141,7 +141,8 @@ def test_gemm_resid_layernorm_producer(engine_small, cg, epi, m, n, k):
     assert rel_err(out, want) < 8e-3
 
 
-@pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12)])
+@pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12),
+                                       (9, 2, 12), (16, 1, 12), (31, 2, 12), (48, 1, 12), (185, 2, 12), (129, 5, 12), (240, 2, 16)])
 def test_attention(engine_small, t, n, heads):
     dev = engine_small.device
     d = heads * 64

@@ -3,12 +3,12 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
-from oracle import common
+from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 from vision_sam3_yolo_lameless_b200 import _lib
 from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
 from gemm_tune import timeit
 
-model = common.hf_model(layers=1)
+model = random_init_vit(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=8)
 n, t, heads = 600, 201, 12
 qkv = (torch.randn(n * t, 3 * heads * 64, device=eng.device) * 0.5).to(torch.bfloat16)

@@ -8,7 +8,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 
-from oracle import common
+from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 from vision_sam3_yolo_lameless_b200 import _lib
 from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
 
@@ -28,7 +28,7 @@ def timeit(fn, iters=20):
 
 def resid_variants():
     """RESID (TMA reduce-add, separate LayerNorm) vs RESID_LN / RESID_LN3 (x through the epilogue, LayerNorm folded)."""
-    model = common.hf_model(layers=1)
+    model = random_init_vit(layers=1)
     eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=8)
     dev = eng.device
     m, n = 1130 * 201, 768
@@ -54,7 +54,7 @@ def resid_variants():
 def main():
     if "--resid" in sys.argv:
         return resid_variants()
-    model = common.hf_model(layers=1)
+    model = random_init_vit(layers=1)
     eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=8)
     dev = eng.device
     m = 1130 * 201

@@ -7,7 +7,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 
-from oracle import common
+from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 from vision_sam3_yolo_lameless_b200 import _lib
 from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
 
@@ -26,7 +26,7 @@ def timeit(fn, iters=20):
 
 
 def main():
-    model = common.hf_model(layers=1)
+    model = random_init_vit(layers=1)
     eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=8)
     dev = eng.device
     m = 300 * 201

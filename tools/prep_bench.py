@@ -3,11 +3,11 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
-from oracle import common
+from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig
 from gemm_tune import timeit
 
-model = common.hf_model(layers=1)
+model = random_init_vit(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=600)
 from vision_sam3_yolo_lameless_b200 import _lib
 modes = [int(a) for a in sys.argv[1:]] or [1, 0]       # preprocess_tma values: 1 = TMA-staged, 0 = direct-load kernel; +2 / +4 = debug bits
