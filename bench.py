@@ -309,6 +309,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         for name, ms_k, work in recs:
             k = kernels.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
             k["launches"] += 1; k["ms"] += ms_k; k["work"] += work
+        if "pool_clips" in kernels:   # K3 bytes: frame embeddings in, clip mean + unit vector out (the offsets live on the device)
+            kernels["pool_clips"]["work"] = 4.0 * cfg.hidden * (frames_total + 2 * clips)
         for name, k in kernels.items():
             k["share"] = k["ms"] / tot
             k["avg_us"] = k["ms"] / k["launches"] * 1e3

@@ -39,6 +39,30 @@ def test_gemm_epilogues(engine_small, cg, m, n, k):
     assert rel_err(out, ref - bias) < 2e-5
 
 
+def test_gelu_epilogue_error(engine_small):
+    """The up-projection epilogue's GELU against nn.functional.gelu (erf form, HF:activations.py) on a dense grid of
+    pre-activations: acc[m, n] = x_m + bias_n covers [-12, 12] in steps of 2^-10.  Allowed: the bf16 rounding of the output
+    (2^-8 relative, half-ulp plus slack) plus 1e-3 absolute for the approximation (gemm_tcgen05.cuh gelu2: fit 2.5e-5 +
+    the MUFU tanh's 2^-11 relative error times |x| / 2)."""
+    eng, dev = engine_small, engine_small.device
+    xs = torch.arange(-12.0, 12.0, 1.0 / 16.0, device=dev)                       # bf16-exact
+    a = torch.zeros(xs.numel(), 64, device=dev)
+    a[:, 0] = xs
+    b = torch.zeros(64, 64, device=dev)
+    b[:, 0] = 1.0
+    bias = torch.arange(64, device=dev, dtype=torch.float32) / 1024.0
+    got = eng.gemm(a.to(torch.bfloat16), b.to(torch.bfloat16), _lib.EPI_GELU, bias=bias, cta_group=1).double().cpu()
+    acc = (xs[:, None] + bias[None, :]).double().cpu()
+    ref = torch.nn.functional.gelu(acc)
+    err = (got - ref).abs()
+    excess = (err - ref.abs() * 2.0 ** -8).clamp_min(0)
+    i = int(excess.argmax())
+    print(f"gelu epilogue: max |err| {err.max():.3e}, max excess over bf16 rounding {excess.max():.3e} at x = {acc.flatten()[i]:.4f}; "
+          f"max |err| on x < 0: {err[acc < 0].max():.3e}")
+    assert excess.max() < 1e-3
+    assert (got[acc < -9.0].abs() < 1e-3).all() and torch.isfinite(got).all()
+
+
 def test_gemm_rejects_bad_shapes(engine_small):
     eng, dev = engine_small, engine_small.device
     a = torch.zeros(8, 100, device=dev, dtype=torch.bfloat16)

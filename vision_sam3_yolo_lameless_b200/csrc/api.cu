@@ -677,9 +677,7 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
     const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
     const int slots = 2 * workers;
     CRE_REQUIRE(slots <= kMaxSlots, "gallery_topk: %d partial slots exceed %d", slots, kMaxSlots);
-    int rc = launch_split_hi_lo(queries_dev, q, dim, a_hilo, stream);
-    if (rc) return rc;
-    rc = launch_fill_topk(part_s, part_i, static_cast<int64_t>(q) * slots * k, stream);
+    int rc = launch_topk_prepare(queries_dev, q, dim, a_hilo, part_s, part_i, static_cast<int64_t>(q) * slots * k, stream);
     if (rc) return rc;
     GemmParams p = base_params(q, rows, 2 * dim);
     p.b_k_extent = dim;

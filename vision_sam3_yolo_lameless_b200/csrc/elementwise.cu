@@ -264,50 +264,63 @@ int launch_fill_prefix(float* x, const float* prefix, int frames, int t, int pre
 // ---------------------------------------------------------------------------------------------
 // Clip pooling (services/dinov3-pipeline/app/main.py:204-208 np.mean over the clip's frame
 // embeddings) + L2 normalisation (services/tracking-service/app/reid/matcher.py:124, +1e-8).
-// One CTA per clip; thread c owns columns c, c+256, ...
+// One CTA per clip.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool_clips_kernel(const float* __restrict__ emb, const int32_t* __restrict__ offs,
-                                                         int dim, float* __restrict__ out_mean,
-                                                         float* __restrict__ out_unit) {
-    __shared__ float red[8];
+__global__ void __launch_bounds__(1024) pool_clips_kernel(const float* __restrict__ emb, const int32_t* __restrict__ offs,
+                                                          int dim, float* __restrict__ out_mean,
+                                                          float* __restrict__ out_unit) {
+    // thread = (frame lane fl, float4 column group cg): dim / 4 <= 256 column groups, 1024 / (dim / 4) frame lanes that stride
+    // over the clip's frames with independent 16-byte loads; the frame lanes are then summed IN A FIXED ORDER through shared
+    // memory (bit-reproducible), and the first dim / 4 threads finish the mean, the norm and both stores.
+    __shared__ float4 part[1024];
+    __shared__ float red[32];
     const int clip = blockIdx.x;
     const int f0 = offs[clip], f1 = offs[clip + 1];
-    const float inv = f1 > f0 ? 1.0f / static_cast<float>(f1 - f0) : 0.0f;
-    float m[4] = {0.f, 0.f, 0.f, 0.f};  // dim <= 1024
-    float ss = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = threadIdx.x + 256 * i;
-        if (c < dim) {
-            float s = 0.0f;
-            for (int f = f0; f < f1; ++f) s += emb[static_cast<size_t>(f) * dim + c];
-            m[i] = s * inv;
-            ss += m[i] * m[i];
+    const int groups = dim >> 2;                     // float4 column groups (dim % 4 == 0)
+    const int lanes = 1024 / groups;                 // frame lanes
+    const int cg = threadIdx.x % groups, fl = threadIdx.x / groups;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fl < lanes) {
+        for (int f = f0 + fl; f < f1; f += lanes) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(emb + static_cast<size_t>(f) * dim) + cg);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    const float inv = f1 > f0 ? 1.0f / static_cast<float>(f1 - f0) : 0.0f;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ss = 0.0f;
+    if (threadIdx.x < groups) {
+        for (int l = 0; l < lanes; ++l) {
+            const float4 v = part[l * groups + threadIdx.x];
+            m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+        }
+        m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
+        ss = m.x * m.x + m.y * m.y + m.z * m.z + m.w * m.w;
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
-    float tot = 0.0f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
-    const float scale = 1.0f / (sqrtf(tot) + 1e-8f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = threadIdx.x + 256 * i;
-        if (c < dim) {
-            if (out_mean != nullptr) out_mean[static_cast<size_t>(clip) * dim + c] = m[i];
-            if (out_unit != nullptr) out_unit[static_cast<size_t>(clip) * dim + c] = m[i] * scale;
-        }
+    if (threadIdx.x < groups) {
+        float tot = 0.0f;
+        for (int w = 0; w < (groups + 31) / 32; ++w) tot += red[w];
+        const float scale = 1.0f / (sqrtf(tot) + 1e-8f);
+        if (out_mean != nullptr) reinterpret_cast<float4*>(out_mean + static_cast<size_t>(clip) * dim)[threadIdx.x] = m;
+        if (out_unit != nullptr)
+            reinterpret_cast<float4*>(out_unit + static_cast<size_t>(clip) * dim)[threadIdx.x] =
+                make_float4(m.x * scale, m.y * scale, m.z * scale, m.w * scale);
     }
 }
 
 int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, int dim, float* out_mean,
                       float* out_unit, cudaStream_t stream) {
     CRE_REQUIRE(clips > 0, "pool_clips: no clips");
-    CRE_REQUIRE(dim > 0 && dim <= 1024, "pool_clips: dim %d out of range (<= 1024)", dim);
-    LaunchScope scope(CRE_K_POOL_CLIPS, 0.0, stream);
-    pool_clips_kernel<<<clips, 256, 0, stream>>>(frame_emb, offs, dim, out_mean, out_unit);
+    CRE_REQUIRE(dim > 0 && dim <= 1024 && dim % 4 == 0, "pool_clips: dim %d out of range (multiple of 4, <= 1024)", dim);
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(frame_emb) & 15) == 0 && (out_mean == nullptr || (reinterpret_cast<uintptr_t>(out_mean) & 15) == 0) &&
+                    (out_unit == nullptr || (reinterpret_cast<uintptr_t>(out_unit) & 15) == 0), "pool_clips: pointers must be 16-byte aligned");
+    LaunchScope scope(CRE_K_POOL_CLIPS, 0.0, stream);   // bytes depend on the device-side offsets: the caller knows them
+    pool_clips_kernel<<<clips, 1024, 0, stream>>>(frame_emb, offs, dim, out_mean, out_unit);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -349,6 +362,36 @@ int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t st
     return 0;
 }
 
+// gallery_topk prologue in ONE launch: the hi / lo split of the queries and the -inf fill of the partial lists (the scan is a
+// ~30 us kernel, so every extra launch in front of it shows)
+__global__ void topk_prepare_kernel(const float* __restrict__ q, int dim, int64_t total, __nv_bfloat16* __restrict__ out,
+                                    float* __restrict__ s, int32_t* __restrict__ idx, int64_t count) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int64_t r = i / dim;
+        const int c = static_cast<int>(i - r * dim);
+        const float v = q[i];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        out[r * 2 * dim + c] = hi;
+        out[r * 2 * dim + dim + c] = lo;
+    }
+    if (i < count) {
+        s[i] = -INFINITY;
+        idx[i] = 0x7fffffff;
+    }
+}
+
+int launch_topk_prepare(const float* q, int rows, int dim, __nv_bfloat16* out, float* scores, int32_t* idx, int64_t count,
+                        cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(rows) * dim;
+    const int64_t n = total > count ? total : count;
+    LaunchScope scope(CRE_K_SPLIT_HI_LO, 8.0 * total + 8.0 * count, stream);
+    topk_prepare_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(q, dim, total, out, scores, idx, count);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Merge candidate lists under the total order (score desc, index asc).  One warp per query: each
 // lane scans a strided share of the lists*per_list candidates into a private sorted top-k, then
@@ -368,18 +411,36 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < CRE_TOPK_MAX; ++j) { bs[j] = -INFINITY; bi[j] = 0x7fffffff; }
     const int total = lists * per_list;
-    for (int c = lane; c < total; c += 32) {
-        const int l = c / per_list, e = c % per_list;
-        const int64_t o = l * list_stride + query * query_stride + e;
-        float cs = scores[o];
-        int ci = idx[o];
-        if (better(cs, ci, bs[CRE_TOPK_MAX - 1], bi[CRE_TOPK_MAX - 1])) {
+    // candidates in batches of kBatch per lane: all loads of a batch are issued before the (dependent) insertions, so the
+    // kernel pays one memory latency per batch instead of one per candidate (it is latency bound: a few KB per query)
+    constexpr int kBatch = 8;
+    for (int c0 = lane; c0 < total; c0 += 32 * kBatch) {
+        float cs_[kBatch];
+        int ci_[kBatch];
 #pragma unroll
-            for (int j = 0; j < CRE_TOPK_MAX; ++j) {
-                if (better(cs, ci, bs[j], bi[j])) {
-                    const float ts = bs[j]; const int ti = bi[j];
-                    bs[j] = cs; bi[j] = ci;
-                    cs = ts; ci = ti;
+        for (int b = 0; b < kBatch; ++b) {
+            const int c = c0 + 32 * b;
+            cs_[b] = -INFINITY;
+            ci_[b] = 0x7fffffff;
+            if (c < total) {
+                const int l = c / per_list, e = c - l * per_list;
+                const int64_t o = l * list_stride + query * query_stride + e;
+                cs_[b] = __ldg(scores + o);
+                ci_[b] = __ldg(idx + o);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            float cs = cs_[b];
+            int ci = ci_[b];
+            if (better(cs, ci, bs[CRE_TOPK_MAX - 1], bi[CRE_TOPK_MAX - 1])) {
+#pragma unroll
+                for (int j = 0; j < CRE_TOPK_MAX; ++j) {
+                    if (better(cs, ci, bs[j], bi[j])) {
+                        const float ts = bs[j]; const int ti = bi[j];
+                        bs[j] = cs; bi[j] = ci;
+                        cs = ts; ci = ti;
+                    }
                 }
             }
         }

@@ -178,6 +178,8 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     CRE_REQUIRE(epi == EPI_TOPK || p.N % (epi_out_bf16(epi) ? 64 : 32) == 0, "gemm: N=%d must be a multiple of %d for this epilogue",
                 p.N, epi_out_bf16(epi) ? 64 : 32);
     CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
+    CRE_REQUIRE(epi != EPI_TOPK || p.K == 2 * p.b_k_extent, "gemm: TOPK expects A = [hi | lo] with K = 2 * b_k_extent (K=%d, extent=%d)", p.K,
+                p.b_k_extent);
     if (epi_resid_ln(epi)) {
         CRE_REQUIRE(p.N % kBlockN == 0 && p.N / 128 == p.ln_slots && p.ln_slots <= 8 && p.ln_stride >= 2 * p.ln_slots + kLnStatsPad,
                     "gemm: RESID_LN needs N %% 256 == 0 and N / 128 = ln_slots <= 8 (N=%d slots=%d stride=%d)", p.N, p.ln_slots, p.ln_stride);

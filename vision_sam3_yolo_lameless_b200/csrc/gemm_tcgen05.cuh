@@ -99,13 +99,14 @@ constexpr int ln_warp_bytes(int epi) { return (ln_x_slots(epi) + 1) * kEpiStageB
 constexpr int kLnStatsPad = 4;               // floats before the partials in one statistics row: [pivot, -, -, -]
 constexpr int default_stages_epi(int epi, int cg) {
     return epi == EPI_RESID_LN ? (cg == 1 ? 2 : 4) : epi == EPI_RESID_LN3 ? (cg == 1 ? 3 : 5)
-                                                   : default_stages(cg) - (epi == EPI_QKV ? 1 : 0);
+                                                   : default_stages(cg) - (epi == EPI_QKV || epi == EPI_TOPK ? 1 : 0);
 }
 
 template <int EPI, int CG, int STAGES>
 struct GemmCfg {
     static constexpr int kStages = STAGES;
-    static constexpr int kSmemA = kBlockM * kBlockK * 2;          // 16 KB
+    // EPI_TOPK stages TWO A boxes per k-block (the hi and the lo half of the fp32 queries, see the MMA issuer): 32 KB
+    static constexpr int kSmemA = kBlockM * kBlockK * 2 * (EPI == EPI_TOPK ? 2 : 1);   // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
     static constexpr int kEpiBytes = epi_resid_ln(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
@@ -137,11 +138,40 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     return d;
 }
 
-// gelu(x) = x * Phi(x) with the exact-erf Phi of nn.functional.gelu (HF:activations.py "gelu").  Phi(x) - 1/2 is odd:
-// Phi(x) = 1/2 + xc * P(xc^2), xc = clamp(x, +-4.5), P a degree-8 near-minimax fit constrained so that Phi(4.5) = 1
-// exactly (|x| > 4.5 then gives x and 0).  Max |error| on gelu over all x: 5.7e-5 (bf16 output half-ulp at |y| = 1 is
-// 2e-3); erff() costs ~30 FMA-pipe instructions per element and made the up-projection epilogue slower than its MMAs.
+// gelu(x) = x * Phi(x) with the exact-erf Phi of nn.functional.gelu (HF:activations.py "gelu").
+//
+// The up-projection (K = 768) is bound by its epilogue, not by its MMAs (ncu: tensor pipe 63 % active, 3.4e8 warp instructions
+// per launch), so the activation is priced in issue slots per element.  Default form (CRE_GELU_TANH = 1):
+//     Phi(x) = 1/2 + 1/2 tanh(x * (c1 + c3 t + c5 t^2)),  t = min(x^2, 50)
+// i.e. the exact identity erf(z) = tanh(atanh(erf(z))) with atanh(erf(x / sqrt 2)) / x fitted by a quadratic in x^2 (near-minimax
+// on |x| <= 7.07; beyond that the argument is >= 12.5 and tanh has saturated): max |error| on gelu 2.5e-5 with an exact tanh.
+// tanh is ONE MUFU op (tanh.approx.f32, relative error <= 2^-11), which adds at most 2.5e-4 |x| -- below the bf16 half-ulp of the
+// output for x > 0 and below 1e-3 absolute for -4 < x < 0 (measured on the B200: tests/test_gpu_kernels.py::test_gelu_epilogue_error).
+// Cost per element: 3 FMA-pipe + 1 ALU + 1 MUFU instruction slots instead of 6 + 2 + 0.
+//
+// CRE_GELU_TANH = 0: Phi(x) = 1/2 + xc * P(xc^2), xc = clamp(x, +-4.5), P a degree-8 near-minimax fit constrained so that
+// Phi(4.5) = 1 exactly; max |error| 5.7e-5, all on the FMA pipe (erff() itself costs ~30 FMA-pipe instructions per element).
+#ifndef CRE_GELU_TANH
+#define CRE_GELU_TANH 1
+#endif
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void gelu2(float& x0, float& x1) {
+#if CRE_GELU_TANH
+    const uint64_t x = pack2(x0, x1);
+    float t0, t1, q0, q1;
+    unpack2(mul2(x, x), t0, t1);
+    const uint64_t t = pack2(fminf(t0, 50.0f), fminf(t1, 50.0f));
+    uint64_t p = fma2(pack2(-3.519023885e-04f, -3.519023885e-04f), t, pack2(3.700802103e-02f, 3.700802103e-02f));
+    p = fma2(p, t, pack2(7.975052595e-01f, 7.975052595e-01f));
+    unpack2(mul2(p, x), q0, q1);
+    const uint64_t th = pack2(tanh_approx(q0), tanh_approx(q1));
+    const uint64_t hx = mul2(x, pack2(0.5f, 0.5f));
+    unpack2(fma2(hx, th, hx), x0, x1);
+#else
     const float a = fminf(fmaxf(x0, -4.5f), 4.5f), b = fminf(fmaxf(x1, -4.5f), 4.5f);
     const uint64_t xc = pack2(a, b);
     const uint64_t t = mul2(xc, xc);
@@ -157,6 +187,7 @@ __device__ __forceinline__ void gelu2(float& x0, float& x1) {
     const uint64_t g = fma2(xc, p, pack2(0.5f, 0.5f));
     const uint64_t y = mul2(pack2(x0, x1), g);
     unpack2(y, x0, x1);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -261,7 +292,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         t_end = num_tiles;
         t_step = num_workers;
     }
-    const int num_kb = p.K / kBlockK;
+    // EPI_TOPK: A = [hi | lo] (K = 2 * b_k_extent columns); one k-block covers the same 64 gallery columns for both halves, so the
+    // gallery tile (the HBM / L2 stream that bounds this kernel) is fetched ONCE and multiplied twice
+    const int num_kb = (EPI == EPI_TOPK ? p.b_k_extent : p.K) / kBlockK;
 
     if (warp == 0 && lane == 0) {
         // =============================== TMA producer ===============================
@@ -294,7 +327,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (prow >= 0) tma_prefetch_2d(&tmap_a, pkb * kBlockK, prow);
                 }
                 tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA, ka, row0, kEvictNormal);
-                tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, kEvictLast);
+                if constexpr (EPI == EPI_TOPK)
+                    tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2, ka + p.b_k_extent, row0, kEvictNormal);
+                tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, EPI == EPI_TOPK ? kEvictNormal : kEvictLast);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -320,6 +355,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
                         umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (EPI == EPI_TOPK) {   // + lo(query) . gallery into the same accumulator
+                            const uint64_t da_lo = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2);
+                            umma_bf16<CG>(tmem_d, da_lo + 2 * k, db + 2 * k, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit<CG>(empty_bar(stage));
