@@ -171,7 +171,7 @@ def run_reference(args, rank: int):
     v = sample * args.steps / dt
     sample_desc = (f"{sample} frames/step of {args.height}x{args.width} uint8 through extract_embedding (HF processor + fp32 batch-1 "
                    f"forward) + clip mean + numpy top-5 over {args.gallery_rows} rows")
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -180,7 +180,7 @@ def run_reference(args, rank: int):
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def workload_config(args, world):
@@ -220,8 +220,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("CRE_NCCL_DEBUG", "WARN")
+        if "CRE_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["CRE_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if args.cta_group:
         set_cta_group(args.cta_group)
@@ -408,14 +408,37 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                               for n, k in kernels.items()},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: park fd 1 on stderr for the whole run (NCCL prints its version banner to stdout at
+    the first communicator, libraries may print warnings) and keep the real stdout for emit_json()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj) -> None:
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -427,7 +450,7 @@ def main():
             # convenience: re-launch under torchrun
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
-            raise SystemExit(subprocess.call(cmd))
+            raise SystemExit(subprocess.call(cmd, stdout=_JSON_FD))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_b200(args, rank, world, local_rank)
 
