@@ -213,11 +213,21 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from vision_sam3_yolo_lameless_b200 import _lib
     from vision_sam3_yolo_lameless_b200.engine import ClipEmbedEngine, VitConfig, set_cta_group
     from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
-    from vision_sam3_yolo_lameless_b200.sharded import ShardedReID, shard_range
+    from vision_sam3_yolo_lameless_b200.sharded import ShardedReID, bind_host_to_gpu, shard_range
     from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit      # the CUDA arm never touches oracle/
+
+    h, w = args.height, args.width
+    # ---- cpu baseline (rank 0, N=1 only): BEFORE this process is bound to the GPU's NUMA node, so it sees every host core ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, n, threads, _ = cpu_reference_sample(args, args.cpu_seconds)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{n} frames of {h}x{w} uint8 through the reference's per-frame path (cvtColor, PIL, HF DINOv3ViTImageProcessor, "
+                         "HF DINOv3ViTModel fp32 batch 1, token mean; oracle/pipeline_ref.py)"}
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_host_to_gpu(local_rank)          # before any pinned allocation: staging buffers on the GPU's own NUMA node
     if world > 1:
         import datetime
         if "CRE_NCCL_DEBUG" in os.environ:
@@ -383,17 +393,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e2e = {"value": world * frames_total * e2e_steps / (te.item() / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(frames_total * per), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "api": "DINOv3Pipeline.embed_clips(list of pinned host clips) -> numpy clip embeddings + top-5",
+               "host_affinity": numa,
                "note": f"{distinct} distinct pinned clips cycled to form the {clips}-clip batch (all bytes are copied every step); "
                        "re-ID in e2e is against the rank-local gallery shard"}
         del host
-
-    # ---- cpu baseline (rank 0, N=1 only) ----------------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, n, threads, _ = cpu_reference_sample(args, args.cpu_seconds)
-        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"{n} frames of {h}x{w} uint8 through the reference's per-frame path (cvtColor, PIL, HF DINOv3ViTImageProcessor, "
-                         "HF DINOv3ViTModel fp32 batch 1, token mean; oracle/pipeline_ref.py)"}
 
     if rank == 0:
         line = {

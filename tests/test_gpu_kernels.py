@@ -191,6 +191,28 @@ def test_preprocess_vs_oracle(engine_small, h, w, kind, bgr):
     assert err < 1.2e-2, err                    # |x| <= 2.64 -> bf16 half-ulp 7.8e-3, plus fp32 summation-order noise
 
 
+@pytest.mark.parametrize("bgr", [True, False])
+def test_preprocess_no_resize_kernel_bit_identical(engine_small, bgr):
+    """Frames that are already 224 x 224 take the normalise + patchify kernel; it must reproduce the filtering kernel (identity
+    taps) bit for bit, for dense and for row-pitched input, and match the oracle."""
+    eng, dev = engine_small, engine_small.device
+    fr = common.noise_frames(5, 224, 224, seed=21)
+    dense = torch.from_numpy(fr).to(dev)
+    pitched = torch.zeros((5, 230, 240, 3), dtype=torch.uint8, device=dev)[:, :224, :224, :]    # row pitch 720 B, frame pitch 165 600 B
+    pitched.copy_(dense)
+    fast = eng.preprocess(dense, bgr=bgr).clone()
+    fast_p = eng.preprocess(pitched, bgr=bgr).clone()
+    _lib.set_tuning("preprocess_identity", 0)
+    try:
+        slow = eng.preprocess(dense, bgr=bgr).clone()
+    finally:
+        _lib.set_tuning("preprocess_identity", 1)
+    assert torch.equal(fast.view(torch.int16), slow.view(torch.int16))
+    assert torch.equal(fast_p.view(torch.int16), slow.view(torch.int16))
+    ref = preprocess_ref.patchify(preprocess_ref.preprocess(fr, bgr=bgr))
+    assert (fast.float().cpu() - torch.from_numpy(ref)).abs().max().item() < 1.2e-2
+
+
 def test_preprocess_vs_hf_processor_golden(engine_small, golden):
     from oracle.make_golden import PREPROCESS_CASES, frames_for
     want = np.load(golden / "preprocess.npz")

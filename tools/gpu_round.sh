@@ -16,3 +16,12 @@ echo "ncu list rc=$?"
 timeout 300 $SMALL > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention|preprocess|layernorm|final_norm" -s 0 -c 11 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
+# the remaining kernels of the step (K3 pooling, K4 scan + prologue + merge, final norm + token mean, row statistics, prefix fill):
+# one launch each, from the same small command
+timeout 300 $SMALL > gpurun_out/plain3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k regex:"pool_clips|topk_prepare|merge_topk|final_norm_mean|row_stats|fill_prefix|gemm_tn_kernel<6" -c 7 -f -o gpurun_out/prof_tail $SMALL > gpurun_out/ncu_tail.log 2>&1
+echo "ncu tail rc=$?"
+for r in prof_layer0 prof_tail; do
+  [ -f gpurun_out/$r.ncu-rep ] && ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null
+done

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_gpu.log | head
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 300 python tools/prep_bench.py 1 > gpurun_out/prep_bench.log 2>&1; echo "prep_bench rc=$?"; cat gpurun_out/prep_bench.log

@@ -818,6 +818,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_preprocess_tma(value);
         return 0;
     }
+    if (strcmp(key, "preprocess_identity") == 0) {   // 0: frames that need no resize go through the filtering kernel anyway
+        set_preprocess_identity(value);
+        return 0;
+    }
     if (strcmp(key, "resid_ln_deep") == 0) {
         g_resid_ln_deep = value & 3;
         return 0;

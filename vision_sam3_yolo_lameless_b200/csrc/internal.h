@@ -44,6 +44,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
 int make_tmap_u8_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t row_pitch,
                     int64_t frame_pitch, int box_cols, int box_rows);
 void set_preprocess_tma(int on);
+void set_preprocess_identity(int on);
 
 struct GemmParams;
 // epi is a cre::GemmEpi value; cg = 1 | 2

@@ -47,6 +47,10 @@ __device__ __forceinline__ float byte_as_unit_float(uint32_t word, uint32_t sele
     return __uint_as_float(__byte_perm(word, 0x3F800000u, selector));
 }
 
+// (x / 255 - mean) / std exactly as every K1 variant evaluates it (one definition so that the compiler contracts it the same way
+// everywhere: the variants must agree bit for bit)
+__device__ __forceinline__ float normalise_px(float s, float mean, float inv_std) { return (s * (1.0f / 255.0f) - mean) * inv_std; }
+
 __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PreParams p) {
     extern __shared__ __align__(16) float vbuf[];  // [16][sstride]
     const int band = blockIdx.x, py = blockIdx.y;
@@ -154,8 +158,55 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int c = p.bgr ? 2 - j : j;  // output (RGB) channel of memory channel j
-            o[c * 256] = __float2bfloat16_rn((sm[j] * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c]);
+            o[c * 256] = __float2bfloat16_rn(normalise_px(sm[j], p.mean[c], p.inv_std[c]));
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// No-resize variant (frame size == model input size: the 224 x 224 clips of BASELINE configs[0] / [3] / [4], 518 / 592 inputs):
+// the antialias tables degenerate to the identity (weights {1, 0}), so K1 is normalise + patchify and purely HBM-bound
+// (3 B in, 6 B out per pixel).  Thread = one 16-pixel row of one patch: 48 contiguous input bytes (three 16-byte loads; a warp
+// covers two neighbouring patches, i.e. 96 contiguous bytes per image row) -> per channel 32 contiguous output bytes (16 threads
+// of a patch write 512 contiguous bytes).  Same arithmetic as the filtered path with identity taps -- 1 + b 2^-15 -> b exactly
+// -> normalise_px -> bf16 -- so the result is bit-identical to preprocess_kernel on the same input.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_identity_kernel(const PreParams p, int64_t total) {
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (gid >= total) return;
+    const int ky = static_cast<int>(gid & 15);
+    const int64_t patch = gid >> 4;
+    const int px = static_cast<int>(patch % p.gw);
+    const int64_t t = patch / p.gw;
+    const int py = static_cast<int>(t % p.gh);
+    const int64_t frame = t / p.gh;
+    const uint8_t* src = p.frames + frame * p.frame_pitch + static_cast<int64_t>(py * 16 + ky) * p.row_pitch + px * 48;
+    uint32_t wds[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        wds[4 * i] = q.x; wds[4 * i + 1] = q.y; wds[4 * i + 2] = q.z; wds[4 * i + 3] = q.w;
+    }
+    float v[48];   // byte 3 i + j = pixel i, memory channel j
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        v[4 * i] = fmaf(byte_as_unit_float(wds[i], 0x7604u), 32768.0f, -32768.0f);
+        v[4 * i + 1] = fmaf(byte_as_unit_float(wds[i], 0x7614u), 32768.0f, -32768.0f);
+        v[4 * i + 2] = fmaf(byte_as_unit_float(wds[i], 0x7624u), 32768.0f, -32768.0f);
+        v[4 * i + 3] = fmaf(byte_as_unit_float(wds[i], 0x7634u), 32768.0f, -32768.0f);
+    }
+    __nv_bfloat16* o = p.out + patch * 768 + ky * 16;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = p.bgr ? 2 - j : j;   // output (RGB) channel of memory channel j
+        const float mean = p.mean[c], inv_std = p.inv_std[c];
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(normalise_px(v[6 * i + j], mean, inv_std), normalise_px(v[6 * i + 3 + j], mean, inv_std));
+        uint4* dst = reinterpret_cast<uint4*>(o + c * 256);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
 }
 
@@ -397,7 +448,7 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int c = p.bgr ? 2 - j : j;  // output (RGB) channel of memory channel j
-                    o[c * 256] = __float2bfloat16_rn((sm[j] * (1.0f / 255.0f) - p.mean[c]) * p.inv_std[c]);
+                    o[c * 256] = __float2bfloat16_rn(normalise_px(sm[j], p.mean[c], p.inv_std[c]));
                 }
             }
             __syncwarp();
@@ -406,8 +457,9 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     }
 }
 
-static int g_pre_tma = 1, g_pre_debug = 0;
+static int g_pre_tma = 1, g_pre_debug = 0, g_pre_identity = 1;
 void set_preprocess_tma(int on) { g_pre_tma = on & 1; g_pre_debug = on >> 1; }
+void set_preprocess_identity(int on) { g_pre_identity = on; }
 
 // returns 1 if the TMA variant was launched, 0 if the input does not qualify, negative on error
 static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStream_t stream) {
@@ -477,6 +529,14 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     p.xkmax = a.tx.kmax;
     p.vec = ((reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && a.row_pitch % 16 == 0 && a.frame_pitch % 16 == 0) ? 1 : 0;
     p.rois = a.rois;
+    if (a.rois == nullptr && g_pre_identity && p.vec && a.ty.in == a.ty.out && a.tx.in == a.tx.out) {
+        // no resize: normalise + patchify only
+        const int64_t total = static_cast<int64_t>(a.n) * a.gh * a.gw * 16;
+        LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
+        preprocess_identity_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p, total);
+        CRE_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (a.rois == nullptr) {
         const int rc = try_launch_preprocess_tma(a, p, stream);
         if (rc != 0) return rc < 0 ? rc : 0;
