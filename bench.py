@@ -115,6 +115,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own per-frame CPU path (oracle/pipeline_ref.py), bounded sample
 # ----------------------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """The CPU arm uses every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    otherwise throttle the reference to one thread at N > 1)."""
+    import torch
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return n
+
+
 def cpu_reference_sample(args, seconds: float, frames_cap: int = 10_000):
     """Times ReferencePipelineCPU.extract_embedding (main.py:95-115 semantics: cvtColor -> PIL -> HF processor -> batch-1 fp32
     forward -> token mean) on frames of the benchmark's shape for about `seconds`; returns (frames/s, frames, threads)."""
@@ -124,6 +134,7 @@ def cpu_reference_sample(args, seconds: float, frames_cap: int = 10_000):
     from oracle import pipeline_ref
     from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 
+    use_all_host_threads()
     pipe = pipeline_ref.ReferencePipelineCPU(random_init_vit(args.model))
     rng = np.random.default_rng(0)
     frames = rng.integers(0, 256, size=(4, args.height, args.width, 3), dtype=np.uint8)
@@ -150,6 +161,7 @@ def run_reference(args, rank: int):
     from oracle import pipeline_ref, reid_ref
     from vision_sam3_yolo_lameless_b200.synthetic import VIT_SHAPES, random_init_vit
 
+    use_all_host_threads()
     pipe = pipeline_ref.ReferencePipelineCPU(random_init_vit(args.model))
     rng = np.random.default_rng(0)
     sample = 8                                             # frames per step: 1 clip sampled at 8 frames
@@ -194,7 +206,7 @@ def workload_config(args, world):
     return {"workload": f"{which}: {name} embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
                         f"({args.clips * args.frames_per_clip} frames) decoded as {args.width}x{args.height} uint8 incl. fused "
                         f"resize/normalize, + cosine top-5 re-ID against a {args.gallery_rows}-row gallery; per rank",
-            "model": args.model, "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip,
+            "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip,
             "frame_hw": [args.height, args.width], "gallery_rows": args.gallery_rows, "top_k": 5,
             "batch_frames": args.batch_frames, "model_input": args.resize,
             "parallelism": f"dp{world} clips + row-sharded gallery",
