@@ -283,7 +283,8 @@ def test_pool_clips(engine_small):
     assert torch.isfinite(unit).all()
 
 
-@pytest.mark.parametrize("q,n,dim", [(3, 1000, 768), (130, 5000, 768), (64, 100000, 768), (5, 3, 768), (9, 700, 1024)])
+@pytest.mark.parametrize("q,n,dim", [(3, 1000, 768), (130, 5000, 768), (64, 100000, 768), (5, 3, 768), (9, 700, 1024),
+                                     (1, 100000, 768), (2, 5000, 1024), (1, 3, 768), (2, 777, 768), (1, 20011, 1024)])
 def test_gallery_topk_bit_exact(engine_small, q, n, dim):
     eng, dev = engine_small, engine_small.device
     gen = torch.Generator(device=dev).manual_seed(q + n)
@@ -305,6 +306,32 @@ def test_gallery_topk_bit_exact(engine_small, q, n, dim):
         assert (i.cpu().numpy()[:, kk:] == 0x7FFFFFFF).all() and np.isneginf(s.cpu().numpy()[:, kk:]).all()
     if n > 10:
         assert i[0].tolist()[:3] == [1007, 1000 + n // 2, 1000 + n - 1]
+
+
+@pytest.mark.parametrize("q,dim", [(1, 768), (2, 768), (1, 1024), (2, 1024)])
+def test_gallery_serving_scan_agrees_with_tile_gemm(engine_small, q, dim):
+    """Q <= 2 takes the HBM-streaming scan (fp32 query x bf16 row on the CUDA cores); the tile GEMM (hi + lo bf16 query halves on the
+    tensor cores) must pick the same rows, with scores equal to fp32 rounding, including planted ties and every k."""
+    eng, dev = engine_small, engine_small.device
+    gen = torch.Generator(device=dev).manual_seed(100 + q + dim)
+    n = 30011
+    g = torch.nn.functional.normalize(torch.randn(n, dim, device=dev, generator=gen), dim=1)
+    g[17] = g[29000]
+    g[12345] = g[29000]
+    gb = g.to(torch.bfloat16).contiguous()
+    qv = torch.nn.functional.normalize(g[29000:29000 + q] + 0.02 * torch.randn(q, dim, device=dev, generator=gen), dim=1)
+    for k in (1, 5, 8):
+        s1, i1, d1 = eng.gallery_topk(qv, gb, k=k, row_base=7, dump_scores=True)
+        _lib.set_tuning("scan_small", 0)
+        try:
+            s0, i0, d0 = eng.gallery_topk(qv, gb, k=k, row_base=7, dump_scores=True)
+        finally:
+            _lib.set_tuning("scan_small", 1)
+        assert (i1.cpu().numpy() == reid_ref.topk_rule(d1.cpu().numpy(), k, row_base=7)[1]).all()
+        np.testing.assert_allclose(d1.cpu().numpy(), d0.cpu().numpy(), atol=5e-6)    # the oracle tolerance of both paths
+        assert i1[0, 0].item() == 7 + 17                                   # three identical rows: the smallest index leads
+        if k >= 5:
+            assert i1[0].tolist()[:3] == [7 + 17, 7 + 12345, 7 + 29000] and i0[0].tolist()[:3] == i1[0].tolist()[:3]
 
 
 def test_gallery_topk_empty_and_k_range(engine_small):

@@ -14,7 +14,7 @@ dev = eng.device
 g = torch.Generator(device=dev).manual_seed(3)
 for rows in (100_000, 12_500):
     gal = torch.nn.functional.normalize(torch.randn(rows, 768, device=dev, generator=g), dim=1).to(torch.bfloat16)
-    for q in (1, 64, 128, 1024):
+    for q in (1, 2, 64, 128, 1024):
         qs = torch.nn.functional.normalize(torch.randn(q, 768, device=dev, generator=g), dim=1)
         eng.gallery_topk(qs, gal, k=5)
         _lib.profile_start(4096)

@@ -184,6 +184,7 @@ struct cre_ctx {
     int device;
     int num_sms;
     uint8_t* fold_buf = nullptr;
+    int* scan_counter = nullptr;   // "CTAs finished" counter of the serving-form gallery scan (zero between calls)
     std::vector<FoldedLinear> fold_qkv, fold_up;
     std::map<std::pair<int, int>, DevTable> resize_tables;
     std::map<std::pair<int, int>, RopeTable> rope_tables;
@@ -349,9 +350,14 @@ int32_t cre_create(const cre_model_cfg* cfg, const void* packed_weights_dev, int
     c->weights = static_cast<const uint8_t*>(packed_weights_dev);
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    const int rc = build_folded_weights(c);   // the packed blob must already hold the weights (it does: see engine.py)
+    int rc = build_folded_weights(c);   // the packed blob must already hold the weights (it does: see engine.py)
+    if (rc == 0 && (cudaMalloc(&c->scan_counter, 256) != cudaSuccess || cudaMemset(c->scan_counter, 0, 256) != cudaSuccess)) {
+        set_error("cre_create: cannot allocate the scan counter");
+        rc = -2;
+    }
     if (rc) {
         cudaFree(c->fold_buf);
+        cudaFree(c->scan_counter);
         delete c;
         return rc;
     }
@@ -368,6 +374,7 @@ int32_t cre_destroy(cre_ctx* ctx) {
     }
     for (auto& kv : ctx->rope_tables) cudaFree(kv.second.axis);
     cudaFree(ctx->fold_buf);
+    cudaFree(ctx->scan_counter);
     delete ctx;
     return 0;
 }
@@ -642,6 +649,7 @@ int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_d
 }
 
 static const int kMaxSlots = 512;
+static int g_scan_small = 1;   // tuning: 0 routes every query count through the tile GEMM
 
 int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k) {
     if (q <= 0 || dim <= 0 || k <= 0 || k > CRE_TOPK_MAX) {
@@ -674,6 +682,14 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
     float* part_s = reinterpret_cast<float*>(sp + a_bytes);
     int32_t* part_i = reinterpret_cast<int32_t*>(sp + a_bytes + part_bytes);
 
+    // serving form (Q <= 2: one message = one query): HBM-streaming scan on the CUDA cores, one partial list per CTA
+    if (g_scan_small) {
+        int small_slots = 2 * ctx->num_sms;
+        if (small_slots > kMaxSlots) small_slots = kMaxSlots;
+        const int took = launch_gallery_scan_small(queries_dev, q, dim, gallery_dev, rows, row_base, k, part_s, part_i, small_slots,
+                                                   dump_scores_dev, ctx->scan_counter, out_scores_dev, out_idx_dev, stream);
+        if (took != 0) return took < 0 ? took : 0;     // the kernel's last CTA has merged the partial lists into the result
+    }
     const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
     const int slots = 2 * workers;
     CRE_REQUIRE(slots <= kMaxSlots, "gallery_topk: %d partial slots exceed %d", slots, kMaxSlots);
@@ -816,6 +832,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     }
     if (strcmp(key, "preprocess_tma") == 0) {
         set_preprocess_tma(value);
+        return 0;
+    }
+    if (strcmp(key, "scan_small") == 0) {
+        g_scan_small = value != 0;
         return 0;
     }
     if (strcmp(key, "preprocess_identity") == 0) {   // 0: frames that need no resize go through the filtering kernel anyway

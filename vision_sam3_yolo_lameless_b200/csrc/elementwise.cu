@@ -482,6 +482,206 @@ int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stri
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4, serving form: Q <= 2 queries against the whole gallery shard.  One pipeline.dinov3 message carries ONE clip embedding
+// (services/tracking-service/app/main.py:318-334 -> matcher.py:127-132; dinov3 main.py:168-172), so this -- not the batched
+// tile GEMM, whose 128-row MMA tile costs the same tensor time for 1 query as for 128 -- is the per-message re-ID step.
+// Pure HBM stream: every warp walks rows w, w + W, ... (ascending), a lane owns the 16-byte chunks lane, lane + 32, ... of a
+// row (three for D = 768), the fp32 query slices live in registers (no hi / lo split: fp32 query x bf16 row, fp32 accumulate),
+// RU rows are in flight per lane, a 5-step shuffle tree finishes the dot products, and lane q keeps query q's running top-k.
+// Block merge through shared memory -> one partial list per CTA; the last CTA to finish merges the lists into the result.
+// ---------------------------------------------------------------------------------------------
+template <int Q, int CH, int RU>
+__global__ void __launch_bounds__(256, 2)
+gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16* __restrict__ gallery, int rows, int row_base, int k,
+                          float* part_s, int32_t* part_i, int slots, float* __restrict__ dump, int* done_counter,
+                          float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+    constexpr int DIM = CH * 256;
+    static_assert(CRE_TOPK_MAX == 8, "the block merge below maps 64 candidates onto 32 lanes x 2");
+    __shared__ float sh_s[8][Q][CRE_TOPK_MAX];
+    __shared__ int sh_i[8][Q][CRE_TOPK_MAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    float qreg[Q][CH][8];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(queries + q * DIM + 8 * (lane + 32 * c)));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(queries + q * DIM + 8 * (lane + 32 * c)) + 1);
+            qreg[q][c][0] = a.x; qreg[q][c][1] = a.y; qreg[q][c][2] = a.z; qreg[q][c][3] = a.w;
+            qreg[q][c][4] = b.x; qreg[q][c][5] = b.y; qreg[q][c][6] = b.z; qreg[q][c][7] = b.w;
+        }
+    float ts[CRE_TOPK_MAX];     // lane q (< Q): running top list of query q, sorted under (score desc, index asc)
+    int ti[CRE_TOPK_MAX];
+#pragma unroll
+    for (int j = 0; j < CRE_TOPK_MAX; ++j) { ts[j] = -INFINITY; ti[j] = 0x7fffffff; }
+
+    for (int r0 = gw; r0 < rows; r0 += nw * RU) {
+        uint4 g[RU][CH];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * nw;
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                g[u][c] = r < rows ? __ldg(reinterpret_cast<const uint4*>(gallery + static_cast<size_t>(r) * DIM) + lane + 32 * c)
+                                   : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * nw;          // ascending within the warp: on equal scores the smaller index is met first
+            float acc[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc[q] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint32_t w[4] = {g[u][c].x, g[u][c].y, g[u][c].z, g[u][c].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        acc[q] = fmaf(lo, qreg[q][c][2 * i], acc[q]);
+                        acc[q] = fmaf(hi, qreg[q][c][2 * i + 1], acc[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+            if (r < rows) {
+                float mine = acc[0];
+#pragma unroll
+                for (int q = 1; q < Q; ++q) mine = lane == q ? acc[q] : mine;
+                if (lane < Q) {
+                    if (dump != nullptr) dump[static_cast<size_t>(lane) * rows + r] = mine;
+                    if (mine > ts[CRE_TOPK_MAX - 1]) {
+                        float cs = mine;
+                        int ci = row_base + r;
+#pragma unroll
+                        for (int j = 0; j < CRE_TOPK_MAX; ++j) {
+                            if (cs > ts[j]) {
+                                const float t1 = ts[j]; const int t2 = ti[j];
+                                ts[j] = cs; ti[j] = ci;
+                                cs = t1; ci = t2;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane < Q) {
+#pragma unroll
+        for (int j = 0; j < CRE_TOPK_MAX; ++j) { sh_s[warp][lane][j] = ts[j]; sh_i[warp][lane][j] = ti[j]; }
+    }
+    __syncthreads();
+    if (warp < Q) {   // warp q merges the 8 lists of query q: 64 candidates, two per lane, k rounds of a warp arg-best
+        const int q = warp;
+        float h_s = sh_s[lane >> 3][q][lane & 7], n_s = sh_s[(lane >> 3) + 4][q][lane & 7];
+        int h_i = sh_i[lane >> 3][q][lane & 7], n_i = sh_i[(lane >> 3) + 4][q][lane & 7];
+        if (better(n_s, n_i, h_s, h_i)) {
+            const float t1 = h_s; const int t2 = h_i;
+            h_s = n_s; h_i = n_i; n_s = t1; n_i = t2;
+        }
+        for (int r = 0; r < k; ++r) {
+            float ws = h_s;
+            int wi = h_i, wl = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (better(os, oi, ws, wi) || (os == ws && oi == wi && ol < wl)) { ws = os; wi = oi; wl = ol; }
+            }
+            if (lane == 0) {
+                const size_t o = (static_cast<size_t>(q) * slots + blockIdx.x) * k + r;
+                part_s[o] = ws;
+                part_i[o] = wi;
+            }
+            if (lane == wl) { h_s = n_s; h_i = n_i; n_s = -INFINITY; n_i = 0x7fffffff; }
+        }
+    }
+
+    // ---- final merge by the LAST CTA to finish (no second launch: the whole call is one ~30 us kernel) ----
+    __shared__ int is_last;
+    __shared__ float red_s[8];
+    __shared__ int red_i[8];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this CTA's partial lists are visible device-wide ...
+        is_last = atomicAdd(done_counter, 1) == static_cast<int>(gridDim.x) - 1;   // ... before it is counted
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    constexpr int NC = 16;                                 // candidates per thread: slots * k <= 512 * 8 = 256 * 16
+    const int total = slots * k;
+    for (int q = 0; q < Q; ++q) {
+        float cs[NC];
+        int ci[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int c = threadIdx.x + 256 * j;
+            cs[j] = -INFINITY;
+            ci[j] = 0x7fffffff;
+            if (c < total) {
+                cs[j] = __ldcg(part_s + static_cast<size_t>(q) * total + c);
+                ci[j] = __ldcg(part_i + static_cast<size_t>(q) * total + c);
+            }
+        }
+        for (int r = 0; r < k; ++r) {                      // k rounds of a block-wide arg-best under (score desc, index asc)
+            float bs = cs[0];
+            int bi = ci[0];
+#pragma unroll
+            for (int j = 1; j < NC; ++j)
+                if (better(cs[j], ci[j], bs, bi)) { bs = cs[j]; bi = ci[j]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+            }
+            if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; }
+            __syncthreads();
+            float ws = red_s[0];
+            int wi = red_i[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w)
+                if (better(red_s[w], red_i[w], ws, wi)) { ws = red_s[w]; wi = red_i[w]; }
+            if (threadIdx.x == 0) {
+                out_scores[q * k + r] = ws;
+                out_idx[q * k + r] = wi;
+            }
+#pragma unroll
+            for (int j = 0; j < NC; ++j)                    // gallery indices are unique: exactly one thread owns the winner
+                if (ci[j] == wi && wi != 0x7fffffff) { cs[j] = -INFINITY; ci[j] = 0x7fffffff; }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) *done_counter = 0;               // ready for the next call on this context
+}
+
+// returns 1 if the serving-form scan was launched (then `slots` partial lists per query are complete), 0 if the problem does
+// not qualify (the caller falls back to the tile GEMM), negative on error
+int launch_gallery_scan_small(const float* queries, int q, int dim, const void* gallery, int rows, int row_base, int k, float* part_s,
+                              int32_t* part_i, int slots, float* dump, int* done_counter, float* out_scores, int32_t* out_idx,
+                              cudaStream_t stream) {
+    if (q < 1 || q > 2 || (dim != 768 && dim != 1024) || done_counter == nullptr || slots * k > 256 * 16) return 0;
+    if ((reinterpret_cast<uintptr_t>(gallery) & 15) != 0 || (reinterpret_cast<uintptr_t>(queries) & 15) != 0) return 0;
+    LaunchScope scope(CRE_K_GEMM_TOPK, 2.0 * rows * dim, stream);
+    const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gallery);
+#define CRE_SCAN(Q_, CH_, RU_) gallery_scan_small_kernel<Q_, CH_, RU_><<<slots, 256, 0, stream>>>(queries, g, rows, row_base, k, part_s, part_i, slots, dump, done_counter, out_scores, out_idx)
+    if (q == 1 && dim == 768) CRE_SCAN(1, 3, 4);
+    else if (q == 1) CRE_SCAN(1, 4, 4);
+    else if (dim == 768) CRE_SCAN(2, 3, 2);
+    else CRE_SCAN(2, 4, 2);
+#undef CRE_SCAN
+    CRE_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 // gallery row <- bf16(normalise(momentum * row + (1 - momentum) * unit_q))   (matcher.py:281-285); one CTA
 __global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* __restrict__ row, int dim,
                                                                  const float* __restrict__ uq, float momentum) {

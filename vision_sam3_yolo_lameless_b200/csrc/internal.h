@@ -75,6 +75,9 @@ int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, in
                       float* out_unit, cudaStream_t stream);
 int launch_split_hi_lo(const float* q, int rows, int dim, __nv_bfloat16* out, cudaStream_t stream);
 int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t stream);
+int launch_gallery_scan_small(const float* queries, int q, int dim, const void* gallery, int rows, int row_base, int k, float* part_s,
+                              int32_t* part_i, int slots, float* dump, int* done_counter, float* out_scores, int32_t* out_idx,
+                              cudaStream_t stream);
 int launch_topk_prepare(const float* q, int rows, int dim, __nv_bfloat16* out, float* scores, int32_t* idx, int64_t count,
                         cudaStream_t stream);
 int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stride, int64_t query_stride,

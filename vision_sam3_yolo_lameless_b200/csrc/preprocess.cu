@@ -265,16 +265,30 @@ int launch_build_roi_tables(const int32_t* rois, int n_rois, int oh, int ow, int
 // TMA-staged, warp-specialised variant (16-byte aligned frames and pitches; the tile must fit shared memory twice).
 // Persistent: one CTA per SM walks tiles (frame, patch row, patch) in raster order.
 //
-//   warp 20 (one lane)  tile scheduler + TMA producer: the raw uint8 rows the tile's 16 output rows depend on -- rows_tile rows
+//   warp 0 (one lane)   tile scheduler + TMA producer: the raw uint8 rows the tile's 16 output rows depend on -- rows_tile rows
 //                       x nbox 256-byte boxes -- land in a 2-deep ring; no thread ever waits on a global load of pixels.
-//   warps 0..15         pass 1, warp r = output row r of the patch, lane = 16-byte column group: vertical taps from shared
+//   warps 9..24         pass 1, warp 9 + r = output row r of the patch, lane = 16-byte column group: vertical taps from shared
 //                       memory (same arithmetic and order as preprocess_kernel: results are bit-identical) -> vbuf ring.
-//   warps 16..19        pass 2: horizontal taps + normalise + bf16 + patch-order stores, two pixels per thread.
+//   warps 1..8          pass 2: horizontal taps + normalise + bf16 + patch-order stores, one pixel per thread.
 //
 // The three roles are connected by mbarriers only (raw full/empty, vbuf full/empty): no __syncthreads in the tile loop.
 // =====================================================================================================================
-constexpr int kPtRowWarps = 16, kPtColWarps = 4;
+constexpr int kPtRowWarps = 16, kPtColWarps = 8;
 constexpr int kPtThreads = (kPtRowWarps + kPtColWarps + 1) * 32;
+// warp roles by index: the scheduler is warp 0, the column warps follow, the row warps come LAST -- the SM's warp arbiter prefers
+// the highest warp id among the eligible ones, and the row warps (ALU-pipe bound) are the stage everything else waits for
+constexpr int kPtColWarp0 = 1, kPtRowWarp0 = 1 + kPtColWarps;
+
+// wait with back-off: the waiting roles (column warps, scheduler) would otherwise spend the row warps' issue slots on polling
+// (ncu: 28 % of the kernel's executed instructions were mbarrier polls)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(200);
+    }
+    __trap();
+}
 constexpr int kPtParamInts = 8;   // per tile: frame, py, px, b0, y_first, nvec
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -327,13 +341,13 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     }
     __syncthreads();
 
-    if (warp == kPtRowWarps + kPtColWarps) {
+    if (warp == 0) {
         // =============================== scheduler + TMA producer ===============================
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
                 const int buf = it & 1;
-                if (it >= 2) mbar_wait(raw_empty(buf), static_cast<uint32_t>((it >> 1) - 1) & 1u);
+                if (it >= 2) mbar_wait_backoff(raw_empty(buf), static_cast<uint32_t>((it >> 1) - 1) & 1u);
                 const int frame = tile / per_frame, rem = tile - frame * per_frame;
                 const int py = rem / p.gw, px = rem - py * p.gw;
                 const int ox0 = px * 16;
@@ -349,9 +363,9 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
                     tma_load_3d(&tmap, raw_full(buf), base_u32 + buf * raw_bytes + j * rows_tile * 256, b0 + j * 256, y_first, frame);
             }
         }
-    } else if (warp < kPtRowWarps) {
+    } else if (warp >= kPtRowWarp0) {
         // =============================== pass 1: vertical filter, warp = output row ===============================
-        const int r = warp;
+        const int r = warp - kPtRowWarp0;
         const int rot = (lane >> 1) & 3;   // store-order rotation: the four 16-byte stores of a lane hit all bank groups evenly
         int it = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
@@ -418,19 +432,20 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
         }
     } else {
         // =============================== pass 2: horizontal filter + normalise + patchify ===============================
-        const int t = tid - kPtRowWarps * 32;   // 0..127: pixels t and t + 128 of the 16 x 16 patch
+        // one thread per pixel of the 16 x 16 patch: the horizontal pass is a chain of shared-memory loads per tap, i.e. latency
+        // bound per warp -- with 4 warps x 2 pixels it was the stage the 16 row warps ended up waiting for (ncu: 28 % of the
+        // kernel's executed instructions were their mbarrier polls)
+        const int pix = tid - kPtColWarp0 * 32;   // 0..255
+        const int ky = pix >> 4, kx = pix & 15;
         int it = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
             const int buf = it & 1;
-            mbar_wait(vb_full(buf), static_cast<uint32_t>(it >> 1) & 1u);
+            mbar_wait_backoff(vb_full(buf), static_cast<uint32_t>(it >> 1) & 1u);
             const int* pr = params + (it & 3) * kPtParamInts;
             const int frame = pr[0], py = pr[1], px = pr[2], b0 = pr[3];
             const float* vbuf = vb0 + buf * vb_floats;
             const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px;
-#pragma unroll
-            for (int half = 0; half < 2 && !(debug & 1); ++half) {
-                const int pix = t + half * 128;
-                const int ky = pix >> 4, kx = pix & 15;
+            if (!(debug & 1)) {
                 const int ox = px * 16 + kx;
                 const int x0 = s_xlo[ox], cnt = s_xcnt[ox];
                 const float* wx = s_xw + ox * p.xkmax;
