@@ -122,7 +122,9 @@ int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_d
 
 /* K4. Cosine re-ID against one gallery shard.  queries_dev f32 [q, dim] (L2-normalised by the caller via
  * cre_pool_clips), gallery_dev bf16 [rows, dim] row-major, L2-normalised rows.  Scores are
- * fp32-query x bf16-gallery dot products accumulated in fp32 (queries are split hi+lo bf16 internally).
+ * fp32-query x bf16-gallery dot products accumulated in fp32: q <= 2 (one message = one query, the reference's call pattern)
+ * streams the shard once on the CUDA cores with the fp32 query in registers, one launch; larger q runs a tcgen05 tile GEMM with the
+ * queries split hi+lo bf16 internally.  All device pointers 16-byte aligned; frame_emb / out_* of cre_pool_clips likewise.
  * Writes the k best (score desc, index asc) per query: out_scores_dev f32 [q, k], out_idx_dev i32 [q, k]
  * with idx = row_base + local row; missing entries (rows < k) are (-inf, INT32_MAX).
  * scratch_dev: cre_gallery_scratch_bytes(q, dim, k) bytes, 256-byte aligned.  dump_scores_dev (optional, may be NULL):
