@@ -16,12 +16,16 @@ echo "ncu list rc=$?"
 timeout 300 $SMALL > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention|preprocess|layernorm|final_norm" -s 0 -c 11 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
-# the remaining kernels of the step (K3 pooling, K4 scan + prologue + merge, final norm + token mean, row statistics, prefix fill):
-# one launch each, from the same small command
+# the remaining kernels of the step (final norm + token mean, row statistics, prefix fill) ...
 timeout 300 $SMALL > gpurun_out/plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:"pool_clips|topk_prepare|merge_topk|final_norm_mean|row_stats|fill_prefix|gemm_tn_kernel<6" -c 7 -f -o gpurun_out/prof_tail $SMALL > gpurun_out/ncu_tail.log 2>&1
+    -k regex:"final_norm_mean|row_stats|fill_prefix" -c 3 -f -o gpurun_out/prof_tail $SMALL > gpurun_out/ncu_tail.log 2>&1
 echo "ncu tail rc=$?"
-for r in prof_layer0 prof_tail; do
+# ... and K3 + both forms of K4 at the bench's sizes (second round of tools/topk_profile.py: 5 launches after the first 5)
+timeout 300 python tools/topk_profile.py > gpurun_out/plain4.log 2>&1 && \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k regex:"pool_clips|topk_prepare|merge_topk|gallery_scan_small|gemm_tn_kernel<6" -s 5 -c 5 -f -o gpurun_out/prof_reid python tools/topk_profile.py > gpurun_out/ncu_reid.log 2>&1
+echo "ncu reid rc=$?"
+for r in prof_layer0 prof_tail prof_reid; do
   [ -f gpurun_out/$r.ncu-rep ] && ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null
 done

@@ -399,6 +399,68 @@ int launch_topk_prepare(const float* q, int rows, int dim, __nv_bfloat16* out, f
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
 
+// Block-wide (256 threads) selection of the k best of `total` <= 256 * kSelNC candidates under (score desc, index asc); equal
+// (score, index) pairs are taken in candidate order, so duplicates come out as often as they went in.  Every thread holds
+// kSelNC candidates in registers (all loads independent: one memory latency), then k rounds of thread-best -> warp arg-best ->
+// 8-entry shared-memory arg-best; the owner of the winner retires it.  red_* : 8 entries each.  Thread 0 writes the result.
+constexpr int kSelNC = 16;
+template <typename LoadS, typename LoadI>
+__device__ __forceinline__ void block_select_topk(int total, int k, LoadS load_s, LoadI load_i, float* out_s, int32_t* out_i,
+                                                  float* red_s, int* red_i, int* red_p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float cs[kSelNC];
+    int ci[kSelNC];
+#pragma unroll
+    for (int j = 0; j < kSelNC; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        cs[j] = -INFINITY;
+        ci[j] = 0x7fffffff;
+        if (c < total) { cs[j] = load_s(c); ci[j] = load_i(c); }
+    }
+    for (int r = 0; r < k; ++r) {
+        float bs = cs[0];
+        int bi = ci[0], bp = threadIdx.x;
+#pragma unroll
+        for (int j = 1; j < kSelNC; ++j)          // positions ascend with j: strict comparison keeps the earlier one on equality
+            if (better(cs[j], ci[j], bs, bi)) { bs = cs[j]; bi = ci[j]; bp = threadIdx.x + 256 * j; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (better(os, oi, bs, bi) || (os == bs && oi == bi && op < bp)) { bs = os; bi = oi; bp = op; }
+        }
+        if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; red_p[warp] = bp; }
+        __syncthreads();
+        float ws = red_s[0];
+        int wi = red_i[0], wp = red_p[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            if (better(red_s[w], red_i[w], ws, wi) || (red_s[w] == ws && red_i[w] == wi && red_p[w] < wp)) {
+                ws = red_s[w]; wi = red_i[w]; wp = red_p[w];
+            }
+        if (threadIdx.x == 0) { out_s[r] = ws; out_i[r] = wi; }
+        if ((wp & 255) == static_cast<int>(threadIdx.x)) {
+#pragma unroll
+            for (int j = 0; j < kSelNC; ++j)
+                if (j == (wp >> 8)) { cs[j] = -INFINITY; ci[j] = 0x7fffffff; }
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per query (merge_topk_kernel below keeps the one-warp-per-query form for candidate counts beyond 256 * kSelNC)
+__global__ void __launch_bounds__(256) merge_topk_block_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
+                                                               int64_t list_stride, int64_t query_stride, int lists, int per_list,
+                                                               int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+    __shared__ float red_s[8];
+    __shared__ int red_i[8], red_p[8];
+    const int query = blockIdx.x;
+    auto off = [&](int c) { const int l = c / per_list; return l * list_stride + query * query_stride + (c - l * per_list); };
+    block_select_topk(lists * per_list, k, [&](int c) { return __ldg(scores + off(c)); }, [&](int c) { return __ldg(idx + off(c)); },
+                      out_scores + static_cast<size_t>(query) * k, out_idx + static_cast<size_t>(query) * k, red_s, red_i, red_p);
+}
+
 __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
                                                          int64_t list_stride, int64_t query_stride, int lists,
                                                          int per_list, int q, int k, float* __restrict__ out_scores,
@@ -476,8 +538,11 @@ int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stri
     CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX && per_list >= 1 && per_list <= CRE_TOPK_MAX, "merge_topk: k=%d per_list=%d out of range (1..%d)", k,
                 per_list, CRE_TOPK_MAX);
     LaunchScope scope(CRE_K_MERGE_TOPK, 8.0 * lists * per_list * q, stream);
-    merge_topk_kernel<<<(q + 3) / 4, 128, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, q, k,
-                                                       out_scores, out_idx);
+    if (static_cast<int64_t>(lists) * per_list <= 256 * kSelNC)
+        merge_topk_block_kernel<<<q, 256, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, k, out_scores, out_idx);
+    else
+        merge_topk_kernel<<<(q + 3) / 4, 128, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, q, k,
+                                                           out_scores, out_idx);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -607,7 +672,7 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
     // ---- final merge by the LAST CTA to finish (no second launch: the whole call is one ~30 us kernel) ----
     __shared__ int is_last;
     __shared__ float red_s[8];
-    __shared__ int red_i[8];
+    __shared__ int red_i[8], red_p[8];
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();                                   // this CTA's partial lists are visible device-wide ...
@@ -616,49 +681,12 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    constexpr int NC = 16;                                 // candidates per thread: slots * k <= 512 * 8 = 256 * 16
-    const int total = slots * k;
+    const int total = slots * k;                           // <= 256 * kSelNC (checked by the launcher)
     for (int q = 0; q < Q; ++q) {
-        float cs[NC];
-        int ci[NC];
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            const int c = threadIdx.x + 256 * j;
-            cs[j] = -INFINITY;
-            ci[j] = 0x7fffffff;
-            if (c < total) {
-                cs[j] = __ldcg(part_s + static_cast<size_t>(q) * total + c);
-                ci[j] = __ldcg(part_i + static_cast<size_t>(q) * total + c);
-            }
-        }
-        for (int r = 0; r < k; ++r) {                      // k rounds of a block-wide arg-best under (score desc, index asc)
-            float bs = cs[0];
-            int bi = ci[0];
-#pragma unroll
-            for (int j = 1; j < NC; ++j)
-                if (better(cs[j], ci[j], bs, bi)) { bs = cs[j]; bi = ci[j]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
-            }
-            if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; }
-            __syncthreads();
-            float ws = red_s[0];
-            int wi = red_i[0];
-#pragma unroll
-            for (int w = 1; w < 8; ++w)
-                if (better(red_s[w], red_i[w], ws, wi)) { ws = red_s[w]; wi = red_i[w]; }
-            if (threadIdx.x == 0) {
-                out_scores[q * k + r] = ws;
-                out_idx[q * k + r] = wi;
-            }
-#pragma unroll
-            for (int j = 0; j < NC; ++j)                    // gallery indices are unique: exactly one thread owns the winner
-                if (ci[j] == wi && wi != 0x7fffffff) { cs[j] = -INFINITY; ci[j] = 0x7fffffff; }
-            __syncthreads();
-        }
+        const float* ps = part_s + static_cast<size_t>(q) * total;
+        const int32_t* pi = part_i + static_cast<size_t>(q) * total;
+        block_select_topk(total, k, [&](int c) { return __ldcg(ps + c); }, [&](int c) { return __ldcg(pi + c); },
+                          out_scores + q * k, out_idx + q * k, red_s, red_i, red_p);
     }
     if (threadIdx.x == 0) *done_counter = 0;               // ready for the next call on this context
 }
@@ -668,7 +696,7 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
 int launch_gallery_scan_small(const float* queries, int q, int dim, const void* gallery, int rows, int row_base, int k, float* part_s,
                               int32_t* part_i, int slots, float* dump, int* done_counter, float* out_scores, int32_t* out_idx,
                               cudaStream_t stream) {
-    if (q < 1 || q > 2 || (dim != 768 && dim != 1024) || done_counter == nullptr || slots * k > 256 * 16) return 0;
+    if (q < 1 || q > 2 || (dim != 768 && dim != 1024) || done_counter == nullptr || slots * k > 256 * kSelNC) return 0;
     if ((reinterpret_cast<uintptr_t>(gallery) & 15) != 0 || (reinterpret_cast<uintptr_t>(queries) & 15) != 0) return 0;
     LaunchScope scope(CRE_K_GEMM_TOPK, 2.0 * rows * dim, stream);
     const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gallery);
