@@ -355,7 +355,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // S = [0, KB) fp32, P = [0, KB/2) packed bf16x2 (written chunk by chunk behind the S read pointer), O = [128, 192).
 // =====================================================================================================================
 constexpr int kFaThreads = 320;
-constexpr uint32_t kFaPolyMask = 0x44;   // pairs 2 and 6 of every 8: 25 % of the exponentials bypass the MUFU (XU vs issue-slot balance)
+// pairs 2 and 6 of every 8: 25 % of the exponentials bypass the MUFU.  Measured again at the end of round 1 (600 frames): 0x00 207.8,
+// 0x04 202.2, 0x44 205.3, 0x54 204.1 us -- the split is inside the noise, i.e. neither the MUFU nor the issue slots bound the kernel
+#ifndef CRE_FA_POLY_MASK
+#define CRE_FA_POLY_MASK 0x44
+#endif
+constexpr uint32_t kFaPolyMask = CRE_FA_POLY_MASK;
 constexpr int kFaQBytes = 256 * 128, kFaKVBytes = 256 * 128;
 constexpr int kFaStageBytes = kFaQBytes + 2 * kFaKVBytes;            // 96 KB
 constexpr int kFaSmemBytes = 2 * kFaStageBytes + 256 + 1024;
