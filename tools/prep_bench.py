@@ -11,7 +11,11 @@ model = random_init_vit(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=600)
 from vision_sam3_yolo_lameless_b200 import _lib
 modes = [int(a) for a in sys.argv[1:]] or [1, 0]       # preprocess_tma values: 1 = TMA-staged, 0 = direct-load kernel; +2 / +4 = debug bits
-for (n, h, w) in [(600, 1080, 1920), (600, 720, 1280), (600, 224, 224)]:
+import os
+SIZES = [(600, 1080, 1920), (600, 720, 1280), (600, 224, 224)]
+if os.environ.get("PREP_SIZES"):          # e.g. PREP_SIZES=540x960,480x640
+    SIZES = [(600, int(a), int(b)) for a, b in (x.split("x") for x in os.environ["PREP_SIZES"].split(","))]
+for (n, h, w) in SIZES:
     fr = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=eng.device)
     for mode in modes:
         _lib.set_tuning("preprocess_tma", mode)

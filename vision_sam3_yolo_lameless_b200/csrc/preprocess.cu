@@ -488,8 +488,10 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     const int nvec_max = (span_px * 3 + 15 + 15) / 16;
     const int nbox = (nvec_max * 16 + 255) / 256;
     if (rows_tile > 256) return 0;
-    // small tiles are bound by the per-tile hand-offs, not by bytes: measured cross-over near a 4x vertical reduction
-    if (sy < 4.0 && !(g_pre_debug & 4)) return 0;
+    // small tiles are bound by the per-tile hand-offs, not by bytes: this variant costs ~1.45 us + 0.16 us/MB per frame, the direct-load
+    // kernel ~1 us/MB.  Measured cross-over (600 frames; direct vs TMA us/frame): 540x960 1.67 / 1.75, 720x1280 2.70 / 1.95,
+    // 1080x1920 4.11 / 2.42 -> at about 12x fewer output than input pixels
+    if (sy * sx < 12.0 && !(g_pre_debug & 4)) return 0;
     p.sstride = nvec_max * 16 + 4;
     const size_t smem = 2 * static_cast<size_t>(nbox) * rows_tile * 256 + 2 * static_cast<size_t>(16) * p.sstride * 4 +
                         4 * kPtParamInts * 4 + 64 + 128 +
