@@ -17,6 +17,8 @@ class StubEngine:
         self.calls = []
 
     def embed_host_frames(self, frames, bgr=True, out=None):
+        if isinstance(frames, (list, tuple)):      # one array per clip, embedded as if concatenated (engine.embed_host_frames)
+            frames = np.concatenate([np.asarray(f) for f in frames], axis=0)
         frames = np.asarray(frames)
         self.calls.append(("embed", frames.shape))
         pv = preprocess_ref.preprocess(frames, bgr=bgr, size=self.resize)

@@ -102,6 +102,70 @@ def test_process_video_transcript_matches_reference(stub, tmp_path, golden, back
     assert len(nats.published) == n, "handler never raises out of the callback (main.py:279-282)"
 
 
+@pytest.mark.parametrize("backend", ["qdrant", "gpu"])
+def test_process_videos_coalesced_equals_sequential(stub, tmp_path, backend):
+    """process_videos(batch) = the same messages through process_video one by one: identical results files, NATS messages and stored
+    points (message k sees the upserts of messages < k), bad messages skipped the same way, ONE engine call per frame size."""
+    clips = []
+    for i, (seed, hw) in enumerate([(61, (48, 64)), (62, (48, 64)), (63, (32, 48)), (64, (48, 64))]):
+        clip = tmp_path / f"c{i}.avi"
+        write_clip(clip, seed=seed, h=hw[0], w=hw[1])
+        clips.append(clip)
+    msgs = [{"video_id": f"vid-{i}", "processed_path": str(c), "filename": c.name, "metadata": {"n": i}} for i, c in enumerate(clips)]
+    msgs.insert(2, {"video_id": "missing", "processed_path": str(tmp_path / "nope.avi")})
+    msgs.insert(4, {"video_id": "unreadable", "processed_path": str(tmp_path)})
+    msgs.append({"video_id": "no-path"})
+
+    seq_dir, bat_dir = tmp_path / "seq", tmp_path / "bat"
+    seq, qd_s, nats_s = make_pipeline(stub, seq_dir, gallery_backend=backend)
+    for m in msgs:
+        try:
+            asyncio.run(seq.process_video(dict(m)))
+        except KeyError:                      # the reference handler raises on a message without processed_path (swallowed by the NATS client)
+            pass
+    bat, qd_b, nats_b = make_pipeline(stub, bat_dir, gallery_backend=backend)
+    stub.calls.clear()
+    asyncio.run(bat.process_videos([dict(m) for m in msgs]))
+    assert sorted(c[1][1:3] for c in stub.calls if c[0] == "embed") == [(32, 48), (48, 64)], "one engine call per frame size"
+    assert sum(c[1][0] for c in stub.calls if c[0] == "embed") == 12        # 4 clips x 3 sampled frames
+
+    files = sorted(p.name for p in seq_dir.glob("*_dinov3.json"))
+    assert files == sorted(p.name for p in bat_dir.glob("*_dinov3.json")) == [f"vid-{i}_dinov3.json" for i in range(4)]
+    for name in files:
+        a, b = json.load(open(seq_dir / name)), json.load(open(bat_dir / name))
+        assert list(a) == list(b)
+        assert a["similar_cases"] == b["similar_cases"] and a["neighbor_evidence"] == b["neighbor_evidence"]
+        assert a["num_embeddings"] == b["num_embeddings"] == 3
+        np.testing.assert_array_equal(np.array(a["canonical_frames"][1]["embedding"]), np.array(b["canonical_frames"][1]["embedding"]))
+    assert [(s, {k: v for k, v in m.items() if k != "results_path"}) for s, m in nats_s.published] == \
+           [(s, {k: v for k, v in m.items() if k != "results_path"}) for s, m in nats_b.published]
+    ids = [f"vid-{i}" for i in range(4)]
+    for x, y in zip(qd_s.retrieve("cow_embeddings", ids, with_vectors=True), qd_b.retrieve("cow_embeddings", ids, with_vectors=True)):
+        assert x.payload == y.payload
+        np.testing.assert_array_equal(np.array(x.vector), np.array(y.vector))
+
+
+def test_coalescing_subscriber_drains_the_queue(stub, tmp_path):
+    """start(coalesce=True)'s worker step: everything queued goes through ONE process_videos call."""
+    clips = []
+    for i in range(3):
+        clip = tmp_path / f"q{i}.avi"
+        write_clip(clip, seed=70 + i)
+        clips.append(clip)
+    pipe, _, nats = make_pipeline(stub, tmp_path / "out")
+
+    async def scenario():
+        queue = asyncio.Queue()
+        for i, c in enumerate(clips):
+            await queue.put({"video_id": f"q-{i}", "processed_path": str(c)})
+        stub.calls.clear()
+        return await pipe.drain_once(queue, max_batch=8)
+
+    assert asyncio.run(scenario()) == 3
+    assert [c for c in stub.calls if c[0] == "embed"] == [("embed", (9, 48, 64, 3))]
+    assert [m["video_id"] for _, m in nats.published] == ["q-0", "q-1", "q-2"]
+
+
 def test_emit_embedding_is_opt_in(stub, tmp_path):
     clip = tmp_path / "c.avi"
     write_clip(clip, seed=51)

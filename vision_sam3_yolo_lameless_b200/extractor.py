@@ -159,8 +159,9 @@ class DINOv3Pipeline:
         raise ValueError(f"unsupported image shape {image.shape}")
 
     # -- main.py:117-163 --------------------------------------------------------------------------
-    def extract_video_embeddings(self, video_path: Path) -> Dict[str, Any]:
-        """Extract embeddings from video frames (1 frame per second, like the reference)."""
+    def _decode_sampled(self, video_path: Path):
+        """The decode loop of extract_video_embeddings (main.py:119-146) without the per-frame forward: returns
+        (staging uint8 [>= n, H, W, 3] or None, sampled frame numbers, fps, total_frames)."""
         import cv2
 
         cap = cv2.VideoCapture(str(video_path))
@@ -197,16 +198,24 @@ class DINOv3Pipeline:
                 picked_idx.append(frame_count)
             frame_count += 1
         cap.release()
+        return staging, picked_idx, fps, total_frames
 
-        embeddings = []
-        if picked_idx:
-            embs = self.engine.embed_host_frames(staging[: len(picked_idx)], bgr=True).cpu().numpy()
-            for idx, e in zip(picked_idx, embs):
-                embeddings.append({"frame": idx, "time": idx / fps if fps > 0 else 0, "embedding": e.tolist()})
+    @staticmethod
+    def _embedding_records(picked_idx, embs, fps, total_frames) -> Dict[str, Any]:
+        """The dict extract_video_embeddings returns (main.py:140-163), from the sampled frame numbers and their embeddings."""
+        embeddings = [{"frame": idx, "time": idx / fps if fps > 0 else 0, "embedding": e.tolist()} for idx, e in zip(picked_idx, embs)]
         canonical_frames = []
         if embeddings:
             canonical_frames = [embeddings[0], embeddings[len(embeddings) // 2], embeddings[-1]]
         return {"embeddings": embeddings, "canonical_frames": canonical_frames, "total_frames": total_frames, "fps": fps}
+
+    def extract_video_embeddings(self, video_path: Path) -> Dict[str, Any]:
+        """Extract embeddings from video frames (1 frame per second, like the reference)."""
+        staging, picked_idx, fps, total_frames = self._decode_sampled(video_path)
+        embs = []
+        if picked_idx:
+            embs = self.engine.embed_host_frames(staging[: len(picked_idx)], bgr=True).cpu().numpy()
+        return self._embedding_records(picked_idx, embs, fps, total_frames)
 
     # -- main.py:165-186 --------------------------------------------------------------------------
     def search_similar(self, query_embedding: np.ndarray, top_k: int = 5) -> List[Dict]:
@@ -241,75 +250,154 @@ class DINOv3Pipeline:
             return
         try:
             embedding_data = self.extract_video_embeddings(processed_path)
-            if embedding_data["embeddings"]:
-                avg_embedding = np.mean([np.array(e["embedding"]) for e in embedding_data["embeddings"]], axis=0)
-            else:
-                print(f"No embeddings extracted for {video_id}")
-                return
-            similar_cases = self.search_similar(avg_embedding, top_k=5)
-            if similar_cases:
-                labels = [case["label"] for case in similar_cases if case["label"] is not None]
-                if labels:
-                    lame_count = sum(1 for label in labels if label == 1)
-                    neighbor_evidence = lame_count / len(labels)
-                else:
-                    neighbor_evidence = 0.5
-            else:
-                neighbor_evidence = 0.5
-            payload = {
-                "video_id": video_id,
-                "filename": video_data.get("filename", ""),
-                "uploaded_at": video_data.get("uploaded_at", ""),
-                "label": None,
-                "metadata": video_data.get("metadata", {}),
-            }
-            try:
-                if self.gallery is not None:
-                    self.gallery.upsert(video_id, avg_embedding, payload)
-                if self.qdrant_client is not None:
-                    point = _point_struct(id=video_id, vector=avg_embedding.tolist(), payload=payload)
-                    self.qdrant_client.upsert(collection_name=self.collection_name, points=[point])
-                print(f"Stored embedding in VectorDB for {video_id}")
-            except Exception as e:
-                print(f"Error storing in VectorDB: {e}")
-            results = {
-                "video_id": video_id,
-                "embedding_dim": len(avg_embedding),
-                "num_embeddings": len(embedding_data["embeddings"]),
-                "similar_cases": similar_cases,
-                "neighbor_evidence": neighbor_evidence,
-                "canonical_frames": embedding_data["canonical_frames"],
-            }
-            if self.emit_embedding:
-                results["embedding"] = avg_embedding.tolist()
-            results_file = self.results_dir / f"{video_id}_dinov3.json"
-            with open(results_file, "w") as f:
-                json.dump(results, f, indent=2)
-            pipeline_result = {
-                "video_id": video_id,
-                "pipeline": "dinov3",
-                "results_path": str(results_file),
-                "neighbor_evidence": neighbor_evidence,
-                "similar_cases": similar_cases,
-                "embedding_dim": len(avg_embedding),
-            }
-            await self.nats_client.publish(self.config["nats"]["subjects"]["pipeline_dinov3"], pipeline_result)
-            print(f"DINOv3 pipeline completed for {video_id}")
+            await self._finish_video(video_id, video_data, embedding_data)
         except Exception as e:
             print(f"Error in DINOv3 pipeline for {video_id}: {e}")
             import traceback
             traceback.print_exc()
 
+    async def process_videos(self, messages: List[dict]) -> None:
+        """Coalesced form of ``process_video`` for messages that are already queued (the admin UI's batch reprocess publishes one
+        `video.preprocessed` per video in a loop, admin backend routers/pipeline.py:312-354; the reference then works through them one
+        blocking handler call at a time).  The sampled frames of ALL messages go to the GPU as one batch per frame size; everything
+        with side effects -- similarity search, VectorDB upsert, results JSON, `pipeline.dinov3` publish -- then runs per message IN
+        ARRIVAL ORDER, so message k still sees the upserts of messages < k and every output is what k sequential ``process_video``
+        calls produce.  A bad message (missing file, unreadable video) is reported and skipped exactly as there."""
+        import traceback
+
+        decoded = []                                  # (message, staging, picked_idx, fps, total_frames) in arrival order
+        for video_data in messages:
+            try:
+                video_id = video_data["video_id"]
+                processed_path = Path(video_data["processed_path"])
+            except KeyError as e:                     # the reference raises inside the callback; nats_client.py:65-66 prints and goes on
+                print(f"Error in message handler: {e}")
+                continue
+            print(f"DINOv3 pipeline processing video {video_id}")
+            if not processed_path.exists():
+                print(f"Processed video not found: {processed_path}")
+                continue
+            try:
+                decoded.append((video_data,) + tuple(self._decode_sampled(processed_path)))
+            except Exception as e:
+                print(f"Error in DINOv3 pipeline for {video_id}: {e}")
+                traceback.print_exc()
+        # one engine call per frame size (K1 takes one H x W per launch sequence)
+        by_shape: Dict[tuple, List[int]] = {}
+        for i, (_, staging, picked, _, _) in enumerate(decoded):
+            if picked:
+                by_shape.setdefault(tuple(staging.shape[1:]), []).append(i)
+        embs: Dict[int, Any] = {}
+        failed: Dict[int, Exception] = {}
+        for shape, members in by_shape.items():
+            try:
+                out = self.engine.embed_host_frames([decoded[i][1][: len(decoded[i][2])] for i in members], bgr=True).cpu().numpy()
+                start = 0
+                for i in members:
+                    embs[i] = out[start:start + len(decoded[i][2])]
+                    start += len(decoded[i][2])
+            except Exception as e:                    # the whole group shares the failure, reported per message below
+                for i in members:
+                    failed[i] = e
+        for i, (video_data, _, picked, fps, total_frames) in enumerate(decoded):
+            video_id = video_data["video_id"]
+            try:
+                if i in failed:
+                    raise failed[i]
+                await self._finish_video(video_id, video_data, self._embedding_records(picked, embs.get(i, []), fps, total_frames))
+            except Exception as e:
+                print(f"Error in DINOv3 pipeline for {video_id}: {e}")
+                traceback.print_exc()
+
+    async def _finish_video(self, video_id: str, video_data: dict, embedding_data: Dict[str, Any]) -> None:
+        """main.py:203-277: clip mean, neighbour evidence, VectorDB upsert, results JSON, `pipeline.dinov3` publish."""
+        if embedding_data["embeddings"]:
+            avg_embedding = np.mean([np.array(e["embedding"]) for e in embedding_data["embeddings"]], axis=0)
+        else:
+            print(f"No embeddings extracted for {video_id}")
+            return
+        similar_cases = self.search_similar(avg_embedding, top_k=5)
+        if similar_cases:
+            labels = [case["label"] for case in similar_cases if case["label"] is not None]
+            if labels:
+                lame_count = sum(1 for label in labels if label == 1)
+                neighbor_evidence = lame_count / len(labels)
+            else:
+                neighbor_evidence = 0.5
+        else:
+            neighbor_evidence = 0.5
+        payload = {
+            "video_id": video_id,
+            "filename": video_data.get("filename", ""),
+            "uploaded_at": video_data.get("uploaded_at", ""),
+            "label": None,
+            "metadata": video_data.get("metadata", {}),
+        }
+        try:
+            if self.gallery is not None:
+                self.gallery.upsert(video_id, avg_embedding, payload)
+            if self.qdrant_client is not None:
+                point = _point_struct(id=video_id, vector=avg_embedding.tolist(), payload=payload)
+                self.qdrant_client.upsert(collection_name=self.collection_name, points=[point])
+            print(f"Stored embedding in VectorDB for {video_id}")
+        except Exception as e:
+            print(f"Error storing in VectorDB: {e}")
+        results = {
+            "video_id": video_id,
+            "embedding_dim": len(avg_embedding),
+            "num_embeddings": len(embedding_data["embeddings"]),
+            "similar_cases": similar_cases,
+            "neighbor_evidence": neighbor_evidence,
+            "canonical_frames": embedding_data["canonical_frames"],
+        }
+        if self.emit_embedding:
+            results["embedding"] = avg_embedding.tolist()
+        results_file = self.results_dir / f"{video_id}_dinov3.json"
+        with open(results_file, "w") as f:
+            json.dump(results, f, indent=2)
+        pipeline_result = {
+            "video_id": video_id,
+            "pipeline": "dinov3",
+            "results_path": str(results_file),
+            "neighbor_evidence": neighbor_evidence,
+            "similar_cases": similar_cases,
+            "embedding_dim": len(avg_embedding),
+        }
+        await self.nats_client.publish(self.config["nats"]["subjects"]["pipeline_dinov3"], pipeline_result)
+        print(f"DINOv3 pipeline completed for {video_id}")
+
     # -- main.py:284-296 --------------------------------------------------------------------------
-    async def start(self):
+    async def start(self, coalesce: bool = False, max_batch: int = 64):
+        """Subscribe to `video.preprocessed` and serve forever (main.py:284-296).  ``coalesce=True`` queues incoming messages and
+        hands everything that has accumulated (up to ``max_batch``) to ``process_videos`` -- same outputs, one GPU batch."""
         import asyncio
 
         await self.nats_client.connect()
         subject = self.config["nats"]["subjects"]["video_preprocessed"]
         print(f"DINOv3 pipeline subscribed to {subject}")
-        await self.nats_client.subscribe(subject, self.process_video)
-        print("DINOv3 pipeline service started. Waiting for videos...")
-        await asyncio.Event().wait()
+        if not coalesce:
+            await self.nats_client.subscribe(subject, self.process_video)
+            print("DINOv3 pipeline service started. Waiting for videos...")
+            await asyncio.Event().wait()
+            return
+        queue: "asyncio.Queue[dict]" = asyncio.Queue()
+
+        async def enqueue(video_data: dict):
+            video_data["video_id"], video_data["processed_path"]     # same KeyError as the reference handler, inside the callback
+            await queue.put(video_data)
+
+        await self.nats_client.subscribe(subject, enqueue)
+        print("DINOv3 pipeline service started (coalescing). Waiting for videos...")
+        while True:
+            await self.drain_once(queue, max_batch)
+
+    async def drain_once(self, queue, max_batch: int = 64) -> int:
+        """Wait for one message, take everything else that is already queued (up to max_batch) and process it as one batch."""
+        batch = [await queue.get()]
+        while len(batch) < max_batch and not queue.empty():
+            batch.append(queue.get_nowait())
+        await self.process_videos(batch)
+        return len(batch)
 
 
 def build_pipeline_from_hf(model, **kw) -> DINOv3Pipeline:
