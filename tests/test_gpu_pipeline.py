@@ -129,6 +129,37 @@ def test_process_video_vs_reference_transcript(engine_b, golden, tmp_path):
                 pipe.gallery.payloads[pipe.gallery._row_of[f"vid-{i}"]]["label"] = i % 2
 
 
+def test_process_videos_coalesced_equals_sequential_on_gpu(engine_b, tmp_path):
+    """Queued messages through process_videos (one GPU batch per frame size) = the same messages through process_video one by one:
+    every kernel of the path is row-independent, so the stored vectors must be bit-identical, not merely close."""
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    eng, _ = engine_b
+    msgs = []
+    for i, (seed, hw) in enumerate([(81, (48, 64)), (82, (96, 128)), (83, (48, 64)), (84, (96, 128)), (85, (48, 64))]):
+        clip = tmp_path / f"c{i}.avi"
+        write_clip(clip, seed=seed, h=hw[0], w=hw[1])
+        msgs.append({"video_id": f"vid-{i}", "processed_path": str(clip), "filename": clip.name})
+    msgs.insert(1, {"video_id": "missing", "processed_path": str(tmp_path / "nope.avi")})
+    stores = {}
+    for mode in ("seq", "bat"):
+        qd, nats = fake_services.FakeQdrant(), fake_services.FakeNats()
+        pipe = DINOv3Pipeline(eng, config=SUBJECTS, nats_client=nats, qdrant_client=qd, results_dir=tmp_path / mode, gallery_backend="gpu")
+        if mode == "seq":
+            for m in msgs:
+                asyncio.run(pipe.process_video(dict(m)))
+        else:
+            asyncio.run(pipe.process_videos([dict(m) for m in msgs]))
+        stores[mode] = (qd, nats)
+    ids = [f"vid-{i}" for i in range(5)]
+    for a, b in zip(stores["seq"][0].retrieve("cow_embeddings", ids, with_vectors=True),
+                    stores["bat"][0].retrieve("cow_embeddings", ids, with_vectors=True)):
+        assert a.payload == b.payload
+        np.testing.assert_array_equal(np.array(a.vector), np.array(b.vector))
+    strip = lambda pub: [(s, {k: v for k, v in m.items() if k != "results_path"}) for s, m in pub]
+    assert strip(stores["seq"][1].published) == strip(stores["bat"][1].published)
+    assert [m["video_id"] for _, m in stores["bat"][1].published] == ids
+
+
 def test_matcher_scenario_vs_reference_transcript(engine_b, golden):
     from vision_sam3_yolo_lameless_b200.reid import CowReIDMatcher
     eng, _ = engine_b
