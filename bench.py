@@ -340,9 +340,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 if name in _lib.FLOP_KERNELS:
                     k["tflops"] = k["work"] / (k["ms"] * 1e-3) / 1e12
                     k["frac"] = k["tflops"] / tf_peak
+                    k["bound"] = "tensor"
                 else:
                     k["gbs"] = k["work"] / (k["ms"] * 1e-3) / 1e9
                     k["frac"] = k["gbs"] / hbm_peak
+                    # a launch whose bytes would take < 10 us at the HBM roofline is bound by launch / pipeline latency, not by bandwidth
+                    k["bound"] = "hbm" if k["work"] / k["launches"] / (hbm_peak * 1e9) >= 10e-6 else "latency"
         gemm = [k for n, k in kernels.items() if n.startswith("gemm_") and n != "gemm_topk"]
         g_ms, g_work, g_l = sum(k["ms"] for k in gemm), sum(k["work"] for k in gemm), sum(k["launches"] for k in gemm)
         traffic = None
