@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRE_ABI_VERSION 1
+#define CRE_ABI_VERSION 2
 #define CRE_TOPK_MAX 8
 
 typedef struct cre_ctx cre_ctx;
@@ -186,7 +186,10 @@ int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const flo
  * (pre-scaled by 1/8, rotary already applied), k at k_col0 + head*64 (rotary applied), v at v_col0 + head*64;
  * out bf16 [n*t, heads*64].  ld and the column offsets are multiples of 8 elements. */
 int32_t cre_attention(cre_ctx* ctx, const void* qkv_dev, int32_t ld, int32_t k_col0, int32_t v_col0, int32_t n,
-                      int32_t t, int32_t heads, void* out_dev, void* stream);
+                      int32_t t, int32_t heads, void* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream);
+/* scratch of cre_attention (the overflow flags of its single-pass softmax: a unit whose scores outrun the fixed stabiliser is
+ * recomputed exactly by a second kernel in the same call, csrc/attention.cu "Exactness"); 256-byte aligned. */
+int64_t cre_attention_scratch_bytes(int32_t n, int32_t heads);
 
 /* ---- launch accounting -------------------------------------------------------------------------------
  * cre_kernel_launches: kernels launched by this library in this process so far (bench.py's gpu_launches).
@@ -198,7 +201,8 @@ enum cre_kernel_id {
     CRE_K_PREPROCESS = 0, CRE_K_FILL_PREFIX = 1, CRE_K_GEMM_PATCH = 2, CRE_K_LAYERNORM = 3, CRE_K_GEMM_QKV = 4,
     CRE_K_ATTENTION = 5, CRE_K_GEMM_RESID = 6, CRE_K_GEMM_GELU = 7, CRE_K_FINAL_NORM_MEAN = 8, CRE_K_POOL_CLIPS = 9,
     CRE_K_SPLIT_HI_LO = 10, CRE_K_FILL_TOPK = 11, CRE_K_GEMM_TOPK = 12, CRE_K_MERGE_TOPK = 13, CRE_K_GEMM_PLAIN = 14,
-    CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_K_ROI_TABLES = 18, CRE_KERNEL_IDS = 19
+    CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_K_ROI_TABLES = 18, CRE_K_ATTENTION_EXACT = 19,
+    CRE_KERNEL_IDS = 20
 };
 int64_t cre_kernel_launches(void);
 int32_t cre_profile_start(int32_t max_launches);
@@ -210,7 +214,9 @@ int32_t cre_set_cta_group(int32_t cta_group);
 /* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..6:
  * TMA pipeline depth of the cre_gemm_bf16 building block), "attention_fast" (1 = persistent TMEM-resident kernel for
  * T <= 256, default; 0 = general kernel), "ln_fold" (1 = LayerNorm folded into the GEMMs, default; 0 = separate LayerNorm
- * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use CRE_EPI_RESID_LN3), "gemm_debug".  Unknown keys return -1. */
+ * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use CRE_EPI_RESID_LN3), "attention_split" (1 = split-S
+ * kernel for 160 < T <= 208, default), "attention_poly" (0 | 1 | 2: share of that kernel's exponentials on the FMA pipe),
+ * "attention_safe_order".  Every setting gives results inside the parity tolerances.  Unknown keys return -1. */
 int32_t cre_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus

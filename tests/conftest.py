@@ -17,8 +17,19 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """GPU tests fail loudly (not skip) when selected on a box without CUDA, unless deselected with -m 'not gpu'."""
-    return
+    """GPU tests must never pass (or skip) silently on a box without CUDA: when they are selected there (`-m gpu`, or no `-m` at
+    all), each one is made to FAIL with the reason; `-m "not gpu"` deselects them before this hook sees them."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+
+    def _no_gpu(*_a, **_k):
+        pytest.fail("GPU test selected on a box without CUDA (run with -m 'not gpu' here; there is no CPU fallback)", pytrace=False)
+
+    for item in items:
+        if item.get_closest_marker("gpu") is not None:
+            item.obj = _no_gpu
 
 
 @pytest.fixture(scope="session")

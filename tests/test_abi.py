@@ -22,7 +22,7 @@ def header_functions():
 def test_library_is_built_and_loads():
     assert _lib.LIB_PATH.exists(), "run __graft_entry__.build() first"
     lib = _lib.load()
-    assert lib.cre_abi_version() == 1
+    assert lib.cre_abi_version() == 2
 
 
 def test_every_header_symbol_is_exported_and_bound():

@@ -165,19 +165,54 @@ def test_gemm_resid_layernorm_producer(engine_small, cg, epi, m, n, k):
     assert rel_err(out, want) < 8e-3
 
 
-@pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12),
-                                       (9, 2, 12), (16, 1, 12), (31, 2, 12), (48, 1, 12), (185, 2, 12), (129, 5, 12), (240, 2, 16)])
-def test_attention(engine_small, t, n, heads):
-    dev = engine_small.device
+def _attention_case(engine, t, n, heads, q_scale=0.125, plant=None, seed=None):
+    """qkv with N(0,1) q / k / v (q times q_scale) -> (kernel output, fp32 softmax reference of HF:modeling_dinov3_vit.py:210-235
+    on the same bf16 inputs).  plant = (key, boost): that key's logit is lifted `boost` nats above every other key of every row."""
+    dev = engine.device
     d = heads * 64
-    gen = torch.Generator(device=dev).manual_seed(t)
+    gen = torch.Generator(device=dev).manual_seed(t if seed is None else seed)
     q, k, v = (torch.randn(n, t, heads, 64, device=dev, generator=gen) for _ in range(3))
-    qs, kb, vb = (q * 0.125).to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    if plant is not None:
+        # every q gets a large component along e0, the planted key is +e0 scaled, every other key has no e0 component
+        key, boost = plant
+        k[:, :, :, 0] = 0.0
+        q[:, :, :, 0] = 16.0 / q_scale                      # stored q[..., 0] = 16 (bf16-exact)
+        k[:, key, :, 0] = boost / 16.0
+    qs, kb, vb = (q * q_scale).to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
     qkv = torch.cat([qs.reshape(n * t, d), kb.reshape(n * t, d), vb.reshape(n * t, d)], dim=1).contiguous()
-    out = engine_small.attention(qkv, n, t, heads)
-    att = torch.softmax(qs.float().permute(0, 2, 1, 3) @ kb.float().permute(0, 2, 3, 1), dim=-1)
-    ref = (att @ vb.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(n * t, d)
+    out = engine.attention(qkv, n, t, heads)
+    att = torch.softmax(qs.double().permute(0, 2, 1, 3) @ kb.double().permute(0, 2, 3, 1), dim=-1)
+    ref = (att @ vb.double().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(n * t, d)
+    return out, ref.float()
+
+
+@pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12),
+                                       (9, 2, 12), (16, 1, 12), (31, 2, 12), (48, 1, 12), (185, 2, 12), (129, 5, 12), (240, 2, 16),
+                                       (161, 2, 12), (176, 3, 12), (177, 2, 12), (192, 2, 16), (200, 1, 12), (208, 2, 12), (209, 2, 12),
+                                       (201, 70, 12), (193, 40, 16)])
+def test_attention(engine_small, t, n, heads):
+    """All three tensor-core kernels (general: T > 256; single-S persistent: T <= 160 and 208 < T <= 256; split-S: 160 < T <= 208)
+    incl. launches with several units per CTA ((201, 70, 12) = 840 units: both halves-first orders of the split-S kernel)."""
+    out, ref = _attention_case(engine_small, t, n, heads)
     assert rel_err(out, ref) < 8e-3                                                             # bf16 P and bf16 output
+
+
+@pytest.mark.parametrize("t,n", [(201, 14), (129, 3), (256, 2), (1029, 1)])
+@pytest.mark.parametrize("sigma", [8.0, 30.0])
+def test_attention_large_logits(engine_small, t, n, sigma):
+    """Trained weights can give logits far from N(0, 1).  The kernels' fixed 32-key stabiliser is only a shift: rows whose later
+    keys outrun it are caught by the row-sum flag and recomputed exactly (csrc/attention.cu "Exactness").  Logit sigma 8 and 30 nats
+    (peaked, near one-hot rows); same tolerance as the small-logit cases."""
+    out, ref = _attention_case(engine_small, t, n, 12, q_scale=sigma / 8.0, seed=1000 + t)     # q.k has sigma 8 for unit q, k
+    assert rel_err(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("t,n,key", [(201, 14, 150), (201, 2, 200), (201, 2, 40), (129, 3, 100), (256, 2, 255), (1029, 1, 900)])
+def test_attention_planted_late_key(engine_small, t, n, key):
+    """One key 100 nats above every other key of every row, outside the stabiliser's 32-key prefix: exp overflows the single-pass
+    kernels, every unit must be flagged and come back from the exact kernel as (almost) that key's value row."""
+    out, ref = _attention_case(engine_small, t, n, 12, plant=(key, 100.0), seed=2000 + t)
+    assert rel_err(out, ref) < 8e-3
 
 
 @pytest.mark.parametrize("h,w,kind,bgr", [(1080, 1920, "noise", True), (720, 1280, "smooth", True), (224, 224, "noise", False),

@@ -25,7 +25,7 @@ BF16_KINDS = {W_PATCH, W_QKV, W_O, W_UP, W_DOWN}
 # enum cre_kernel_id
 KERNEL_NAMES = ["preprocess", "fill_prefix", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu",
                 "final_norm_mean", "pool_clips", "split_hi_lo", "fill_topk", "gemm_topk", "merge_topk", "gemm_plain",
-                "gallery_update", "row_stats", "fold_ln_weights", "roi_tables"]
+                "gallery_update", "row_stats", "fold_ln_weights", "roi_tables", "attention_exact"]
 # kernels whose `work` is FLOPs (tensor-bound); the others report bytes (HBM-bound)
 FLOP_KERNELS = {"gemm_patch", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu", "gemm_plain"}
 
@@ -78,7 +78,8 @@ PROTOTYPES = {
     "cre_row_stats": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "cre_fold_ln_weights": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "cre_gemm_ln": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
-    "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "cre_attention_scratch_bytes": (_i64, [_i32, _i32]),
     "cre_set_cta_group": (_i32, [_i32]),
     "cre_set_tuning": (_i32, [C.c_char_p, _i32]),
     "cre_kernel_launches": (_i64, []),

@@ -113,6 +113,8 @@ struct Workspace {
     __nv_bfloat16* mlp;  // [M, F]
     __nv_bfloat16* xb;   // [M, D] bf16(x - row pivot): A operand of the LayerNorm-folded GEMMs
     float* stats[2];     // [M, ln_stride] LayerNorm statistics rows (ping-pong between the two norms of a block)
+    int* attn_flags;     // [layers] x [64-int "any" slot] then [frames * heads] unit flags: attention overflow tracking
+    int64_t attn_flag_bytes;
     int64_t total;
 };
 inline int ln_slots(const cre_model_cfg* c) { return c->hidden / 128; }
@@ -131,6 +133,8 @@ Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) 
     w.xb = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
     w.stats[0] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
     w.stats[1] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
+    w.attn_flag_bytes = (64LL * c->layers + static_cast<int64_t>(frames) * c->heads) * 4;
+    w.attn_flags = reinterpret_cast<int*>(take(w.attn_flag_bytes));
     w.total = off;
     return w;
 }
@@ -519,6 +523,8 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
     int rc = get_rope_table(ctx, grid_h, grid_w, &rope);
     if (rc) return rc;
 
+    // attention overflow flags: one "any" slot per layer + the per-unit flags (which every layer leaves zeroed again)
+    CRE_CUDA_OK(cudaMemsetAsync(ws.attn_flags, 0, static_cast<size_t>(ws.attn_flag_bytes), stream));
     rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
     if (rc) return rc;
     {   // patch embedding: [n*P, 768] x [D, 768]^T + bias -> token rows prefix.. of x
@@ -576,6 +582,8 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             a.t = T;
             a.heads = c.heads;
             a.out = ws.h;
+            a.any_flag = ws.attn_flags + 64 * l;
+            a.unit_flags = ws.attn_flags + 64 * c.layers;
             rc = launch_attention(a, stream);
             if (rc) return rc;
         }
@@ -791,10 +799,25 @@ int32_t cre_layernorm_bf16(const float* x_dev, const float* gamma_dev, const flo
                                  static_cast<cudaStream_t>(stream));
 }
 
+int64_t cre_attention_scratch_bytes(int32_t n, int32_t heads) {
+    if (n <= 0 || heads <= 0) {
+        set_error("attention_scratch_bytes: n=%d heads=%d", n, heads);
+        return -1;
+    }
+    return align_up(attention_flag_ints(n, heads) * 4, kAlign);
+}
+
 int32_t cre_attention(cre_ctx* ctx, const void* qkv_dev, int32_t ld, int32_t k_col0, int32_t v_col0, int32_t n, int32_t t,
-                      int32_t heads, void* out_dev, void* stream) {
-    CRE_REQUIRE(ctx != nullptr && qkv_dev != nullptr && out_dev != nullptr, "attention: NULL argument");
+                      int32_t heads, void* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
+    CRE_REQUIRE(ctx != nullptr && qkv_dev != nullptr && out_dev != nullptr && scratch_dev != nullptr, "attention: NULL argument");
+    CRE_REQUIRE(n > 0 && heads > 0, "attention: n=%d heads=%d", n, heads);
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 255) == 0, "attention: scratch must be 256-byte aligned");
+    const int64_t need = cre_attention_scratch_bytes(n, heads);
+    CRE_REQUIRE(scratch_bytes >= need, "attention: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)need);
+    CRE_CUDA_OK(cudaMemsetAsync(scratch_dev, 0, static_cast<size_t>(need), static_cast<cudaStream_t>(stream)));
     AttnArgs a;
+    a.any_flag = static_cast<int*>(scratch_dev);
+    a.unit_flags = static_cast<int*>(scratch_dev) + 64;
     a.qkv = qkv_dev;
     a.ld = ld;
     a.k_col0 = k_col0;
@@ -826,8 +849,17 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_attention_fast(value);
         return 0;
     }
-    if (strcmp(key, "attention_debug") == 0) {
-        set_attention_debug(value);
+    if (strcmp(key, "attention_split") == 0) {
+        set_attention_split(value);
+        return 0;
+    }
+    if (strcmp(key, "attention_poly") == 0) {
+        CRE_REQUIRE(value >= 0 && value <= 2, "set_tuning: attention_poly=%d", value);
+        set_attention_poly(value);
+        return 0;
+    }
+    if (strcmp(key, "attention_safe_order") == 0) {
+        set_attention_safe_order(value);
         return 0;
     }
     if (strcmp(key, "preprocess_tma") == 0) {
@@ -850,10 +882,12 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         g_ln_fold = value != 0;
         return 0;
     }
-    if (strcmp(key, "gemm_debug") == 0) {
+#ifdef CRE_TUNING
+    if (strcmp(key, "gemm_debug") == 0) {   // tuning builds only (make EXTRA=-DCRE_TUNING): results are garbage
         set_gemm_debug(value);
         return 0;
     }
+#endif
     set_error("set_tuning: unknown key '%s'", key);
     return -1;
 }

@@ -35,7 +35,24 @@ struct AttnParams {
     __nv_bfloat16* out;
     int ld_out;
     int k_col0, v_col0;
+    int* any_flag;     // see "Exactness" below; both may be NULL (building-block callers that accept the fixed stabiliser)
+    int* unit_flags;
 };
+
+// Exactness.  The tensor-core kernels below are SINGLE-pass softmaxes with a fixed stabiliser m = the row's maximum over a
+// 32-key prefix (softmax is shift invariant: any m gives the same result as long as nothing overflows; with m <= the true maximum
+// the largest term is >= 1, so nothing underflows either).  A row overflows only when some later score exceeds the prefix maximum by
+// tens of nats; that is detected for free from the row sum l: every thread checks l < 2^64 (false for +inf and NaN too), and a row
+// that fails raises the flag of its (frame, head) unit.  attention_exact_kernel, launched right behind, recomputes the flagged units
+// with a true row maximum in fp32 on the CUDA cores (two passes, nothing approximated) and exits at once when no flag is up.
+// l < 2^64 guarantees every p < 2^64 and |O| < 2^64 * max|v|: no overflow anywhere in an unflagged row.
+constexpr float kRowSumLimit = 18446744073709551616.0f;   // 2^64
+__device__ __forceinline__ void raise_unit_flag(int* any_flag, int* unit_flags, int unit) {
+    if (unit_flags != nullptr) {
+        unit_flags[unit] = 1;
+        *any_flag = 1;
+    }
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -314,7 +331,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float* l_x = reinterpret_cast<float*>(p_gen);
     l_x[side * 128 + row] = l_lo + l_hi;
     __syncthreads();
-    const float inv = 1.0f / (l_x[row] + l_x[128 + row]);
+    const float l_row = l_x[row] + l_x[128 + row];
+    if (tok < T && !(l_row < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, frame * p.heads + head);
+    const float inv = 1.0f / l_row;
     uint32_t o[32];                                         // this thread's half of the 64 output dims
 #pragma unroll
     for (int c = 0; c < 32; c += 16) {
@@ -370,7 +389,8 @@ struct FaParams {
     __nv_bfloat16* out;
     int ld_out;
     int k_col0, v_col0;
-    int debug;   // tuning only: 1 skip softmax math, 2 skip PV MMAs, 4 skip S MMAs, 8 skip O read/store, 16 skip TMA loads
+    int* any_flag;     // overflow flags ("Exactness" above); NULL = not tracked
+    int* unit_flags;
 };
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -439,10 +459,6 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const int s = i & 1;
             const int frame = u / p.heads, head = u - frame * p.heads;
             mbar_wait(kv_empty(s), ((i >> 1) & 1) ^ 1u);
-            if (p.debug & 16) {
-                mbar_arrive(kv_full(s));
-                continue;
-            }
             mbar_arrive_expect_tx(kv_full(s), kFaQBytes + 2 * KB * 128);
             tma_load_2d<1>(&tmap_q, kv_full(s), s_q(s), head * 64, frame * T, kEvictFirst);
             tma_load_2d<1>(&tmap_kv, kv_full(s), s_k(s), p.k_col0 + head * 64, frame * T, kEvictFirst);
@@ -478,17 +494,15 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         tc_fence_after();
                         const uint64_t dq = umma_desc_k_sw128(s_q(s) + g * (128 * 128));
                         const uint64_t dk = umma_desc_k_sw128(s_k(s));
-                        if (!(p.debug & 4)) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base + g * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                        }
+                        for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base + g * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     }
                     umma_commit<1>(s_full(g));
                     st[g] = 1;
                 } else {
                     if (!mbar_test(p_full(g), ph)) continue;
                     tc_fence_after();
-                    if (g * 128 < T && !(p.debug & 2)) {
+                    if (g * 128 < T) {
                         for (int ks = 0; ks < nk; ++ks)
                             umma_bf16_ts(tmem_base + g * 256 + 128, tmem_base + g * 256 + 8 * ks,
                                          umma_desc_mn_sw128(s_v(s) + ks * 2048), idesc_o, ks != 0);
@@ -519,7 +533,7 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             __syncwarp();
             tc_fence_after();
             float l_sum = 1.0f;
-            if (warp_active && !(p.debug & 1)) {
+            if (warp_active) {
                 // ---- stabiliser: maximum over the FIRST 32 keys only (CLS, registers, first patches).  This kernel is
                 //      bound by the TMEM read port (64 B/clk/SM: a full max pass doubles the S traffic), and softmax is
                 //      shift invariant: any m works as long as exp2 neither overflows nor flushes the row's largest term.
@@ -614,7 +628,7 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             mbar_wait(o_full(g), ph);
             __syncwarp();
             tc_fence_after();
-            if (warp_active && !(p.debug & 8)) {
+            if (warp_active) {
                 uint32_t o[64];
 #pragma unroll
                 for (int c = 0; c < 64; c += 16) {
@@ -629,6 +643,7 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_free(g));
                 if (row < T) {
+                    if (!(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, u);
                     const float inv = 1.0f / l_sum;
                     uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + row) * p.ld_out + head * 64);
 #pragma unroll
@@ -654,10 +669,442 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
 }
 
-static int g_attn_fast = 1;
-static int g_attn_debug = 0;
-void set_attention_debug(int mask) { g_attn_debug = mask; }
+// =====================================================================================================================
+// Split-S kernel for 160 < T <= 208 keys (THE production shape: 224 x 224 input -> T = 201).
+//
+// The fast path above keeps two softmax chains per SM busy, but each chain is strictly serial -- S MMA -> softmax -> PV MMA ->
+// O read-back -- and TMEM (2 x (208 S + 64 O) > 512 columns) leaves no room to prefetch the next S.  The round-1 source-level
+// profile put 45 % of the softmax warps' time in their two waits for the tensor pipe.  Here the 208 keys of a unit are split
+// into halves h0 = keys [0, 128) and h1 = keys [128, KB), and consecutive units visit them in ALTERNATING order, which makes
+// every MMA except the last half's PV run under the exponentials of the other half:
+//
+//   TMEM columns of group g (base 256 g):   [0, 128) S_h0   (P_h0 = bf16 pairs in [0, 64), written behind the read pointer)
+//                                           [128, 128 + 16 n1) S_h1,   P_h1 in [256 - 8 n1, 256)   (n1 = (KB - 128) / 16 <= 5)
+//   O of an even unit lives in [64, 128)  (the part of h0's region that is free once h0 has been exponentiated),
+//   O of an odd unit in [128, 192)        (h1's region).
+//
+//   even unit i: softmax h0, then h1;  odd unit: softmax h1, then h0.  Per group the issuer runs, in program order,
+//       S_first(i)            straight behind PV_last(i - 1): that region was last READ by softmax_last(i - 1) (p_full) and holds
+//                             no live P (P_h0 is consumed by the in-order PV in front of it, P_h1 has its own columns)
+//       S_last(i)             after O(i - 1), which overlays that region, has been drained (tmem_free)
+//       PV_first(i)           after p_full(first); runs under softmax_last(i)
+//       PV_last(i), commit    after p_full(last): the only tensor work a softmax warp ever waits for
+//   so S_first(i + 1) is already in TMEM when the softmax warps come back from reading O(i).
+//
+// One issuer warp per group (blocking mbarrier waits instead of a polling loop over both groups), rows are exponentiated with
+// no clamp (overflow is caught by the row-sum flag, see "Exactness"), 32-key TMEM loads / 16-column stores.
+// =====================================================================================================================
+constexpr int kFsThreads = 384;   // warp 0 TMA, warps 1-2 MMA issuers (group 0 / 1), warp 3 TMEM allocator, warps 4-11 softmax
+constexpr int kFsSmemBytes = kFaSmemBytes;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// NK (16 | 32) scores of one row -> exponentials -> running sum + packed bf16 pairs.  POLY: bit i set = pair i of every 8 runs on
+// the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0.
+template <int NK, uint32_t POLY, bool MASK>
+__device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t (&pk)[NK / 2], int nvalid, uint64_t l2e2,
+                                              uint64_t neg_m2, uint64_t& l2) {
+#pragma unroll
+    for (int j = 0; j < NK; j += 2) {
+        float x0, x1, e0, e1;
+        unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
+        if ((POLY >> ((j >> 1) & 7)) & 1) {
+            // the exponent-field add of exp2_poly2 wraps beyond 2^128: clamp, so that an overflowing row ends as inf / NaN (flagged)
+            exp2_poly2(pack2(fminf(x0, 128.0f), fminf(x1, 128.0f)), e0, e1);
+        } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+        }
+        if constexpr (MASK) {
+            if (j >= nvalid) e0 = 0.0f;
+            if (j + 1 >= nvalid) e1 = 0.0f;
+        }
+        l2 = add2(l2, pack2(e0, e1));
+        pk[j >> 1] = pack_bf16x2_pos(e0, e1);
+    }
+}
+
+struct FsParams {
+    int t, heads, kb, units;
+    __nv_bfloat16* out;
+    int ld_out;
+    int k_col0, v_col0;
+    int* any_flag;
+    int* unit_flags;
+    int safe_order;    // 1: never issue an S MMA over P columns a queued PV MMA still reads (do not rely on in-order execution)
+};
+
+template <uint32_t POLY>
+__global__ void __launch_bounds__(kFsThreads, 1)
+attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto s_q = [&](int s) { return smem_base + s * kFaStageBytes; };
+    auto s_k = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes; };
+    auto s_v = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes + kFaKVBytes; };
+    const uint32_t bar_base = smem_base + 2 * kFaStageBytes;
+    auto kv_full = [&](int s) { return bar_base + 8u * s; };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto s_full = [&](int g, int h) { return bar_base + 8u * (4 + 2 * g + h); };
+    auto p_full = [&](int g, int h) { return bar_base + 8u * (8 + 2 * g + h); };
+    auto o_full = [&](int g) { return bar_base + 8u * (12 + g); };
+    auto tmem_free = [&](int g) { return bar_base + 8u * (14 + g); };
+    const uint32_t tmem_slot = bar_base + 8u * 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.t, KB = p.kb;
+    const int n1 = (KB - 128) >> 4;                    // 16-key steps of the second half (3..5)
+    const uint32_t p1_col = 256u - 8u * n1;            // P_h1 columns
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_kv);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(kv_full(i), 1);
+            mbar_init(kv_empty(i), 2);                 // one tcgen05.commit per issuer
+            mbar_init(s_full(i, 0), 1);
+            mbar_init(s_full(i, 1), 1);
+            mbar_init(p_full(i, 0), 4);
+            mbar_init(p_full(i, 1), 4);
+            mbar_init(o_full(i), 1);
+            mbar_init(tmem_free(i), 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 3) {
+        tmem_alloc<1>(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // =============================== TMA producer ===============================
+        // Q, K and V of a unit are the same KB rows of the fused matrix at three column offsets; Q rows >= KB of the second
+        // query tile are never loaded (their S rows are never read)
+        int i = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+            const int s = i & 1;
+            const int frame = u / p.heads, head = u - frame * p.heads;
+            mbar_wait(kv_empty(s), ((i >> 1) & 1) ^ 1u);
+            mbar_arrive_expect_tx(kv_full(s), 3 * KB * 128);
+            tma_load_2d<1>(&tmap_kv, kv_full(s), s_q(s), head * 64, frame * T, kEvictFirst);
+            tma_load_2d<1>(&tmap_kv, kv_full(s), s_k(s), p.k_col0 + head * 64, frame * T, kEvictFirst);
+            tma_load_2d<1>(&tmap_kv, kv_full(s), s_v(s), p.v_col0 + head * 64, frame * T, kEvictFirst);
+        }
+    } else if ((warp == 1 || warp == 2) && lane == 0) {
+        // =============================== MMA issuer of group g ===============================
+        const int g = warp - 1;
+        const uint32_t gb = tmem_base + g * 256;
+        const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, 16 * n1);
+        const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+        int i = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+            const int s = i & 1;
+            const uint32_t ph = i & 1;
+            const int first = i & 1, last = first ^ 1;           // which half goes first in this unit
+            const uint32_t o_col = gb + (first == 0 ? 64u : 128u);
+            const uint64_t dq = umma_desc_k_sw128(s_q(s) + g * (128 * 128));
+            auto issue_s = [&](int h) {
+                const uint64_t dk = umma_desc_k_sw128(s_k(s) + h * (128 * 128));
+                const uint32_t idesc = h == 0 ? idesc_s0 : idesc_s1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16<1>(gb + h * 128, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+                umma_commit<1>(s_full(g, h));
+            };
+            auto issue_pv = [&](int h, bool fresh) {
+                const int steps = h == 0 ? 8 : n1;
+                const uint32_t pa = gb + (h == 0 ? 0u : p1_col);
+                for (int ks = 0; ks < steps; ++ks)
+                    umma_bf16_ts(o_col, pa + 8 * ks, umma_desc_mn_sw128(s_v(s) + (h * 8 + ks) * 2048), idesc_o, !(fresh && ks == 0));
+            };
+            mbar_wait(kv_full(s), (i >> 1) & 1);
+            // S_h0 overwrites the P_h0 columns the PV MMAs queued right in front of it read: the tensor pipe executes one thread's
+            // MMAs in issue order, so no wait is needed (safe_order waits for that PV to retire instead)
+            if (p.safe_order && first == 0) mbar_wait(o_full(g), ph ^ 1u);
+            tc_fence_after();
+            issue_s(first);
+            mbar_wait(tmem_free(g), ph ^ 1u);                   // O of the previous unit (it overlays this region) is in registers
+            tc_fence_after();
+            issue_s(last);
+            mbar_wait(p_full(g, first), ph);
+            tc_fence_after();
+            issue_pv(first, true);
+            mbar_wait(p_full(g, last), ph);
+            tc_fence_after();
+            issue_pv(last, false);
+            umma_commit<1>(o_full(g));
+            umma_commit<1>(kv_empty(s));                        // this group is done with the smem stage
+        }
+    } else if (warp >= 4) {
+        // =============================== softmax groups ===============================
+        const int g = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int row = g * 128 + quarter * 32 + lane;          // query token inside the frame
+        const bool warp_active = g * 128 + quarter * 32 < T;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 256;
+        constexpr float kLog2e = 1.4426950408889634f;
+        const uint64_t l2e2 = pack2(kLog2e, kLog2e);
+        const int nf1 = (T - 128) >> 4, rem = T & 15;           // full 16-key steps of h1 (2..5), keys in its partial step
+        int i = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+            const uint32_t ph = i & 1;
+            const int first = i & 1;
+            const int frame = u / p.heads, head = u - frame * p.heads;
+            uint64_t l2 = pack2(0.0f, 0.0f);
+            uint64_t neg_m2 = pack2(0.0f, 0.0f);
+            // stabiliser from the 32 scores in hand: m = their maximum
+            auto set_m = [&](const uint32_t (&v)[32]) {
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                neg_m2 = pack2(-m * kLog2e, -m * kLog2e);
+            };
+#pragma unroll 1
+            for (int step = 0; step < 2; ++step) {
+                const int h = step == 0 ? first : first ^ 1;
+                mbar_wait(s_full(g, h), ph);
+                __syncwarp();
+                tc_fence_after();
+                if (warp_active) {
+                    uint32_t va[32], vb[32];
+                    uint32_t pk[16];
+                    if (h == 0) {
+                        // ---- keys [0, 128): four 32-key blocks, the TMEM read of block b + 1 in flight under block b ----
+                        tmem_ld32(t_row, va);
+                        tmem_ld_wait();
+                        if (step == 0) set_m(va);
+                        tmem_ld32(t_row + 32, vb);
+                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                        tmem_st16(t_row, pk);
+                        tmem_ld_wait();
+                        tmem_ld32(t_row + 64, va);
+                        softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                        tmem_st16(t_row + 16, pk);
+                        tmem_ld_wait();
+                        tmem_ld32(t_row + 96, vb);
+                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                        tmem_st16(t_row + 32, pk);
+                        tmem_ld_wait();
+                        softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                        tmem_st16(t_row + 48, pk);
+                    } else {
+                        // ---- keys [128, KB): nf1 full 16-key steps (+ a partial one) as up to three blocks: 32 | 32 or 16 | 16 ----
+                        const uint32_t s1 = t_row + 128, p1 = t_row + p1_col;
+                        uint32_t(&vb16)[16] = reinterpret_cast<uint32_t(&)[16]>(vb);
+                        uint32_t(&va16)[16] = reinterpret_cast<uint32_t(&)[16]>(va);
+                        uint32_t(&pk8)[8] = reinterpret_cast<uint32_t(&)[8]>(pk);
+                        const bool wide = nf1 >= 4;                   // second block: steps 2, 3 (else: step 2 alone)
+                        const int c3 = wide ? 4 : 3;                  // step of the third block, if there is one
+                        tmem_ld32(s1, va);
+                        tmem_ld_wait();
+                        if (step == 0) set_m(va);
+                        if (wide) tmem_ld32(s1 + 32, vb);
+                        else if (n1 >= 3) tmem_ld16(s1 + 32, vb16);
+                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                        tmem_st16(p1, pk);
+                        tmem_ld_wait();
+                        if (n1 > c3) tmem_ld16(s1 + 16 * c3, va16);
+                        if (wide) {
+                            softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                            tmem_st16(p1 + 16, pk);
+                        } else if (n1 >= 3) {
+                            if (nf1 >= 3) softmax_block<16, POLY, false>(vb16, pk8, 16, l2e2, neg_m2, l2);
+                            else softmax_block<16, POLY, true>(vb16, pk8, rem, l2e2, neg_m2, l2);
+                            tmem_st8(p1 + 16, pk8);
+                        }
+                        tmem_ld_wait();
+                        if (n1 > c3) {
+                            if (c3 < nf1) softmax_block<16, POLY, false>(va16, pk8, 16, l2e2, neg_m2, l2);
+                            else softmax_block<16, POLY, true>(va16, pk8, rem, l2e2, neg_m2, l2);
+                            tmem_st8(p1 + 8 * c3, pk8);
+                        }
+                    }
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(g, h));
+            }
+
+            mbar_wait(o_full(g), ph);
+            __syncwarp();
+            tc_fence_after();
+            if (warp_active) {
+                const uint32_t o_col = t_row + (first == 0 ? 64u : 128u);
+                uint32_t o[64];
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(o_col + c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[c + j] = v[j];
+                }
+                tmem_ld_wait();
+                // O is in registers: hand the TMEM columns back before the global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_free(g));
+                if (row < T) {
+                    float l_lo, l_hi;
+                    unpack2(l2, l_lo, l_hi);
+                    const float l_sum = l_lo + l_hi;
+                    if (!(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, u);
+                    const float inv = 1.0f / l_sum;
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + row) * p.ld_out + head * 64);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                                            pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+                }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_free(g));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+// =====================================================================================================================
+// Exact recomputation of the units the tensor-core kernels flagged ("Exactness" above): fp32 on the CUDA cores, true row maximum
+// (two passes over the keys), fp32 probabilities, nothing approximated -- HF:modeling_dinov3_vit.py:210-235 on the bf16 q / k / v
+// the fast kernels read.  One CTA per flagged unit, one thread per query row, key tiles of 128 in shared memory.  With no flag up
+// (every launch in practice) all CTAs return after one load.
+// =====================================================================================================================
+constexpr int kExKeys = 128;
+__global__ void __launch_bounds__(256)
+attention_exact_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int k_col0, int v_col0, int t, int heads, int units,
+                       __nv_bfloat16* __restrict__ out, int ld_out, const int* any_flag, int* unit_flags) {
+    if (__ldcg(any_flag) == 0) return;
+    __shared__ __align__(16) uint4 sk[kExKeys * 8];     // [key][64 bf16]
+    __shared__ __align__(16) uint4 sv[kExKeys * 8];
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        if (__ldcg(unit_flags + u) == 0) continue;      // uniform across the CTA
+        const int frame = u / heads, head = u - frame * heads;
+        const __nv_bfloat16* base = qkv + static_cast<size_t>(frame) * t * ld;
+        auto load_tile = [&](uint4* dst, int col0, int k0) {
+            __syncthreads();                            // the previous tile is no longer being read
+            for (int e = threadIdx.x; e < kExKeys * 8; e += 256) {
+                const int key = k0 + (e >> 3);
+                dst[e] = key < t ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(key) * ld + col0 + head * 64) + (e & 7))
+                                 : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        for (int r0 = 0; r0 < t; r0 += 256) {
+            const int r = r0 + threadIdx.x;
+            const bool ok = r < t;
+            float q[64];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) w = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * ld + head * 64) + c);
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    q[8 * c + 2 * e] = __uint_as_float(ww[e] << 16);
+                    q[8 * c + 2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u);
+                }
+            }
+            auto score = [&](int j) {
+                float s = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 w = sk[j * 8 + c];
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s = fmaf(q[8 * c + 2 * e], __uint_as_float(ww[e] << 16), s);
+                        s = fmaf(q[8 * c + 2 * e + 1], __uint_as_float(ww[e] & 0xffff0000u), s);
+                    }
+                }
+                return s;
+            };
+            float m = -INFINITY;
+            for (int k0 = 0; k0 < t; k0 += kExKeys) {
+                load_tile(sk, k_col0, k0);
+                __syncthreads();
+                const int nk = min(kExKeys, t - k0);
+                for (int j = 0; j < nk; ++j) m = fmaxf(m, score(j));
+            }
+            float l = 0.0f, acc[64];
+#pragma unroll
+            for (int d = 0; d < 64; ++d) acc[d] = 0.0f;
+            for (int k0 = 0; k0 < t; k0 += kExKeys) {
+                load_tile(sk, k_col0, k0);
+                for (int e = threadIdx.x; e < kExKeys * 8; e += 256) {
+                    const int key = k0 + (e >> 3);
+                    sv[e] = key < t ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(key) * ld + v_col0 + head * 64) + (e & 7))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncthreads();
+                const int nk = min(kExKeys, t - k0);
+                for (int j = 0; j < nk; ++j) {
+                    const float pj = expf(score(j) - m);
+                    l += pj;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = sv[j * 8 + c];
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            acc[8 * c + 2 * e] = fmaf(pj, __uint_as_float(ww[e] << 16), acc[8 * c + 2 * e]);
+                            acc[8 * c + 2 * e + 1] = fmaf(pj, __uint_as_float(ww[e] & 0xffff0000u), acc[8 * c + 2 * e + 1]);
+                        }
+                    }
+                }
+            }
+            if (ok) {
+                const float inv = 1.0f / l;
+                uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(frame) * t + r) * ld_out + head * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    dst[c] = make_uint4(pack_bf16x2(acc[8 * c] * inv, acc[8 * c + 1] * inv), pack_bf16x2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
+                                        pack_bf16x2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv), pack_bf16x2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) unit_flags[u] = 0;        // flags are all zero again when the last flagged unit is done
+    }
+}
+
+static int g_attn_fast = 1;     // 0: general kernel for every T; 1: persistent kernels for T <= 256
+static int g_attn_split = 1;    // 1: split-S kernel for 160 < T <= 208; 0: the single-S fast kernel
+static int g_attn_poly = 1;     // split-S kernel: share of the exponentials on the FMA pipe (0: none, 1: 25 %, 2: 50 %)
+static int g_attn_safe = 0;
 void set_attention_fast(int on) { g_attn_fast = on; }
+void set_attention_split(int on) { g_attn_split = on; }
+void set_attention_poly(int v) { g_attn_poly = v; }
+void set_attention_safe_order(int on) { g_attn_safe = on; }
+
+static int launch_exact(const AttnArgs& a, cudaStream_t stream) {
+    if (a.unit_flags == nullptr) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int units = a.n * a.heads;
+    LaunchScope scope(CRE_K_ATTENTION_EXACT, 0.0, stream);
+    attention_exact_kernel<<<units < 2 * sms ? units : 2 * sms, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(a.qkv), a.ld, a.k_col0, a.v_col0, a.t, a.heads, units, static_cast<__nv_bfloat16*>(a.out),
+        a.heads * 64, a.any_flag, a.unit_flags);
+    CRE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.n > 0 && a.t > 0 && a.heads > 0, "attention: empty problem");
@@ -669,17 +1116,48 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     kb = (kb + 15) & ~15;
     CRE_REQUIRE(kb >= 16 && kb <= kb_cap, "attention: key block %d out of range", kb);
     const int64_t rows = static_cast<int64_t>(a.n) * a.t;
+    CRE_REQUIRE((a.any_flag == nullptr) == (a.unit_flags == nullptr), "attention: any_flag and unit_flags go together");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     CUtensorMap tq, tkv;
+    if (fast && g_attn_split && a.t > 160 && a.t <= 208) {
+        int rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
+        if (rc) return rc;
+        FsParams fp;
+        fp.t = a.t;
+        fp.heads = a.heads;
+        fp.kb = kb;
+        fp.units = a.n * a.heads;
+        fp.out = static_cast<__nv_bfloat16*>(a.out);
+        fp.ld_out = a.heads * 64;
+        fp.k_col0 = a.k_col0;
+        fp.v_col0 = a.v_col0;
+        fp.any_flag = a.any_flag;
+        fp.unit_flags = a.unit_flags;
+        fp.safe_order = g_attn_safe;
+        const int grid = fp.units < sms ? fp.units : sms;
+        {
+            LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+#define CRE_FS_LAUNCH(POLY_)                                                                                                     \
+    do {                                                                                                                         \
+        CRE_SMEM_ATTR_ONCE(attention_split_kernel<POLY_>, kFsSmemBytes);                                                         \
+        attention_split_kernel<POLY_><<<grid, kFsThreads, kFsSmemBytes, stream>>>(tkv, fp);                                      \
+    } while (0)
+            if (g_attn_poly == 0) CRE_FS_LAUNCH(0x00u);
+            else if (g_attn_poly == 2) CRE_FS_LAUNCH(0x55u);
+            else CRE_FS_LAUNCH(0x44u);
+#undef CRE_FS_LAUNCH
+            CRE_CUDA_OK(cudaGetLastError());
+        }
+        return launch_exact(a, stream);
+    }
     if (fast) {
         int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 256);
         if (rc) return rc;
         rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
         if (rc) return rc;
-        static bool fast_attr_set = false;
-        if (!fast_attr_set) {
-            CRE_CUDA_OK(cudaFuncSetAttribute(attention_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
-            fast_attr_set = true;
-        }
+        CRE_SMEM_ATTR_ONCE(attention_fast_kernel, kFaSmemBytes);
         FaParams fp;
         fp.t = a.t;
         fp.heads = a.heads;
@@ -689,25 +1167,21 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         fp.ld_out = a.heads * 64;
         fp.k_col0 = a.k_col0;
         fp.v_col0 = a.v_col0;
-        fp.debug = g_attn_debug;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        fp.any_flag = a.any_flag;
+        fp.unit_flags = a.unit_flags;
         const int grid = fp.units < sms ? fp.units : sms;
-        LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
-        attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
-        CRE_CUDA_OK(cudaGetLastError());
-        return 0;
+        {
+            LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+            attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
+            CRE_CUDA_OK(cudaGetLastError());
+        }
+        return launch_exact(a, stream);
     }
     int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 128);
     if (rc) return rc;
     rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CRE_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-        attr_set = true;
-    }
+    CRE_SMEM_ATTR_ONCE(attention_kernel, kAttnSmemBytes);
     AttnParams p;
     p.t = a.t;
     p.heads = a.heads;
@@ -717,11 +1191,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     p.ld_out = a.heads * 64;
     p.k_col0 = a.k_col0;
     p.v_col0 = a.v_col0;
+    p.any_flag = a.any_flag;
+    p.unit_flags = a.unit_flags;
     dim3 grid((a.t + 127) / 128, a.heads, a.n);
-    LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
-    attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tkv, p);
-    CRE_CUDA_OK(cudaGetLastError());
-    return 0;
+    {
+        LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+        attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tkv, p);
+        CRE_CUDA_OK(cudaGetLastError());
+    }
+    return launch_exact(a, stream);
 }
 
 }  // namespace cre

@@ -34,6 +34,19 @@ void set_error(const char* fmt, ...);
         }                                 \
     } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory, once per DEVICE (the attribute is per device: a second engine on
+// another GPU of the same process needs its own call).  Use inside functions that return an int status.
+#define CRE_SMEM_ATTR_ONCE(kern, bytes)                                                                          \
+    do {                                                                                                         \
+        static int done_bytes_[64] = {};                                                                         \
+        int dev_ = 0;                                                                                            \
+        CRE_CUDA_OK(cudaGetDevice(&dev_));                                                                       \
+        if (dev_ < 0 || dev_ >= 64 || done_bytes_[dev_] < static_cast<int>(bytes)) {                             \
+            CRE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes))); \
+            if (dev_ >= 0 && dev_ < 64) done_bytes_[dev_] = static_cast<int>(bytes);                             \
+        }                                                                                                        \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------

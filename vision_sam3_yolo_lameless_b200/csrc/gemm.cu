@@ -108,11 +108,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     }
     static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline does not fit in shared memory");
     auto* kern = gemm_tn_kernel<EPI, CG, STAGES>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CRE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    CRE_SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);   // per instantiation and device
     const int rows_per_tile = kBlockM * CG;
     const int64_t tiles = static_cast<int64_t>((p.M + rows_per_tile - 1) / rows_per_tile) *
                           ((p.N + kBlockN - 1) / kBlockN);
@@ -148,8 +144,10 @@ int gemm_workers(int m, int n, int cg, int num_sms) {
     return workers < 1 ? 1 : workers;
 }
 
+#ifdef CRE_TUNING
 static int g_debug_mode = 0;
 void set_gemm_debug(int mode) { g_debug_mode = mode; }
+#endif
 static int g_tune_stages = 0;  // 0 = default_stages(cg); otherwise a tuning override for the plain epilogues
 void set_gemm_stages(int stages) { g_tune_stages = stages; }
 
@@ -188,6 +186,7 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     }
     if (p.ln_stats_in != nullptr && !epi_resid_ln(epi))
         CRE_REQUIRE(p.c1 != nullptr && p.bias != nullptr && p.ln_slots >= 1 && p.ln_slots <= 8, "gemm: folded LayerNorm needs c1, bias and 1..8 slots");
+#ifdef CRE_TUNING
     if (g_debug_mode != 0 && (epi == EPI_NONE || g_debug_mode >= 4)) {
         GemmParams q = p;
         q.debug_mode = g_debug_mode;
@@ -197,6 +196,7 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         g_debug_mode = saved;
         return r;
     }
+#endif
     if (epi == EPI_QKV && p.c1 == nullptr) {   // unfolded QKV: c1 is multiplied by 0
         GemmParams q = p;
         q.c1 = p.bias;

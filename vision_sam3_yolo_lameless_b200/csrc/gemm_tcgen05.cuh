@@ -74,8 +74,14 @@ struct GemmParams {
     int* part_idx;       // [M, slots, k]
     int part_slots;      // 2 * gridDim.x
     float* dump_scores;  // optional [M, N] full score matrix (parity tests)
-    int debug_mode;      // tuning only: 1 = no TMA (MMA issue rate), 2 = no MMA (TMA rate); results are garbage
+    int debug_mode;      // -DCRE_TUNING builds only: 1 = no TMA (MMA issue rate), 2 = no MMA (TMA rate), 4 / 8 / 16 = epilogue cut
+                         // short, 32 = L2 prefetch of A; results are garbage.  The shipped build compiles none of these paths.
 };
+#ifdef CRE_TUNING
+__device__ __forceinline__ int gemm_dbg(const GemmParams& p) { return p.debug_mode; }
+#else
+__device__ __forceinline__ constexpr int gemm_dbg(const GemmParams&) { return 0; }
+#endif
 
 constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;
@@ -300,7 +306,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // =============================== TMA producer ===============================
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = t_begin; t < t_end && p.debug_mode != 1; t += t_step) {
+        for (int t = t_begin; t < t_end && gemm_dbg(p) != 1; t += t_step) {
             const int mt = t / num_nt, nt = t % num_nt;
             const int row0 = (mt * CG + static_cast<int>(cta_rank)) * kBlockM;
             const int col0 = nt * kBlockN + static_cast<int>(cta_rank) * (kBlockN / CG);
@@ -316,7 +322,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 const int ka = kb * kBlockK;
                 const int kbb = ka % p.b_k_extent;
-                if (p.debug_mode & 32) {
+                if (gemm_dbg(p) & 32) {
                     // tuning: pull the A box kPrefetchKb k-blocks ahead (next tile's first boxes at the tail) into L2
                     int pkb = kb + kPrefetchKb, prow = row0;
                     if (pkb >= num_kb) {
@@ -346,11 +352,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * kBlockN;
             for (int kb = 0; kb < num_kb; ++kb) {
-                if (p.debug_mode != 1) mbar_wait(full_bar(stage), phase);
+                if (gemm_dbg(p) != 1) mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint64_t da = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA);
                 const uint64_t db = umma_desc_k_sw128(smem_b + stage * Cfg::kSmemB);
-                if (p.debug_mode != 2) {
+                if (gemm_dbg(p) != 2) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
@@ -580,12 +586,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int hh = 0; hh < 2; ++hh) {
                     const int n0 = ncol0 + hh * 64;
                     if (n0 >= p.N) break;
-                    if (p.debug_mode & 4) break;          // tuning: accumulators are never read
+                    if (gemm_dbg(p) & 4) break;          // tuning: accumulators are never read
                     uint32_t a[32], b[32];
                     tmem_ld32(taddr + hh * 64, a);
                     tmem_ld32(taddr + hh * 64 + 32, b);
                     tmem_ld_wait();
-                    if (p.debug_mode & 8) {               // tuning: TMEM read only
+                    if (gemm_dbg(p) & 8) {               // tuning: TMEM read only
                         uint32_t acc_or = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc_or |= a[j] | b[j];
@@ -622,7 +628,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     stage_begin();
 #pragma unroll
                     for (int u = 0; u < 8; ++u) stage_store(u, make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]));
-                    if (p.debug_mode & 16) continue;      // tuning: staged, never stored
+                    if (gemm_dbg(p) & 16) continue;      // tuning: staged, never stored
                     stage_commit(n0, row_base);
                 }
             } else if constexpr (epi_resid_ln(EPI)) {

@@ -14,9 +14,13 @@ void set_error(const char* fmt, ...);
 const char* last_error();
 int gemm_workers(int m, int n, int cg, int num_sms);
 void set_gemm_stages(int stages);
+#ifdef CRE_TUNING
 void set_gemm_debug(int mode);
+#endif
 void set_attention_fast(int on);
-void set_attention_debug(int mask);
+void set_attention_split(int on);
+void set_attention_poly(int v);
+void set_attention_safe_order(int on);
 
 // Kernel ids reported by cre_profile_stop (include/cre.h enum cre_kernel_id)
 // RAII bracket around one kernel launch: bumps the launch counter and, when the profiler is on, records an
@@ -57,7 +61,10 @@ struct AttnArgs {
     int k_col0, v_col0;
     int n, t, heads;
     void* out;        // bf16 [n*t, heads*64]
+    int* any_flag = nullptr;     // zeroed by the caller: set to 1 when some (frame, head) unit overflowed the fixed stabiliser ...
+    int* unit_flags = nullptr;   // ... and [n * heads] flags naming the units (attention.cu "Exactness"); all zero again on return
 };
+inline int64_t attention_flag_ints(int n, int heads) { return 64 + static_cast<int64_t>(n) * heads; }   // [any (64-int slot) | units]
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
 int launch_layernorm_bf16(const float* x, const float* g, const float* b, int rows, int dim, float eps,

@@ -500,11 +500,7 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     CUtensorMap tmap;
     int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows_tile);
     if (rc) return rc;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        CRE_CUDA_OK(cudaFuncSetAttribute(preprocess_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        smem_set = smem;
-    }
+    CRE_SMEM_ATTR_ONCE(preprocess_tma_kernel, smem);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -567,11 +563,7 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     p.sstride = sstride;
     const size_t smem = static_cast<size_t>(16) * sstride * sizeof(float);
     CRE_REQUIRE(smem <= 220 * 1024, "preprocess: input too wide for one band (%zu bytes of shared memory)", smem);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        CRE_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        smem_set = smem;
-    }
+    CRE_SMEM_ATTR_ONCE(preprocess_kernel, smem);
     dim3 grid((a.gw + kBandPatches - 1) / kBandPatches, a.gh, a.rois != nullptr ? a.n_rois : a.n);
     // two balanced rounds of the vertical pass: 16 rows x nvec column groups over the block
     const int nvec_max = (span_px * 3 + 15 + 15) / 16;

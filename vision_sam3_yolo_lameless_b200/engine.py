@@ -454,8 +454,10 @@ class ClipEmbedEngine:
         """qkv bf16 [n*t, 3*heads*64] (q pre-scaled, rotary applied) -> bf16 [n*t, heads*64]."""
         d = heads * 64
         out = torch.empty((n * t, d), dtype=torch.bfloat16, device=self.device)
+        need = _lib.check_size(self.lib.cre_attention_scratch_bytes(n, heads), "cre_attention_scratch_bytes")
+        scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         _lib.check(self.lib.cre_attention(self._ctx, qkv.data_ptr(), qkv.shape[1], d, 2 * d, n, t, heads, out.data_ptr(),
-                                          self._stream()), "cre_attention")
+                                          scratch.data_ptr(), need, self._stream()), "cre_attention")
         return out
 
 
