@@ -34,7 +34,8 @@ extern "C" {
 #endif
 
 #define CRE_ABI_VERSION 2
-#define CRE_TOPK_MAX 8
+#define CRE_TOPK_MAX 8      /* candidates one scan pass keeps per query */
+#define CRE_TOPK_LIMIT 256  /* largest k of cre_gallery_topk / cre_merge_topk (k > CRE_TOPK_MAX: ceil(k / 8) scan passes) */
 
 typedef struct cre_ctx cre_ctx;
 
@@ -126,7 +127,9 @@ int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_d
  * streams the shard once on the CUDA cores with the fp32 query in registers, one launch; larger q runs a tcgen05 tile GEMM with the
  * queries split hi+lo bf16 internally.  All device pointers 16-byte aligned; frame_emb / out_* of cre_pool_clips likewise.
  * Writes the k best (score desc, index asc) per query: out_scores_dev f32 [q, k], out_idx_dev i32 [q, k]
- * with idx = row_base + local row; missing entries (rows < k) are (-inf, INT32_MAX).
+ * with idx = row_base + local row; missing entries (rows < k) are (-inf, INT32_MAX).  1 <= k <= CRE_TOPK_LIMIT: the reference's
+ * callers pass any limit (main.py:165, matcher.py:104-108, gnn-pipeline main.py:52-58); k <= CRE_TOPK_MAX is one pass over the shard,
+ * larger k repeats the scan ceil(k / 8) times, each pass admitting only candidates that rank after the previous pass's last entry.
  * scratch_dev: cre_gallery_scratch_bytes(q, dim, k) bytes, 256-byte aligned.  dump_scores_dev (optional, may be NULL):
  * f32 [q, rows] full score matrix for parity tests. */
 int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k);
@@ -136,13 +139,17 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
                          int32_t* out_idx_dev, float* dump_scores_dev, void* stream);
 
 /* Merge `lists` candidate lists per query (e.g. one per gallery shard after the all-gather):
- * scores_dev f32 [lists, q, k], idx_dev i32 [lists, q, k] -> best k by (score desc, index asc). */
+ * scores_dev f32 [lists, q, k], idx_dev i32 [lists, q, k] -> best k by (score desc, index asc).  k <= CRE_TOPK_LIMIT;
+ * lists * k <= 4096 when k > CRE_TOPK_MAX. */
 int32_t cre_merge_topk(const float* scores_dev, const int32_t* idx_dev, int32_t lists, int32_t q, int32_t k,
                        float* out_scores_dev, int32_t* out_idx_dev, void* stream);
 
 /* Gallery maintenance (matcher.py:203-255 create_identity, :257-301 momentum update):
- * row <- bf16( normalise( momentum * row + (1 - momentum) * unit_query ) ); momentum = 0 writes the query. */
-int32_t cre_gallery_update_row(void* gallery_dev, int32_t dim, int32_t row, const float* unit_query_dev,
+ * v = normalise( momentum * old + (1 - momentum) * unit_query ); momentum = 0 writes the query.  master_dev f32 [rows, dim]
+ * (may be NULL) is the full-precision copy of the gallery -- the vector the reference keeps in Qdrant, blends into and upserts
+ * (matcher.py:267-301): old = its row, and it receives v.  gallery_dev bf16 [rows, dim], the copy cre_gallery_topk scans, receives
+ * bf16(v); with master_dev == NULL old is read from the bf16 row. */
+int32_t cre_gallery_update_row(void* gallery_dev, float* master_dev, int32_t dim, int32_t row, const float* unit_query_dev,
                                float momentum, void* stream);
 
 /* ---- building blocks exported for the parity tests (same kernels the calls above launch) ---------- */

@@ -60,11 +60,13 @@ class FakeQdrant:
                                            vector=col["vectors"][r].tolist() if with_vectors else None))
         return out
 
-    def scroll(self, collection_name, limit=10, with_vectors=False, with_payload=True, **kw):
+    def scroll(self, collection_name, limit=10, with_vectors=False, with_payload=True, offset=None, **kw):
+        """(points, next_page_offset) like qdrant_client: next_page_offset is None on the last page."""
         col = self.collections[collection_name]
-        pts = [SimpleNamespace(id=i, payload=p, vector=v.tolist() if with_vectors else None)
-               for i, v, p in list(zip(col["ids"], col["vectors"], col["payloads"]))[:limit]]
-        return pts, None
+        start = int(offset or 0)
+        rows = list(zip(col["ids"], col["vectors"], col["payloads"]))
+        pts = [SimpleNamespace(id=i, payload=p, vector=v.tolist() if with_vectors else None) for i, v, p in rows[start:start + limit]]
+        return pts, (start + limit if start + limit < len(rows) else None)
 
     def _search(self, collection_name, query, limit) -> List[SimpleNamespace]:
         col = self.collections[collection_name]

@@ -99,3 +99,33 @@ def assert_knn_equivalent(ei, ew, want_ei, want_ew, emb, k, tol=6e-3):
         assert len(set(sel.tolist())) == len(sel) and i not in sel
         assert (sim[i, sel] >= sim[i, ref].min() - tol).all(), i
         assert (np.diff(np.asarray(ew)[ei[0] == i]) >= -1e-6).all(), "neighbours must come in ascending similarity"
+
+
+def replay_reid_tight(engine, golden, sim_tol):
+    """Replay tests/golden/reid_tight.npz (oracle/make_golden_reid.py: the reference matcher driven 2e-3 on either side of every
+    threshold) through CowReIDMatcher on `engine`: same decisions and sighting counts, similarities within sim_tol, and the durable
+    store receives what the reference stores -- the full-precision normalised / momentum-blended vector (matcher.py:228-246,281-301),
+    not a bf16 rounding of it.  Returns the largest similarity difference seen."""
+    import asyncio
+    import json
+
+    import numpy as np
+    from oracle import fake_services
+    from vision_sam3_yolo_lameless_b200.reid import CowReIDMatcher
+
+    data = np.load(golden / "reid_tight.npz")
+    steps = json.loads(str(data["transcript"]))
+    qd = fake_services.FakeQdrant()
+    m = CowReIDMatcher(qdrant_url="fake://", engine=engine, qdrant_client=qd)
+    asyncio.run(m.connect())
+    worst = 0.0
+    for k, (q, want_vec, step) in enumerate(zip(data["queries"], data["stored_after"], steps)):
+        got = m.match_or_create(np.asarray(q), video_id=f"video-{step['name']}", track_id=k)
+        assert (got.cow_id, got.confidence, got.is_new_identity) == (step["cow_id"], step["confidence"], step["is_new"]), step["name"]
+        worst = max(worst, abs(got.similarity - step["similarity"]))
+        col = qd.collections[CowReIDMatcher.COLLECTION_NAME]
+        row = col["ids"].index(str(got.identity_id))
+        assert col["payloads"][row]["total_sightings"] == step["total_sightings"], step["name"]
+        np.testing.assert_allclose(col["vectors"][row], want_vec, atol=2e-6, err_msg=step["name"])    # fp32 master vs the reference's fp64
+    assert worst < sim_tol, worst
+    return worst

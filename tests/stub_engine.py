@@ -51,8 +51,11 @@ class StubEngine:
         s, i = reid_ref.merge_rule(scores.numpy(), idx.numpy(), scores.shape[2])
         return torch.from_numpy(s), torch.from_numpy(i)
 
-    def gallery_update_row(self, gallery, row, unit_query, momentum):
-        old = gallery[row].float().numpy().astype(np.float64)
+    def gallery_update_row(self, gallery, row, unit_query, momentum, master=None):
+        old = (master if master is not None else gallery)[row].float().numpy().astype(np.float64)
         uq = unit_query.reshape(-1).numpy().astype(np.float64)
         v = momentum * old + (1.0 - momentum) * uq if momentum != 0.0 else uq
-        gallery[row] = torch.from_numpy(v / (np.linalg.norm(v) + 1e-8)).to(gallery.dtype)
+        v = v / (np.linalg.norm(v) + 1e-8)
+        gallery[row] = torch.from_numpy(v).to(gallery.dtype)
+        if master is not None:
+            master[row] = torch.from_numpy(v).to(master.dtype)

@@ -81,7 +81,8 @@ def test_argument_validation_without_gpu():
     ws = lib.cre_workspace_bytes(C.byref(ok), 256, 14, 14)
     m = 256 * 201
     assert ws >= m * 768 * 4 + m * 768 * 2 + m * 1536 * 2 + m * 3072 * 2
-    assert lib.cre_gallery_scratch_bytes(64, 768, 9) == -1                  # k > CRE_TOPK_MAX
+    assert lib.cre_gallery_scratch_bytes(64, 768, 257) == -1                # k > CRE_TOPK_LIMIT
+    assert lib.cre_gallery_scratch_bytes(64, 768, 9) == lib.cre_gallery_scratch_bytes(64, 768, 8) > 0   # k > 8: passes of 8
     assert lib.cre_gallery_scratch_bytes(64, 768, 5) > 0
     assert lib.cre_set_cta_group(3) == -1
     assert lib.cre_destroy(None) == 0

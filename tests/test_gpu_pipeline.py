@@ -170,10 +170,18 @@ def test_matcher_scenario_vs_reference_transcript(engine_b, golden):
     for k, ((name, q), step) in enumerate(zip(reid_queries(), want["steps"])):
         got = m.match_or_create(np.asarray(q), video_id=f"video-{name}", track_id=k)
         assert (got.cow_id, got.confidence, got.is_new_identity) == (step["cow_id"], step["confidence"], step["is_new"]), name
-        assert abs(got.similarity - step["similarity"]) < 5e-3, name        # gallery rows are stored in bf16
+        assert abs(got.similarity - step["similarity"]) < 4e-4, name        # bf16 rounding of the scan copy only (fp32 master rows)
     _, cands = m.match_embedding(np.asarray(reid_queries()[0][1]))
     assert [c.cow_id for c in cands] == [c["cow_id"] for c in want["final_candidates"]]
-    np.testing.assert_allclose([c.similarity for c in cands], [c["similarity"] for c in want["final_candidates"]], atol=5e-3)
+    np.testing.assert_allclose([c.similarity for c in cands], [c["similarity"] for c in want["final_candidates"]], atol=4e-4)
+
+
+def test_matcher_near_thresholds_and_durable_store(engine_b, golden):
+    """The reference matcher's own transcript 2e-3 on either side of 0.65 / 0.75 / 0.85 (tests/golden/reid_tight.npz): same decisions,
+    similarities within the bf16 scan-copy error, and Qdrant receives the fp32 master vector (matcher.py:228-246,281-301)."""
+    from conftest import replay_reid_tight
+    worst = replay_reid_tight(engine_b[0], golden, sim_tol=4e-4)
+    print(f"largest similarity difference vs the reference transcript: {worst:.2e}")
 
 
 def test_full_size_properties(engine_b):

@@ -13,7 +13,8 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "libcre_b200.so"
 
-TOPK_MAX = 8
+TOPK_MAX = 8        # candidates one scan pass keeps per query (CRE_TOPK_MAX)
+TOPK_LIMIT = 256    # largest k of cre_gallery_topk / cre_merge_topk (CRE_TOPK_LIMIT)
 
 # enum cre_weight_kind
 W_PATCH, B_PATCH, PREFIX, LN_F_G, LN_F_B = 0, 1, 2, 3, 4
@@ -72,7 +73,7 @@ PROTOTYPES = {
     "cre_gallery_scratch_bytes": (_i64, [_i32, _i32, _i32]),
     "cre_gallery_topk": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "cre_merge_topk": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "cre_gallery_update_row": (_i32, [_vp, _i32, _i32, _vp, _f32, _vp]),
+    "cre_gallery_update_row": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, _vp]),
     "cre_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "cre_layernorm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "cre_row_stats": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),

@@ -660,13 +660,56 @@ static const int kMaxSlots = 512;
 static int g_scan_small = 1;   // tuning: 0 routes every query count through the tile GEMM
 
 int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k) {
-    if (q <= 0 || dim <= 0 || k <= 0 || k > CRE_TOPK_MAX) {
-        set_error("gallery_scratch_bytes: q=%d dim=%d k=%d", q, dim, k);
+    if (q <= 0 || dim <= 0 || k <= 0 || k > CRE_TOPK_LIMIT) {
+        set_error("gallery_scratch_bytes: q=%d dim=%d k=%d (k <= %d)", q, dim, k, CRE_TOPK_LIMIT);
         return -1;
     }
+    const int kp = k < CRE_TOPK_MAX ? k : CRE_TOPK_MAX;      // candidates kept per partial list and pass
     const int64_t a = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
-    const int64_t part = align_up(static_cast<int64_t>(q) * kMaxSlots * k * 4, 1024);
+    const int64_t part = align_up(static_cast<int64_t>(q) * kMaxSlots * kp * 4, 1024);
     return a + 2 * part;
+}
+
+// One pass of the gallery scan: the kp best candidates per query that come strictly AFTER (cut_s, cut_i) in the (score desc, index
+// asc) order (cut_s == NULL: no cutoff), written to out_* with row stride out_stride.
+static int gallery_topk_pass(cre_ctx* ctx, const float* queries_dev, int q, int dim, const void* gallery_dev, int rows, int row_base, int kp,
+                             uint8_t* sp, float* out_scores, int32_t* out_idx, int out_stride, const float* cut_s, const int32_t* cut_i,
+                             float* dump_scores_dev, bool first_pass, cudaStream_t stream) {
+    __nv_bfloat16* a_hilo = reinterpret_cast<__nv_bfloat16*>(sp);
+    const int64_t a_bytes = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
+    const int64_t part_bytes = align_up(static_cast<int64_t>(q) * kMaxSlots * kp * 4, 1024);
+    float* part_s = reinterpret_cast<float*>(sp + a_bytes);
+    int32_t* part_i = reinterpret_cast<int32_t*>(sp + a_bytes + part_bytes);
+
+    // serving form (Q <= 2: one message = one query): HBM-streaming scan on the CUDA cores, one partial list per CTA
+    if (g_scan_small) {
+        int small_slots = 2 * ctx->num_sms;
+        if (small_slots > kMaxSlots) small_slots = kMaxSlots;
+        const int took = launch_gallery_scan_small(queries_dev, q, dim, gallery_dev, rows, row_base, kp, part_s, part_i, small_slots,
+                                                   dump_scores_dev, ctx->scan_counter, out_scores, out_idx, out_stride, cut_s, cut_i, stream);
+        if (took != 0) return took < 0 ? took : 0;     // the kernel's last CTA has merged the partial lists into the result
+    }
+    const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
+    const int slots = 2 * workers;
+    CRE_REQUIRE(slots <= kMaxSlots, "gallery_topk: %d partial slots exceed %d", slots, kMaxSlots);
+    // the hi / lo split of the queries survives from the first pass; later passes only refill the partial lists
+    int rc = first_pass ? launch_topk_prepare(queries_dev, q, dim, a_hilo, part_s, part_i, static_cast<int64_t>(q) * slots * kp, stream)
+                        : launch_fill_topk(part_s, part_i, static_cast<int64_t>(q) * slots * kp, stream);
+    if (rc) return rc;
+    GemmParams p = base_params(q, rows, 2 * dim);
+    p.b_k_extent = dim;
+    p.topk = kp;
+    p.col_base = row_base;
+    p.part_scores = part_s;
+    p.part_idx = part_i;
+    p.part_slots = slots;
+    p.dump_scores = dump_scores_dev;
+    p.cut_scores = cut_s;
+    p.cut_idx = cut_i;
+    p.cut_stride = out_stride;
+    rc = launch_gemm(EPI_TOPK, 1, a_hilo, 2 * dim, gallery_dev, dim, p, ctx->num_sms, stream);
+    if (rc) return rc;
+    return launch_merge_topk(part_s, part_i, kp, static_cast<int64_t>(slots) * kp, slots, kp, q, kp, out_scores, out_idx, out_stride, stream);
 }
 
 int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int32_t dim, const void* gallery_dev,
@@ -675,60 +718,38 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
     CRE_REQUIRE(ctx != nullptr && queries_dev != nullptr && scratch_dev != nullptr && out_scores_dev != nullptr &&
                     out_idx_dev != nullptr, "gallery_topk: NULL argument");
     CRE_REQUIRE(q > 0 && dim > 0 && dim % 64 == 0 && rows >= 0, "gallery_topk: q=%d dim=%d rows=%d", q, dim, rows);
-    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX, "gallery_topk: k=%d out of range (1..%d)", k, CRE_TOPK_MAX);
+    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_LIMIT, "gallery_topk: k=%d out of range (1..%d)", k, CRE_TOPK_LIMIT);
     CRE_REQUIRE((reinterpret_cast<uintptr_t>(scratch_dev) & 255) == 0, "gallery_topk: scratch must be 256-byte aligned");
     const int64_t need = cre_gallery_scratch_bytes(q, dim, k);
     CRE_REQUIRE(scratch_bytes >= need, "gallery_topk: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)need);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rows == 0) return launch_fill_topk(out_scores_dev, out_idx_dev, static_cast<int64_t>(q) * k, stream);
     CRE_REQUIRE(gallery_dev != nullptr, "gallery_topk: NULL gallery");
-
+    // k <= CRE_TOPK_MAX (the reference asks for 5 everywhere): one pass.  Larger k: ceil(k / 8) passes over the shard, pass j
+    // keeping only candidates that rank strictly after entry 8 j - 1 of the result so far (read on the device: no host sync).
     uint8_t* sp = static_cast<uint8_t*>(scratch_dev);
-    __nv_bfloat16* a_hilo = reinterpret_cast<__nv_bfloat16*>(sp);
-    const int64_t a_bytes = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
-    const int64_t part_bytes = align_up(static_cast<int64_t>(q) * kMaxSlots * k * 4, 1024);
-    float* part_s = reinterpret_cast<float*>(sp + a_bytes);
-    int32_t* part_i = reinterpret_cast<int32_t*>(sp + a_bytes + part_bytes);
-
-    // serving form (Q <= 2: one message = one query): HBM-streaming scan on the CUDA cores, one partial list per CTA
-    if (g_scan_small) {
-        int small_slots = 2 * ctx->num_sms;
-        if (small_slots > kMaxSlots) small_slots = kMaxSlots;
-        const int took = launch_gallery_scan_small(queries_dev, q, dim, gallery_dev, rows, row_base, k, part_s, part_i, small_slots,
-                                                   dump_scores_dev, ctx->scan_counter, out_scores_dev, out_idx_dev, stream);
-        if (took != 0) return took < 0 ? took : 0;     // the kernel's last CTA has merged the partial lists into the result
+    for (int done = 0; done < k; done += CRE_TOPK_MAX) {
+        const int kp = k - done < CRE_TOPK_MAX ? k - done : CRE_TOPK_MAX;
+        const int rc = gallery_topk_pass(ctx, queries_dev, q, dim, gallery_dev, rows, row_base, kp, sp, out_scores_dev + done, out_idx_dev + done,
+                                         k, done ? out_scores_dev + done - 1 : nullptr, done ? out_idx_dev + done - 1 : nullptr,
+                                         done ? nullptr : dump_scores_dev, done == 0, stream);
+        if (rc) return rc;
     }
-    const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
-    const int slots = 2 * workers;
-    CRE_REQUIRE(slots <= kMaxSlots, "gallery_topk: %d partial slots exceed %d", slots, kMaxSlots);
-    int rc = launch_topk_prepare(queries_dev, q, dim, a_hilo, part_s, part_i, static_cast<int64_t>(q) * slots * k, stream);
-    if (rc) return rc;
-    GemmParams p = base_params(q, rows, 2 * dim);
-    p.b_k_extent = dim;
-    p.topk = k;
-    p.col_base = row_base;
-    p.part_scores = part_s;
-    p.part_idx = part_i;
-    p.part_slots = slots;
-    p.dump_scores = dump_scores_dev;
-    rc = launch_gemm(EPI_TOPK, 1, a_hilo, 2 * dim, gallery_dev, dim, p, ctx->num_sms, stream);
-    if (rc) return rc;
-    return launch_merge_topk(part_s, part_i, k, static_cast<int64_t>(slots) * k, slots, k, q, k, out_scores_dev, out_idx_dev,
-                             stream);
+    return 0;
 }
 
 int32_t cre_merge_topk(const float* scores_dev, const int32_t* idx_dev, int32_t lists, int32_t q, int32_t k,
                        float* out_scores_dev, int32_t* out_idx_dev, void* stream) {
     CRE_REQUIRE(scores_dev != nullptr && idx_dev != nullptr && out_scores_dev != nullptr && out_idx_dev != nullptr,
                 "merge_topk: NULL argument");
-    return launch_merge_topk(scores_dev, idx_dev, static_cast<int64_t>(q) * k, k, lists, k, q, k, out_scores_dev, out_idx_dev,
+    return launch_merge_topk(scores_dev, idx_dev, static_cast<int64_t>(q) * k, k, lists, k, q, k, out_scores_dev, out_idx_dev, k,
                              static_cast<cudaStream_t>(stream));
 }
 
-int32_t cre_gallery_update_row(void* gallery_dev, int32_t dim, int32_t row, const float* unit_query_dev, float momentum,
-                               void* stream) {
+int32_t cre_gallery_update_row(void* gallery_dev, float* master_dev, int32_t dim, int32_t row, const float* unit_query_dev,
+                               float momentum, void* stream) {
     CRE_REQUIRE(gallery_dev != nullptr && unit_query_dev != nullptr, "gallery_update_row: NULL argument");
-    return launch_gallery_update_row(static_cast<__nv_bfloat16*>(gallery_dev), dim, row, unit_query_dev, momentum,
+    return launch_gallery_update_row(static_cast<__nv_bfloat16*>(gallery_dev), master_dev, dim, row, unit_query_dev, momentum,
                                      static_cast<cudaStream_t>(stream));
 }
 

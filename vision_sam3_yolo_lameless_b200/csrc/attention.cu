@@ -695,7 +695,11 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // no clamp (overflow is caught by the row-sum flag, see "Exactness"), 32-key TMEM loads / 16-column stores.
 // =====================================================================================================================
 constexpr int kFsThreads = 384;   // warp 0 TMA, warps 1-2 MMA issuers (group 0 / 1), warp 3 TMEM allocator, warps 4-11 softmax
-constexpr int kFsSmemBytes = kFaSmemBytes;
+constexpr int kFsTileBytes = 208 * 128;                     // Q, K or V of one unit: <= 208 rows x 64 bf16
+constexpr int kFsStageBytes = 3 * kFsTileBytes;             // 78 KB
+constexpr int kFsOutOff = 2 * kFsStageBytes;                // eight 32-row x 128-byte O staging tiles (one per softmax warp)
+constexpr int kFsBarOff = kFsOutOff + 8 * 4096;
+constexpr int kFsSmemBytes = kFsBarOff + 512 + 1024;
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -704,14 +708,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// two fp32 -> packed bf16x2, round-half-up in magnitude, on the ALU pipe (F2FP is an XU-pipe instruction, and the XU pipe -- the
+// exponentials -- is what bounds this kernel).  Same 2^-9 relative error bound as round-to-nearest-even; inf stays inf.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632u);
+}
 
 // NK (16 | 32) scores of one row -> exponentials -> running sum + packed bf16 pairs.  POLY: bit i set = pair i of every 8 runs on
-// the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0.
+// the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0 (and is not computed).
 template <int NK, uint32_t POLY, bool MASK>
 __device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t (&pk)[NK / 2], int nvalid, uint64_t l2e2,
                                               uint64_t neg_m2, uint64_t& l2) {
 #pragma unroll
     for (int j = 0; j < NK; j += 2) {
+        if constexpr (MASK) {
+            if (j >= nvalid) {       // warp-uniform
+                pk[j >> 1] = 0u;
+                continue;
+            }
+        }
         float x0, x1, e0, e1;
         unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
         if ((POLY >> ((j >> 1) & 7)) & 1) {
@@ -722,7 +742,6 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t 
             e1 = ex2_approx(x1);
         }
         if constexpr (MASK) {
-            if (j >= nvalid) e0 = 0.0f;
             if (j + 1 >= nvalid) e1 = 0.0f;
         }
         l2 = add2(l2, pack2(e0, e1));
@@ -732,8 +751,6 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t 
 
 struct FsParams {
     int t, heads, kb, units;
-    __nv_bfloat16* out;
-    int ld_out;
     int k_col0, v_col0;
     int* any_flag;
     int* unit_flags;
@@ -742,38 +759,46 @@ struct FsParams {
 
 template <uint32_t POLY>
 __global__ void __launch_bounds__(kFsThreads, 1)
-attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsParams p) {
+attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ CUtensorMap tmap_out, const FsParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    auto s_q = [&](int s) { return smem_base + s * kFaStageBytes; };
-    auto s_k = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes; };
-    auto s_v = [&](int s) { return smem_base + s * kFaStageBytes + kFaQBytes + kFaKVBytes; };
-    const uint32_t bar_base = smem_base + 2 * kFaStageBytes;
+    auto s_q = [&](int s) { return smem_base + s * kFsStageBytes; };
+    auto s_k = [&](int s) { return smem_base + s * kFsStageBytes + kFsTileBytes; };
+    auto s_v = [&](int s) { return smem_base + s * kFsStageBytes + 2 * kFsTileBytes; };
+    const uint32_t bar_base = smem_base + kFsBarOff;
     auto kv_full = [&](int s) { return bar_base + 8u * s; };
     auto kv_empty = [&](int s) { return bar_base + 8u * (2 + s); };
     auto s_full = [&](int g, int h) { return bar_base + 8u * (4 + 2 * g + h); };
-    auto p_full = [&](int g, int h) { return bar_base + 8u * (8 + 2 * g + h); };
-    auto o_full = [&](int g) { return bar_base + 8u * (12 + g); };
-    auto tmem_free = [&](int g) { return bar_base + 8u * (14 + g); };
-    const uint32_t tmem_slot = bar_base + 8u * 16;
+    auto o_full = [&](int g) { return bar_base + 8u * (8 + g); };
+    auto tmem_free = [&](int g) { return bar_base + 8u * (10 + g); };
+    // P is handed over block by block (h0: four 32-key blocks; h1: up to three), one barrier per block and one phase per unit
+    auto p_full = [&](int g, int h, int b) { return bar_base + 8u * (12 + 7 * g + 4 * h + b); };
+    const uint32_t tmem_slot = bar_base + 8u * 26;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.t, KB = p.kb;
     const int n1 = (KB - 128) >> 4;                    // 16-key steps of the second half (3..5)
+    const int nf1 = (T - 128) >> 4, rem = T & 15;      // its full steps (2..5), keys in its partial step
     const uint32_t p1_col = 256u - 8u * n1;            // P_h1 columns
+    // h1 as blocks: steps {0, 1} | {2, 3} or {2} | {c3}
+    const bool wide = nf1 >= 4;
+    const int c3 = wide ? 4 : 3;
+    const int nb1 = 1 + (n1 >= 3 ? 1 : 0) + (n1 > c3 ? 1 : 0);
 
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_kv);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_out);
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(kv_full(i), 1);
             mbar_init(kv_empty(i), 2);                 // one tcgen05.commit per issuer
             mbar_init(s_full(i, 0), 1);
             mbar_init(s_full(i, 1), 1);
-            mbar_init(p_full(i, 0), 4);
-            mbar_init(p_full(i, 1), 4);
             mbar_init(o_full(i), 1);
             mbar_init(tmem_free(i), 4);
+            for (int b = 0; b < 7; ++b) mbar_init(p_full(i, 0, b), 4);
         }
         fence_barrier_init();
     } else if (warp == 3) {
@@ -818,11 +843,18 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsPara
                 for (int k = 0; k < 4; ++k) umma_bf16<1>(gb + h * 128, dq + 2 * k, dk + 2 * k, idesc, k != 0);
                 umma_commit<1>(s_full(g, h));
             };
+            // O (+)= P_h V_h, each block of P as soon as the softmax warps have published it
             auto issue_pv = [&](int h, bool fresh) {
-                const int steps = h == 0 ? 8 : n1;
                 const uint32_t pa = gb + (h == 0 ? 0u : p1_col);
-                for (int ks = 0; ks < steps; ++ks)
-                    umma_bf16_ts(o_col, pa + 8 * ks, umma_desc_mn_sw128(s_v(s) + (h * 8 + ks) * 2048), idesc_o, !(fresh && ks == 0));
+                const int nb = h == 0 ? 4 : nb1;
+                for (int b = 0; b < nb; ++b) {
+                    const int k0 = h == 0 ? 2 * b : (b == 0 ? 0 : (b == 1 ? 2 : c3));
+                    const int k1 = h == 0 ? k0 + 2 : (b == 0 ? 2 : (b == 1 ? (wide ? 4 : 3) : c3 + 1));
+                    mbar_wait(p_full(g, h, b), ph);
+                    tc_fence_after();
+                    for (int ks = k0; ks < k1; ++ks)
+                        umma_bf16_ts(o_col, pa + 8 * ks, umma_desc_mn_sw128(s_v(s) + (h * 8 + ks) * 2048), idesc_o, !(fresh && ks == 0));
+                }
             };
             mbar_wait(kv_full(s), (i >> 1) & 1);
             // S_h0 overwrites the P_h0 columns the PV MMAs queued right in front of it read: the tensor pipe executes one thread's
@@ -833,11 +865,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsPara
             mbar_wait(tmem_free(g), ph ^ 1u);                   // O of the previous unit (it overlays this region) is in registers
             tc_fence_after();
             issue_s(last);
-            mbar_wait(p_full(g, first), ph);
-            tc_fence_after();
             issue_pv(first, true);
-            mbar_wait(p_full(g, last), ph);
-            tc_fence_after();
             issue_pv(last, false);
             umma_commit<1>(o_full(g));
             umma_commit<1>(kv_empty(s));                        // this group is done with the smem stage
@@ -851,12 +879,24 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsPara
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 256;
         constexpr float kLog2e = 1.4426950408889634f;
         const uint64_t l2e2 = pack2(kLog2e, kLog2e);
-        const int nf1 = (T - 128) >> 4, rem = T & 15;           // full 16-key steps of h1 (2..5), keys in its partial step
+        // this warp's O staging tile (TMA 128B-swizzle layout): row r at r * 128, 16-byte unit u at (u ^ (r & 7))
+        const uint32_t stage_u32 = smem_base + kFsOutOff + (warp - 4) * 4096;
+        uint8_t* stage_row = smem_raw + (stage_u32 - smem_u32(smem_raw)) + lane * 128;
+        const uint32_t r7 = lane & 7;
+        // (frame, head) of the unit, advanced without a division per unit
+        const int step_frame = static_cast<int>(gridDim.x) / p.heads, step_head = static_cast<int>(gridDim.x) % p.heads;
+        int frame = static_cast<int>(blockIdx.x) / p.heads, head = static_cast<int>(blockIdx.x) % p.heads;
+        // publish block b of half h: its tcgen05.st (and every earlier one) has completed
+        auto publish = [&](int h, int b) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(g, h, b));
+        };
         int i = 0;
         for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
             const uint32_t ph = i & 1;
             const int first = i & 1;
-            const int frame = u / p.heads, head = u - frame * p.heads;
             uint64_t l2 = pack2(0.0f, 0.0f);
             uint64_t neg_m2 = pack2(0.0f, 0.0f);
             // stabiliser from the 32 scores in hand: m = their maximum
@@ -872,65 +912,78 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsPara
                 mbar_wait(s_full(g, h), ph);
                 __syncwarp();
                 tc_fence_after();
-                if (warp_active) {
-                    uint32_t va[32], vb[32];
-                    uint32_t pk[16];
-                    if (h == 0) {
-                        // ---- keys [0, 128): four 32-key blocks, the TMEM read of block b + 1 in flight under block b ----
-                        tmem_ld32(t_row, va);
-                        tmem_ld_wait();
-                        if (step == 0) set_m(va);
-                        tmem_ld32(t_row + 32, vb);
-                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                        tmem_st16(t_row, pk);
-                        tmem_ld_wait();
-                        tmem_ld32(t_row + 64, va);
-                        softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                        tmem_st16(t_row + 16, pk);
-                        tmem_ld_wait();
-                        tmem_ld32(t_row + 96, vb);
-                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                        tmem_st16(t_row + 32, pk);
-                        tmem_ld_wait();
-                        softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                        tmem_st16(t_row + 48, pk);
-                    } else {
-                        // ---- keys [128, KB): nf1 full 16-key steps (+ a partial one) as up to three blocks: 32 | 32 or 16 | 16 ----
-                        const uint32_t s1 = t_row + 128, p1 = t_row + p1_col;
-                        uint32_t(&vb16)[16] = reinterpret_cast<uint32_t(&)[16]>(vb);
-                        uint32_t(&va16)[16] = reinterpret_cast<uint32_t(&)[16]>(va);
-                        uint32_t(&pk8)[8] = reinterpret_cast<uint32_t(&)[8]>(pk);
-                        const bool wide = nf1 >= 4;                   // second block: steps 2, 3 (else: step 2 alone)
-                        const int c3 = wide ? 4 : 3;                  // step of the third block, if there is one
-                        tmem_ld32(s1, va);
-                        tmem_ld_wait();
-                        if (step == 0) set_m(va);
-                        if (wide) tmem_ld32(s1 + 32, vb);
-                        else if (n1 >= 3) tmem_ld16(s1 + 32, vb16);
-                        softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                        tmem_st16(p1, pk);
-                        tmem_ld_wait();
-                        if (n1 > c3) tmem_ld16(s1 + 16 * c3, va16);
-                        if (wide) {
-                            softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                            tmem_st16(p1 + 16, pk);
-                        } else if (n1 >= 3) {
-                            if (nf1 >= 3) softmax_block<16, POLY, false>(vb16, pk8, 16, l2e2, neg_m2, l2);
-                            else softmax_block<16, POLY, true>(vb16, pk8, rem, l2e2, neg_m2, l2);
-                            tmem_st8(p1 + 16, pk8);
-                        }
-                        tmem_ld_wait();
-                        if (n1 > c3) {
-                            if (c3 < nf1) softmax_block<16, POLY, false>(va16, pk8, 16, l2e2, neg_m2, l2);
-                            else softmax_block<16, POLY, true>(va16, pk8, rem, l2e2, neg_m2, l2);
-                            tmem_st8(p1 + 8 * c3, pk8);
-                        }
-                    }
-                    tmem_st_wait();
+                if (!warp_active) {
+                    tc_fence_before();
+                    __syncwarp();
+                    const int nb = h == 0 ? 4 : nb1;
+                    if (lane == 0)
+                        for (int b = 0; b < nb; ++b) mbar_arrive(p_full(g, h, b));
+                    continue;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full(g, h));
+                uint32_t va[32], vb[32];
+                uint32_t pk[16];
+                if (h == 0) {
+                    // ---- keys [0, 128): four 32-key blocks; the TMEM read of block b + 1 is in flight under the exponentials of block
+                    //      b, and block b is published (its store has long landed) just before block b + 1 is stored ----
+                    tmem_ld32(t_row, va);
+                    tmem_ld_wait();
+                    if (step == 0) set_m(va);
+                    tmem_ld32(t_row + 32, vb);
+                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                    tmem_st16(t_row, pk);
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + 64, va);
+                    softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                    publish(0, 0);
+                    tmem_st16(t_row + 16, pk);
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + 96, vb);
+                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                    publish(0, 1);
+                    tmem_st16(t_row + 32, pk);
+                    tmem_ld_wait();
+                    softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                    publish(0, 2);
+                    tmem_st16(t_row + 48, pk);
+                    publish(0, 3);
+                } else {
+                    // ---- keys [128, KB): nf1 full 16-key steps (+ a partial one) as up to three blocks: 32 | 32 or 16 | 16 ----
+                    const uint32_t s1 = t_row + 128, p1 = t_row + p1_col;
+                    uint32_t(&vb16)[16] = reinterpret_cast<uint32_t(&)[16]>(vb);
+                    uint32_t(&va16)[16] = reinterpret_cast<uint32_t(&)[16]>(va);
+                    uint32_t(&pk8)[8] = reinterpret_cast<uint32_t(&)[8]>(pk);
+                    tmem_ld32(s1, va);
+                    tmem_ld_wait();
+                    if (step == 0) set_m(va);
+                    if (wide) tmem_ld32(s1 + 32, vb);
+                    else if (n1 >= 3) tmem_ld16(s1 + 32, vb16);
+                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                    tmem_st16(p1, pk);
+                    tmem_ld_wait();
+                    if (n1 > c3) tmem_ld16(s1 + 16 * c3, va16);
+                    if (wide) {
+                        softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                        publish(1, 0);
+                        tmem_st16(p1 + 16, pk);
+                    } else if (n1 >= 3) {
+                        if (nf1 >= 3) softmax_block<16, POLY, false>(vb16, pk8, 16, l2e2, neg_m2, l2);
+                        else softmax_block<16, POLY, true>(vb16, pk8, rem, l2e2, neg_m2, l2);
+                        publish(1, 0);
+                        tmem_st8(p1 + 16, pk8);
+                    } else {
+                        publish(1, 0);
+                    }
+                    tmem_ld_wait();
+                    if (n1 > c3) {
+                        if (c3 < nf1) softmax_block<16, POLY, false>(va16, pk8, 16, l2e2, neg_m2, l2);
+                        else softmax_block<16, POLY, true>(va16, pk8, rem, l2e2, neg_m2, l2);
+                        publish(1, 1);
+                        tmem_st8(p1 + 8 * c3, pk8);
+                        publish(1, 2);
+                    } else if (n1 >= 3) {
+                        publish(1, 1);
+                    }
+                }
             }
 
             mbar_wait(o_full(g), ph);
@@ -947,30 +1000,51 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const FsPara
                     for (int j = 0; j < 16; ++j) o[c + j] = v[j];
                 }
                 tmem_ld_wait();
-                // O is in registers: hand the TMEM columns back before the global stores
+                // O is in registers: hand the TMEM columns back, then scale, round and store through this warp's staging tile
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_free(g));
-                if (row < T) {
-                    float l_lo, l_hi;
-                    unpack2(l2, l_lo, l_hi);
-                    const float l_sum = l_lo + l_hi;
-                    if (!(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, u);
-                    const float inv = 1.0f / l_sum;
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + row) * p.ld_out + head * 64);
+                if (lane == 0) {
+                    mbar_arrive(tmem_free(g));
+                    bulk_wait_read0();                  // the previous unit's bulk store has drained the staging tile
+                }
+                __syncwarp();
+                float l_lo, l_hi;
+                unpack2(l2, l_lo, l_hi);
+                const float l_sum = l_lo + l_hi;
+                if (row < T && !(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, u);
+                const float inv = 1.0f / l_sum;
+                const uint64_t inv2 = pack2(inv, inv);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        dst[j] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
-                                            pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
-                                            pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
-                                            pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a, b;
+                        unpack2(mul2(pack2(__uint_as_float(o[8 * j + 2 * e]), __uint_as_float(o[8 * j + 2 * e + 1])), inv2), a, b);
+                        w[e] = pack_bf16x2_alu(a, b);
+                    }
+                    *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(j) ^ r7) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    // rows >= T of the box (the tail of the second query tile) fall outside the tensor map's row dimension: clipped
+                    tma_store_3d(&tmap_out, stage_u32, head * 64, g * 128 + quarter * 32, frame);
+                    bulk_commit();
                 }
             } else {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_free(g));
             }
+            frame += step_frame;
+            head += step_head;
+            if (head >= p.heads) {
+                head -= p.heads;
+                ++frame;
+            }
         }
+        if (lane == 0) bulk_wait0();   // every bulk store of this warp has completed before the CTA may exit
     }
 
     tc_fence_before();
@@ -1129,20 +1203,21 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         fp.heads = a.heads;
         fp.kb = kb;
         fp.units = a.n * a.heads;
-        fp.out = static_cast<__nv_bfloat16*>(a.out);
-        fp.ld_out = a.heads * 64;
         fp.k_col0 = a.k_col0;
         fp.v_col0 = a.v_col0;
         fp.any_flag = a.any_flag;
         fp.unit_flags = a.unit_flags;
         fp.safe_order = g_attn_safe;
+        CUtensorMap tout;   // out as [frames][T][heads * 64]: a 32-row store box is clipped at the frame's last token
+        rc = make_tmap_bf16_3d(&tout, a.out, a.heads * 64, a.t, a.n, a.heads * 64, static_cast<int64_t>(a.t) * a.heads * 64, 32);
+        if (rc) return rc;
         const int grid = fp.units < sms ? fp.units : sms;
         {
             LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
 #define CRE_FS_LAUNCH(POLY_)                                                                                                     \
     do {                                                                                                                         \
         CRE_SMEM_ATTR_ONCE(attention_split_kernel<POLY_>, kFsSmemBytes);                                                         \
-        attention_split_kernel<POLY_><<<grid, kFsThreads, kFsSmemBytes, stream>>>(tkv, fp);                                      \
+        attention_split_kernel<POLY_><<<grid, kFsThreads, kFsSmemBytes, stream>>>(tkv, tout, fp);                                 \
     } while (0)
             if (g_attn_poly == 0) CRE_FS_LAUNCH(0x00u);
             else if (g_attn_poly == 2) CRE_FS_LAUNCH(0x55u);

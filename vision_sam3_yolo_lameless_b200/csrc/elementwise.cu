@@ -452,19 +452,21 @@ __device__ __forceinline__ void block_select_topk(int total, int k, LoadS load_s
 // one CTA per query (merge_topk_kernel below keeps the one-warp-per-query form for candidate counts beyond 256 * kSelNC)
 __global__ void __launch_bounds__(256) merge_topk_block_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
                                                                int64_t list_stride, int64_t query_stride, int lists, int per_list,
-                                                               int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+                                                               int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                                                               int out_stride) {
     __shared__ float red_s[8];
     __shared__ int red_i[8], red_p[8];
     const int query = blockIdx.x;
     auto off = [&](int c) { const int l = c / per_list; return l * list_stride + query * query_stride + (c - l * per_list); };
     block_select_topk(lists * per_list, k, [&](int c) { return __ldg(scores + off(c)); }, [&](int c) { return __ldg(idx + off(c)); },
-                      out_scores + static_cast<size_t>(query) * k, out_idx + static_cast<size_t>(query) * k, red_s, red_i, red_p);
+                      out_scores + static_cast<size_t>(query) * out_stride, out_idx + static_cast<size_t>(query) * out_stride, red_s, red_i,
+                      red_p);
 }
 
 __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
                                                          int64_t list_stride, int64_t query_stride, int lists,
                                                          int per_list, int q, int k, float* __restrict__ out_scores,
-                                                         int32_t* __restrict__ out_idx) {
+                                                         int32_t* __restrict__ out_idx, int out_stride) {
     const int query = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (query >= q) return;
     const int lane = threadIdx.x & 31;
@@ -519,8 +521,8 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
             if (better(os, oi, ws, wi) || (os == ws && oi == wi && ol < wl)) { ws = os; wi = oi; wl = ol; }
         }
         if (lane == 0) {
-            out_scores[static_cast<size_t>(query) * k + r] = ws;
-            out_idx[static_cast<size_t>(query) * k + r] = wi;
+            out_scores[static_cast<size_t>(query) * out_stride + r] = ws;
+            out_idx[static_cast<size_t>(query) * out_stride + r] = wi;
         }
         if (lane == wl) {  // pop the winner from its lane
 #pragma unroll
@@ -532,17 +534,24 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
 }
 
 int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stride, int64_t query_stride,
-                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx,
+                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx, int out_stride,
                       cudaStream_t stream) {
     CRE_REQUIRE(q > 0 && lists > 0, "merge_topk: empty input");
-    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_MAX && per_list >= 1 && per_list <= CRE_TOPK_MAX, "merge_topk: k=%d per_list=%d out of range (1..%d)", k,
-                per_list, CRE_TOPK_MAX);
+    CRE_REQUIRE(k >= 1 && k <= CRE_TOPK_LIMIT && per_list >= 1 && per_list <= CRE_TOPK_LIMIT && out_stride >= k,
+                "merge_topk: k=%d per_list=%d out of range (1..%d)", k, per_list, CRE_TOPK_LIMIT);
+    const bool block_form = static_cast<int64_t>(lists) * per_list <= 256 * kSelNC;
+    if (!block_form && (k > CRE_TOPK_MAX || per_list > CRE_TOPK_MAX)) {
+        set_error("merge_topk: %d lists x %d candidates with k=%d: more than %d candidates per query need k, per_list <= %d", lists, per_list, k,
+                  256 * kSelNC, CRE_TOPK_MAX);
+        return -3;
+    }
     LaunchScope scope(CRE_K_MERGE_TOPK, 8.0 * lists * per_list * q, stream);
-    if (static_cast<int64_t>(lists) * per_list <= 256 * kSelNC)
-        merge_topk_block_kernel<<<q, 256, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, k, out_scores, out_idx);
+    if (block_form)
+        merge_topk_block_kernel<<<q, 256, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, k, out_scores, out_idx,
+                                                       out_stride);
     else
         merge_topk_kernel<<<(q + 3) / 4, 128, 0, stream>>>(scores, idx, list_stride, query_stride, lists, per_list, q, k,
-                                                           out_scores, out_idx);
+                                                           out_scores, out_idx, out_stride);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -560,7 +569,8 @@ template <int Q, int CH, int RU>
 __global__ void __launch_bounds__(256, 2)
 gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16* __restrict__ gallery, int rows, int row_base, int k,
                           float* part_s, int32_t* part_i, int slots, float* __restrict__ dump, int* done_counter,
-                          float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+                          float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int out_stride,
+                          const float* __restrict__ cut_scores, const int32_t* __restrict__ cut_idx) {
     constexpr int DIM = CH * 256;
     static_assert(CRE_TOPK_MAX == 8, "the block merge below maps 64 candidates onto 32 lanes x 2");
     __shared__ float sh_s[8][Q][CRE_TOPK_MAX];
@@ -581,6 +591,13 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
     int ti[CRE_TOPK_MAX];
 #pragma unroll
     for (int j = 0; j < CRE_TOPK_MAX; ++j) { ts[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    // later passes of a k > CRE_TOPK_MAX request: only candidates strictly after the previous pass's last entry compete
+    float cut_s = INFINITY;
+    int cut_i = -1;
+    if (cut_scores != nullptr && lane < Q) {
+        cut_s = cut_scores[lane * out_stride];
+        cut_i = cut_idx[lane * out_stride];
+    }
 
     for (int r0 = gw; r0 < rows; r0 += nw * RU) {
         uint4 g[RU][CH];
@@ -621,7 +638,7 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
                 for (int q = 1; q < Q; ++q) mine = lane == q ? acc[q] : mine;
                 if (lane < Q) {
                     if (dump != nullptr) dump[static_cast<size_t>(lane) * rows + r] = mine;
-                    if (mine > ts[CRE_TOPK_MAX - 1]) {
+                    if (mine > ts[CRE_TOPK_MAX - 1] && (mine < cut_s || (mine == cut_s && row_base + r > cut_i))) {
                         float cs = mine;
                         int ci = row_base + r;
 #pragma unroll
@@ -686,7 +703,7 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
         const float* ps = part_s + static_cast<size_t>(q) * total;
         const int32_t* pi = part_i + static_cast<size_t>(q) * total;
         block_select_topk(total, k, [&](int c) { return __ldcg(ps + c); }, [&](int c) { return __ldcg(pi + c); },
-                          out_scores + q * k, out_idx + q * k, red_s, red_i, red_p);
+                          out_scores + q * out_stride, out_idx + q * out_stride, red_s, red_i, red_p);
     }
     if (threadIdx.x == 0) *done_counter = 0;               // ready for the next call on this context
 }
@@ -695,12 +712,12 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
 // not qualify (the caller falls back to the tile GEMM), negative on error
 int launch_gallery_scan_small(const float* queries, int q, int dim, const void* gallery, int rows, int row_base, int k, float* part_s,
                               int32_t* part_i, int slots, float* dump, int* done_counter, float* out_scores, int32_t* out_idx,
-                              cudaStream_t stream) {
+                              int out_stride, const float* cut_scores, const int32_t* cut_idx, cudaStream_t stream) {
     if (q < 1 || q > 2 || (dim != 768 && dim != 1024) || done_counter == nullptr || slots * k > 256 * kSelNC) return 0;
     if ((reinterpret_cast<uintptr_t>(gallery) & 15) != 0 || (reinterpret_cast<uintptr_t>(queries) & 15) != 0) return 0;
     LaunchScope scope(CRE_K_GEMM_TOPK, 2.0 * rows * dim, stream);
     const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gallery);
-#define CRE_SCAN(Q_, CH_, RU_) gallery_scan_small_kernel<Q_, CH_, RU_><<<slots, 256, 0, stream>>>(queries, g, rows, row_base, k, part_s, part_i, slots, dump, done_counter, out_scores, out_idx)
+#define CRE_SCAN(Q_, CH_, RU_) gallery_scan_small_kernel<Q_, CH_, RU_><<<slots, 256, 0, stream>>>(queries, g, rows, row_base, k, part_s, part_i, slots, dump, done_counter, out_scores, out_idx, out_stride, cut_scores, cut_idx)
     if (q == 1 && dim == 768) CRE_SCAN(1, 3, 4);
     else if (q == 1) CRE_SCAN(1, 4, 4);
     else if (dim == 768) CRE_SCAN(2, 3, 2);
@@ -710,8 +727,10 @@ int launch_gallery_scan_small(const float* queries, int q, int dim, const void* 
     return 1;
 }
 
-// gallery row <- bf16(normalise(momentum * row + (1 - momentum) * unit_q))   (matcher.py:281-285); one CTA
-__global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* __restrict__ row, int dim,
+// gallery row <- normalise(momentum * row + (1 - momentum) * unit_q)   (matcher.py:281-285); one CTA.  `master` (optional) is the
+// fp32 copy of the row -- what the reference keeps in Qdrant and blends into (matcher.py:267-301): the update reads and writes IT,
+// and the bf16 row, the scan copy, is only ever a rounding of the master, so repeated updates do not accumulate bf16 error.
+__global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* __restrict__ row, float* __restrict__ master, int dim,
                                                                  const float* __restrict__ uq, float momentum) {
     __shared__ float red[8];
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -720,7 +739,7 @@ __global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* 
     for (int i = 0; i < 4; ++i) {
         const int c = threadIdx.x + 256 * i;
         if (c < dim) {
-            const float old = momentum != 0.0f ? __bfloat162float(row[c]) : 0.0f;
+            const float old = momentum != 0.0f ? (master != nullptr ? master[c] : __bfloat162float(row[c])) : 0.0f;
             v[i] = momentum * old + (1.0f - momentum) * uq[c];
             ss += v[i] * v[i];
         }
@@ -735,15 +754,20 @@ __global__ void __launch_bounds__(256) gallery_update_row_kernel(__nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = threadIdx.x + 256 * i;
-        if (c < dim) row[c] = __float2bfloat16_rn(v[i] * scale);
+        if (c < dim) {
+            row[c] = __float2bfloat16_rn(v[i] * scale);
+            if (master != nullptr) master[c] = v[i] * scale;
+        }
     }
 }
 
-int launch_gallery_update_row(__nv_bfloat16* gallery, int dim, int row, const float* unit_q, float momentum,
+int launch_gallery_update_row(__nv_bfloat16* gallery, float* master, int dim, int row, const float* unit_q, float momentum,
                               cudaStream_t stream) {
     CRE_REQUIRE(dim > 0 && dim <= 1024 && row >= 0, "gallery_update_row: bad dim/row");
     LaunchScope scope(CRE_K_GALLERY_UPDATE, 8.0 * dim, stream);
-    gallery_update_row_kernel<<<1, 256, 0, stream>>>(gallery + static_cast<size_t>(row) * dim, dim, unit_q, momentum);
+    gallery_update_row_kernel<<<1, 256, 0, stream>>>(gallery + static_cast<size_t>(row) * dim,
+                                                     master != nullptr ? master + static_cast<size_t>(row) * dim : nullptr, dim, unit_q,
+                                                     momentum);
     CRE_CUDA_OK(cudaGetLastError());
     return 0;
 }

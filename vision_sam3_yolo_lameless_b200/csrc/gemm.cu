@@ -54,6 +54,27 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
     return 0;
 }
 
+// bf16 tensor [frames][rows][cols] (row stride ld elements, frame stride in elements) -> [1, box_rows, 64] boxes, 128B swizzle:
+// boxes are clipped at the end of a frame's rows (stores) / zero filled (loads)
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t ld, int64_t frame_stride,
+                      int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CRE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0 && (frame_stride * 2) % 16 == 0,
+                "TMA 3-D tensor needs a 16-byte aligned base and strides");
+    CRE_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range: %d", box_rows);
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(frames)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(frame_stride) * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D bf16) failed with CUresult %d (cols=%lld rows=%lld frames=%lld)", (int)r,
+                (long long)cols, (long long)rows, (long long)frames);
+    return 0;
+}
+
 int make_tmap_u8_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t row_pitch,
                     int64_t frame_pitch, int box_cols, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();

@@ -74,6 +74,11 @@ struct GemmParams {
     int* part_idx;       // [M, slots, k]
     int part_slots;      // 2 * gridDim.x
     float* dump_scores;  // optional [M, N] full score matrix (parity tests)
+    // later passes of a k > kTopKMax request: only candidates strictly AFTER (cut_scores[m * cut_stride], cut_idx[m * cut_stride])
+    // in the (score desc, index asc) order compete.  NULL = first pass.
+    const float* cut_scores;
+    const int* cut_idx;
+    int cut_stride;
     int debug_mode;      // -DCRE_TUNING builds only: 1 = no TMA (MMA issue rate), 2 = no MMA (TMA rate), 4 / 8 / 16 = epilogue cut
                          // short, 32 = L2 prefetch of A; results are garbage.  The shipped build compiles none of these paths.
 };
@@ -477,6 +482,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         };
         if constexpr (EPI == EPI_TOPK) topk_reset();
+        [[maybe_unused]] float cut_s = INFINITY;     // this thread's row: cutoff of the previous pass (none: every finite score is after it)
+        [[maybe_unused]] int cut_i = -1;
 
         int it = 0;
         for (int t = t_begin; t < t_end; t += t_step, ++it) {
@@ -493,6 +500,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (mt != tk_mt) {
                     if (tk_mt >= 0) { topk_flush(tk_mt); topk_reset(); }
                     tk_mt = mt;
+                    if (p.cut_scores != nullptr && row_ok) {
+                        cut_s = p.cut_scores[static_cast<size_t>(row) * p.cut_stride];
+                        cut_i = p.cut_idx[static_cast<size_t>(row) * p.cut_stride];
+                    }
                 }
             }
             mbar_wait(tmem_full_bar(as), aphase);
@@ -779,7 +790,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 const int n = n0 + j;
                                 const float s = x[j];
                                 // columns arrive in ascending index, so on ties the earlier (smaller) index stays ahead
-                                if (n < p.N && s > tk_s[kTopKMax - 1]) {
+                                if (n < p.N && s > tk_s[kTopKMax - 1] && (s < cut_s || (s == cut_s && p.col_base + n > cut_i))) {
                                     float cs_ = s;
                                     int ci_ = p.col_base + n;
 #pragma unroll

@@ -43,6 +43,9 @@ int profile_stop(int32_t* ids, float* ms, double* work, int cap);
 // [box_rows x 64] box and 128-byte swizzle.  Returns 0 / negative error code.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t ld, int64_t frame_stride,
+                      int box_rows);
+
 // uint8 tensor [frames, rows, cols] (strides in bytes, multiples of 16) -> TMA descriptor with a [1, box_rows, box_cols] box,
 // no swizzle, zero fill out of bounds
 int make_tmap_u8_3d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t frames, int64_t row_pitch,
@@ -84,13 +87,13 @@ int launch_split_hi_lo(const float* q, int rows, int dim, __nv_bfloat16* out, cu
 int launch_fill_topk(float* scores, int32_t* idx, int64_t count, cudaStream_t stream);
 int launch_gallery_scan_small(const float* queries, int q, int dim, const void* gallery, int rows, int row_base, int k, float* part_s,
                               int32_t* part_i, int slots, float* dump, int* done_counter, float* out_scores, int32_t* out_idx,
-                              cudaStream_t stream);
+                              int out_stride, const float* cut_scores, const int32_t* cut_idx, cudaStream_t stream);
 int launch_topk_prepare(const float* q, int rows, int dim, __nv_bfloat16* out, float* scores, int32_t* idx, int64_t count,
                         cudaStream_t stream);
 int launch_merge_topk(const float* scores, const int32_t* idx, int64_t list_stride, int64_t query_stride,
-                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx,
+                      int lists, int per_list, int q, int k, float* out_scores, int32_t* out_idx, int out_stride,
                       cudaStream_t stream);
-int launch_gallery_update_row(__nv_bfloat16* gallery, int dim, int row, const float* unit_q, float momentum,
+int launch_gallery_update_row(__nv_bfloat16* gallery, float* master, int dim, int row, const float* unit_q, float momentum,
                               cudaStream_t stream);
 
 struct ResizeTable {   // device-resident separable antialias weights for one axis

@@ -386,8 +386,13 @@ class ClipEmbedEngine:
                                            out_i.data_ptr(), self._stream()), "cre_merge_topk")
         return out_s, out_i
 
-    def gallery_update_row(self, gallery: torch.Tensor, row: int, unit_query: torch.Tensor, momentum: float) -> None:
-        _lib.check(self.lib.cre_gallery_update_row(gallery.data_ptr(), gallery.shape[1], int(row),
+    def gallery_update_row(self, gallery: torch.Tensor, row: int, unit_query: torch.Tensor, momentum: float,
+                           master: Optional[torch.Tensor] = None) -> None:
+        """One gallery row <- normalise(momentum * old + (1 - momentum) * unit_query); ``master`` f32 [N, D] is the full-precision
+        copy (read for ``old``, written), ``gallery`` bf16 [N, D] the scan copy."""
+        if master is not None and (master.dtype != torch.float32 or master.shape != gallery.shape or not master.is_contiguous()):
+            raise ValueError("master must be a contiguous f32 tensor of the gallery's shape")
+        _lib.check(self.lib.cre_gallery_update_row(gallery.data_ptr(), _ptr(master), gallery.shape[1], int(row),
                                                    unit_query.to(torch.float32).contiguous().data_ptr(),
                                                    float(momentum), self._stream()), "cre_gallery_update_row")
 

@@ -71,6 +71,7 @@ class DINOv3Pipeline:
         self.results_dir = Path(results_dir) if results_dir is not None else Path("/app/data/results/dinov3")
         self.results_dir.mkdir(parents=True, exist_ok=True)
         self._ensure_collection()
+        self._mirror_collection()
 
     # -- main.py:70-93 ---------------------------------------------------------------------------
     def _ensure_collection(self):
@@ -88,6 +89,22 @@ class DINOv3Pipeline:
                 print(f"Created Qdrant collection: {self.collection_name}")
         except Exception as e:
             print(f"Error ensuring collection: {e}")
+
+    def _mirror_collection(self):
+        """gallery_backend == 'gpu': load what the durable store already holds (service restart) into the device gallery, so that
+        search_similar sees the same points the reference's Qdrant search would.  If the mirror cannot be loaded the device gallery is
+        dropped and searches go to Qdrant, as with gallery_backend == 'qdrant' -- never a silently empty gallery."""
+        if self.gallery is None or self.qdrant_client is None:
+            return
+        try:
+            names = [c.name for c in self.qdrant_client.get_collections().collections]
+            if self.collection_name in names:
+                n = self.gallery.load_from_qdrant(self.qdrant_client, self.collection_name)
+                print(f"Mirrored {n} points of {self.collection_name} into the GPU gallery")
+        except Exception as e:
+            print(f"Error mirroring {self.collection_name} into the GPU gallery ({e}); searching Qdrant instead")
+            self.gallery = None
+            self.gallery_backend = "qdrant"
 
     # -- batched entry points (new; the reference embeds one frame per call) ------------------------
     def embed_frames(self, frames: np.ndarray, bgr: bool = True) -> np.ndarray:

@@ -4,18 +4,25 @@ Replaces the similarity + top-k arithmetic of the remote Qdrant calls at
 services/tracking-service/app/reid/matcher.py:127-132 (query_points) and
 services/dinov3-pipeline/app/main.py:168-172 (search); upserts (matcher.py:243-246,291-301,
 dinov3 main.py:240-243) keep going to Qdrant as the durable store when a client is attached
-("write-through"), and also land in the device matrix so that the next search sees them.
+("write-through"), and also land in the device matrices so that the next search sees them.
 
-Vectors are stored L2-normalised in bf16 [capacity, D] (Qdrant normalises COSINE vectors on insert).
+Two device copies of every vector, both L2-normalised (Qdrant normalises COSINE vectors on insert):
+
+* ``master`` f32 [capacity, D] -- the vector at the precision Qdrant keeps it.  The reference reads it back
+  (``retrieve(with_vectors=True)``, matcher.py:267-271), blends the new embedding into it and upserts the result
+  (:281-301): momentum updates therefore read and write THIS copy, and ``vector()`` / the Qdrant write-through return it;
+* ``matrix`` bf16 [capacity, D] -- what the scan kernel (K4) streams: always a rounding of the master row, never a source.
+
 Row order = insertion order; search ties break on the lower row index.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
 import torch
 
+from . import _lib
 from .engine import ClipEmbedEngine
 
 
@@ -31,12 +38,24 @@ class ScoredPoint:
         return f"ScoredPoint(id={self.id!r}, score={self.score:.6f})"
 
 
+def scroll_all(qdrant_client, collection_name: str, page: int = 1024) -> Iterable[Any]:
+    """Every point of a collection with its vector, paged (``scroll`` returns (points, next_page_offset))."""
+    offset = None
+    while True:
+        points, offset = qdrant_client.scroll(collection_name=collection_name, limit=page, offset=offset,
+                                              with_vectors=True, with_payload=True)
+        yield from points
+        if offset is None or not points:
+            return
+
+
 class GpuGallery:
     def __init__(self, engine: ClipEmbedEngine, dim: int, capacity: int = 4096):
         self.engine = engine
         self.dim = int(dim)
         self.capacity = int(capacity)
         self.matrix = torch.zeros((self.capacity, self.dim), dtype=torch.bfloat16, device=engine.device)
+        self.master = torch.zeros((self.capacity, self.dim), dtype=torch.float32, device=engine.device)
         self.ids: List[Any] = []
         self.payloads: List[Dict[str, Any]] = []
         self._row_of: Dict[Any, int] = {}
@@ -48,24 +67,46 @@ class GpuGallery:
         if need <= self.capacity:
             return
         cap = max(need, 2 * self.capacity)
-        m = torch.zeros((cap, self.dim), dtype=torch.bfloat16, device=self.engine.device)
-        m[: len(self.ids)] = self.matrix[: len(self.ids)]
-        self.matrix, self.capacity = m, cap
+        n = len(self.ids)
+        for name, dt in (("matrix", torch.bfloat16), ("master", torch.float32)):
+            m = torch.zeros((cap, self.dim), dtype=dt, device=self.engine.device)
+            m[:n] = getattr(self, name)[:n]
+            setattr(self, name, m)
+        self.capacity = cap
 
-    def load(self, ids: List[Any], unit_vectors: torch.Tensor, payloads: Optional[List[Dict[str, Any]]] = None) -> None:
-        """Bulk load already-normalised vectors [N, D] (any float dtype, host or device)."""
+    def _unit(self, vectors) -> torch.Tensor:
+        """[n, D] (host or device, any float dtype) -> device f32 unit rows, e / (||e|| + 1e-8) (K3b: one-row "clips")."""
+        v = vectors if isinstance(vectors, torch.Tensor) else torch.as_tensor(np.asarray(vectors, dtype=np.float32))
+        v = v.to(device=self.engine.device, dtype=torch.float32).reshape(-1, self.dim)
+        _, unit = self.engine.pool_clips(v, torch.arange(v.shape[0] + 1, dtype=torch.int32))
+        return unit
+
+    def load(self, ids: List[Any], vectors, payloads: Optional[List[Dict[str, Any]]] = None) -> None:
+        """Replace the contents with n vectors [n, D] in ONE normalisation launch (rows need not be normalised)."""
         n = len(ids)
         self._grow(n)
-        self.matrix[:n] = unit_vectors.to(device=self.engine.device, dtype=torch.bfloat16)
+        if n:
+            unit = self._unit(vectors)
+            self.master[:n] = unit
+            self.matrix[:n] = unit              # dtype cast on copy: round-to-nearest-even bf16
         self.ids = list(ids)
-        self.payloads = list(payloads) if payloads is not None else [{} for _ in ids]
+        self.payloads = [dict(p or {}) for p in payloads] if payloads is not None else [{} for _ in ids]
         self._row_of = {pid: r for r, pid in enumerate(self.ids)}
+
+    def load_from_qdrant(self, qdrant_client, collection_name: str, page: int = 1024) -> int:
+        """Mirror an existing collection (service start / restart): paged scroll, one bulk load.  Returns the point count."""
+        ids, vecs, payloads = [], [], []
+        for p in scroll_all(qdrant_client, collection_name, page):
+            ids.append(p.id)
+            vecs.append(np.asarray(p.vector, dtype=np.float32))
+            payloads.append(dict(p.payload or {}))
+        self.load(ids, np.stack(vecs) if vecs else np.zeros((0, self.dim), np.float32), payloads)
+        return len(ids)
 
     def upsert(self, point_id: Any, vector, payload: Optional[Dict[str, Any]] = None, momentum: float = 0.0) -> int:
         """Insert or overwrite one point; the row is normalised on the device (cre_gallery_update_row).
-        momentum > 0 blends with the stored row: row <- norm(momentum * row + (1 - momentum) * unit(vector))."""
-        v = torch.as_tensor(np.asarray(vector, dtype=np.float32)).to(self.engine.device).reshape(1, -1)
-        _, v = self.engine.pool_clips(v, torch.tensor([0, 1], dtype=torch.int32))  # unit(vector), matcher.py:274
+        momentum > 0 blends with the stored MASTER row: row <- norm(momentum * row + (1 - momentum) * unit(vector))."""
+        unit = self._unit(np.asarray(vector, dtype=np.float32)[None, :])          # unit(vector), matcher.py:274
         row = self._row_of.get(point_id)
         if row is None:
             row = len(self.ids)
@@ -76,25 +117,30 @@ class GpuGallery:
             momentum = 0.0
         elif payload is not None:
             self.payloads[row] = dict(payload)
-        self.engine.gallery_update_row(self.matrix, row, v, momentum)
+        self.engine.gallery_update_row(self.matrix, row, unit, momentum, master=self.master)
         return row
 
     def vector(self, point_id: Any) -> Optional[np.ndarray]:
+        """The stored unit vector at full (f32) precision -- what Qdrant's retrieve(with_vectors=True) returns."""
         row = self._row_of.get(point_id)
-        return None if row is None else self.matrix[row].float().cpu().numpy()
+        return None if row is None else self.master[row].cpu().numpy()
 
     def search(self, query, k: int = 5) -> List[ScoredPoint]:
         """One query -> up to k ScoredPoints in descending cosine order (Qdrant normalises the query too)."""
         return self.search_batch(np.asarray(query, dtype=np.float32)[None, :], k)[0]
 
     def search_batch(self, queries, k: int = 5) -> List[List[ScoredPoint]]:
-        q = torch.as_tensor(np.asarray(queries, dtype=np.float32)).to(self.engine.device)
+        k = int(k)
+        if k < 1:
+            raise ValueError(f"top_k={k}: must be >= 1")
+        if k > _lib.TOPK_LIMIT:
+            raise ValueError(f"top_k={k} exceeds the kernel limit ({_lib.TOPK_LIMIT}); the request is refused rather than truncated")
+        q = np.asarray(queries, dtype=np.float32)
         n = len(self.ids)
         if n == 0:
             return [[] for _ in range(q.shape[0])]
-        offs = torch.arange(q.shape[0] + 1, dtype=torch.int32)
-        _, unit = self.engine.pool_clips(q, offs)  # one-frame "clips": L2 normalisation with the +1e-8 rule
-        scores, idx = self.engine.gallery_topk(unit, self.matrix[:n], k=min(k, 8))
+        unit = self._unit(q)                     # L2 normalisation with the +1e-8 rule
+        scores, idx = self.engine.gallery_topk(unit, self.matrix[:n], k=min(k, n))
         scores, idx = scores.cpu().numpy(), idx.cpu().numpy()
         out = []
         for r in range(q.shape[0]):

@@ -6,7 +6,8 @@
 Same constructor arguments, thresholds, method names, return types and error behaviour.  The read
 path (normalise -> cosine top-k, matcher.py:123-132) runs on the GPU-resident gallery
 (:class:`GpuGallery`, kernels K3b/K4); the write path (create / momentum update, matcher.py:203-301)
-updates the device row with one kernel and writes through to Qdrant when a client is attached.
+updates the device rows with one kernel -- the fp32 master row is what gets blended and what is written
+through to Qdrant when a client is attached (matcher.py:267-301); the bf16 row is only the scan copy.
 Threshold / decision logic (matcher.py:144-201,303-311) stays on the host, unchanged.
 """
 from __future__ import annotations
@@ -76,10 +77,7 @@ class CowReIDMatcher:
                 print(f"Created Qdrant collection: {self.COLLECTION_NAME}")
             else:
                 print(f"Using existing Qdrant collection: {self.COLLECTION_NAME}")
-                points, _ = self.qdrant_client.scroll(collection_name=self.COLLECTION_NAME, limit=1_000_000,
-                                                      with_vectors=True)
-                for p in points:
-                    self.client.upsert(p.id, np.asarray(p.vector, dtype=np.float32), p.payload)
+                self.client.load_from_qdrant(self.qdrant_client, self.COLLECTION_NAME)     # paged scroll, one bulk load
         self.identity_counter = len(self.client)
 
     # -- matcher.py:104-149 ----------------------------------------------------------------------
