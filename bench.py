@@ -17,6 +17,11 @@ memory: host->device copies (pipelined with compute) and the device->host read o
 one extra instrumented step after the timed region (cre_profile_start/stop bracket every launch on its stream).
 `cpu_baseline`: the reference's per-frame path (oracle/pipeline_ref.py = HF processor + HF DINOv3ViTModel fp32, batch 1) on
 this box's host cores, bounded sample.
+`gpu_baseline` (N = 1) / `--impl hf_gpu`: the GPU comparison point SURVEY.md 8(d) names -- the stock HF path the reference itself
+takes when CUDA is present (main.py:33-36,107-113): DINOv3ViTImageProcessor on CUDA tensors + DINOv3ViTModel.to(cuda, bf16) with
+SDPA, at the same batch -- on a bounded sample of the same frames.
+`sharded_check` (N > 1): once, outside the timed region, every rank scans the WHOLE gallery (all-gathered) with all queries and
+compares with the sharded result bit for bit.
 """
 from __future__ import annotations
 
@@ -41,7 +46,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--impl", choices=["b200", "reference", "hf_gpu"], default="b200")
     ap.add_argument("--clips", type=int, default=64, help="clips per rank per step")
     ap.add_argument("--frames-per-clip", type=int, default=150)
     ap.add_argument("--height", type=int, default=1080)
@@ -55,6 +60,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--gpu-baseline-batches", type=int, default=2, help="timed batches of the stock-HF GPU sample")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table of the instrumented step to stderr")
     return ap.parse_args()
 
@@ -195,17 +202,82 @@ def run_reference(args, rank: int):
     })
 
 
+def hf_gpu_sample(args, dev, frames_dev, batches: int):
+    """The reference's own code path on this GPU (main.py:33-36: `self.model.to(self.device)`, :107-113: processor -> model ->
+    token mean), batched: stock HF DINOv3ViTImageProcessor applied to CUDA tensors (chunks of 64 frames: the processor works in
+    fp32 at full resolution), stock HF DINOv3ViTModel in bf16 with its default SDPA attention at batch `--batch-frames`, token mean.
+    None of this repo's kernels run here.  Returns a dict for the `gpu_baseline` key."""
+    import torch
+    from transformers import DINOv3ViTImageProcessor
+
+    from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
+
+    model = random_init_vit(args.model).to(dev, torch.bfloat16).eval()
+    proc = DINOv3ViTImageProcessor(size={"height": args.resize, "width": args.resize})
+    n = min(args.batch_frames, frames_dev.shape[0])
+
+    def run(fr):
+        pv = []
+        for c0 in range(0, fr.shape[0], 64):
+            x = fr[c0:c0 + 64].flip(-1).permute(0, 3, 1, 2)                  # cv2 BGR -> RGB, NCHW
+            pv.append(proc(images=x, return_tensors="pt")["pixel_values"].to(dev, torch.bfloat16))
+        with torch.no_grad():
+            out = model(pixel_values=torch.cat(pv))
+        return out.last_hidden_state.float().mean(dim=1)
+
+    run(frames_dev[:n])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in range(batches):
+        s = (b * n) % max(1, frames_dev.shape[0] - n + 1)
+        emb = run(frames_dev[s:s + n])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    # the model alone (pixel_values resident), to separate the processor's share
+    pvals = torch.randn(n, 3, args.resize, args.resize, device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        model(pixel_values=pvals)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(batches):
+            model(pixel_values=pvals)
+        e1.record()
+    torch.cuda.synchronize(dev)
+    ms_model = e0.elapsed_time(e1)
+    del model, pvals
+    torch.cuda.empty_cache()
+    return {"value": batches * n / (ms / 1e3), "unit": UNIT, "model_only_frames_per_s": batches * n / (ms_model / 1e3),
+            "kind": "stock HF DINOv3ViTImageProcessor on CUDA tensors + DINOv3ViTModel bf16 (SDPA), token mean: the reference's own "
+                    "path with CUDA present (main.py:33-36,107-113), batched",
+            "batch": n, "sample": f"{batches} batches of {n} frames of {args.height}x{args.width} uint8 (resident in HBM)",
+            "embedding_dim": int(emb.shape[1])}
+
+
+def which_config(args, world) -> str:
+    """BASELINE.json `configs` entry this run corresponds to."""
+    if args.model == "vitl16":
+        return "configs[4]"
+    if args.resize != 224:
+        return "configs[2]"
+    if args.height == args.resize and args.width == args.resize and args.clips * world >= 1024:
+        return "configs[3]"          # 1 024 clips of model-sized frames sharded over the ranks + row-sharded gallery re-ID
+    return "configs[1]"
+
+
 def workload_config(args, world):
     from vision_sam3_yolo_lameless_b200.synthetic import vit_flops_per_frame
 
     tokens = (args.resize // 16) ** 2 + 5
-    which = "configs[4]" if args.model == "vitl16" else "configs[1]" if args.resize == 224 else "configs[2]"
+    which = which_config(args, world)
     name = "ViT-L/16" if args.model == "vitl16" else "ViT-B/16"
     gf = vit_flops_per_frame(args.model, tokens, tokens - 5) / 1e9
     step_bytes = args.clips * args.frames_per_clip * args.height * args.width * 3
     return {"workload": f"{which}: {name} embedding of {args.clips} synthetic clips x {args.frames_per_clip} frames "
-                        f"({args.clips * args.frames_per_clip} frames) decoded as {args.width}x{args.height} uint8 incl. fused "
-                        f"resize/normalize, + cosine top-5 re-ID against a {args.gallery_rows}-row gallery; per rank",
+                        f"({args.clips * args.frames_per_clip} frames) per rank ({args.clips * world} clips in all) decoded as "
+                        f"{args.width}x{args.height} uint8 incl. fused resize/normalize, + cosine top-5 re-ID against a "
+                        f"{args.gallery_rows}-row gallery (row-sharded over {world} rank{'s' if world > 1 else ''})",
             "clips_per_rank": args.clips, "frames_per_clip": args.frames_per_clip,
             "frame_hw": [args.height, args.width], "gallery_rows": args.gallery_rows, "top_k": 5,
             "batch_frames": args.batch_frames, "model_input": args.resize,
@@ -283,7 +355,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             m = min(resident, frames_total - s)
             eng.embed_frames(frames_dev[:m], bgr=True, out=frame_emb[s:s + m])
         _, unit = eng.pool_clips(frame_emb, offsets)
-        return reid.search(unit, k=5)
+        return (unit,) + tuple(reid.search(unit, k=5))
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -301,7 +373,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        scores, idx = step_resident()
+        unit, scores, idx = step_resident()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -312,6 +384,27 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = t.item()
     value = world * frames_total * args.steps / (ms_max / 1e3)
+
+    # ---- sharded check (N > 1; outside the timed region): all queries against the WHOLE gallery on every rank == sharded result ----
+    sharded_check = None
+    if world > 1:
+        counts = [shard_range(args.gallery_rows, r, world) for r in range(world)]
+        rows_max = max(b - a for a, b in counts)
+        padded = torch.zeros((rows_max, cfg.hidden), dtype=torch.bfloat16, device=dev)
+        padded[: hi - lo] = shard
+        allg = torch.empty((world * rows_max, cfg.hidden), dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(allg, padded)
+        whole = torch.cat([allg[r * rows_max: r * rows_max + (b - a)] for r, (a, b) in enumerate(counts)], dim=0).contiguous()
+        all_q = reid.gather_queries(unit)
+        ws, wi = eng.gallery_topk(all_q, whole, k=5)
+        same = torch.equal(wi, idx) and torch.equal(ws, scores)
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_check = "ok" if flag.item() == 1 else "MISMATCH"
+        if sharded_check != "ok":
+            bad = int((wi != idx).any(dim=1).sum().item())
+            print(f"[rank {rank}] sharded top-5 differs from the whole-gallery scan on {bad} of {idx.shape[0]} queries", file=sys.stderr)
+        del allg, whole, padded
 
     # ---- instrumented step: per-kernel CUDA-event durations (roofline) ----------------------------------------------
     kernels = {}
@@ -324,9 +417,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     sync_all()
     if rank == 0:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)     # a kernel timed inside a long step -> sustained figure
+        tf_peak = peaks.get("bf16_tflops_sustained", 1590.0)     # a kernel timed inside a long step -> sustained figure
+        tf_burst = peaks.get("bf16_tflops", 1590.0)              # fallbacks: B200_PROFILING.md (6.65 TB/s, 1.59 PFLOP/s)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        which = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
+        which = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "of fallback (B200_PROFILING.md)"
         tot = sum(r[1] for r in recs) or 1.0
         for name, ms_k, work in recs:
             k = kernels.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
@@ -363,7 +457,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         fwd_names = [n for n in kernels if n in _lib.FLOP_KERNELS or n in ("row_stats", "layernorm", "final_norm_mean", "fill_prefix")]
         fwd_ms = sum(kernels[n]["ms"] for n in fwd_names)
         fwd_tf = frames_total * cfg.flops_per_frame(grid, grid) / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
-        roofline["vit_forward"] = {"tflops": fwd_tf, "frac_of_burst_peak": fwd_tf / peaks.get("bf16_tflops", 1623.1) if fwd_tf else None,
+        roofline["vit_forward"] = {"tflops": fwd_tf, "frac_of_burst_peak": fwd_tf / tf_burst if fwd_tf else None,
                                    "frac_of_sustained_peak": fwd_tf / tf_peak if fwd_tf else None, "ms": fwd_ms,
                                    "how": "sum of the CUDA-event durations of the forward's launches in the instrumented step"}
         if args.breakdown:
@@ -375,8 +469,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ---- e2e: reference-facing API, frames in pinned host memory --------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        pipe = DINOv3Pipeline(eng, results_dir=Path("/tmp/cre_bench_results"), gallery_backend="gpu")
-        pipe.gallery.load(list(range(lo, hi)), shard)
+        pipe = DINOv3Pipeline(eng, results_dir=Path("/tmp/cre_bench_results"))
         distinct = min(clips, 4)
         host = torch.empty((distinct, fpc, h, w, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(frames_dev[: distinct * fpc].view(distinct, fpc, h, w, 3) if resident >= distinct * fpc
@@ -386,7 +479,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         offs_host = np.arange(0, frames_total + 1, fpc, dtype=np.int32)
 
         def step_e2e():
-            mean, unit, sc, ix = pipe.embed_clips(clip_list, offs_host, bgr=True, top_k=5)   # returns numpy (D2H inside)
+            # the sharded search (both NCCL all-gathers + merge at N > 1) is part of the call; returns numpy (D2H inside)
+            mean, unit_h, sc, ix = pipe.embed_clips(clip_list, offs_host, bgr=True, top_k=5, sharded=reid)
             return mean, sc, ix
 
         e2e_steps = max(1, min(args.steps, 3))
@@ -405,13 +499,42 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         d2h = int(mean.nbytes * 2 + sc.nbytes + ix.nbytes)
+        # ---- H2D-only probe: the same pinned buffers, chunking, streams and events, no kernels -> this box's copy ceiling ----
+        eng.embed_host_frames(clip_list, bgr=True, copy_only=True)
+        sync_all()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(e2e_steps):
+            eng.embed_host_frames(clip_list, bgr=True, copy_only=True)
+        p1.record()
+        sync_all()
+        probe_gbs = frames_total * per * e2e_steps / (p0.elapsed_time(p1) / 1e3) / 1e9
+        pg = torch.tensor([probe_gbs], dtype=torch.float64, device=dev)
+        allp = [torch.zeros_like(pg) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allp, pg)
+        else:
+            allp = [pg]
+        h2d_only = [round(float(x.item()), 2) for x in allp]
         e2e = {"value": world * frames_total * e2e_steps / (te.item() / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(frames_total * per), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "DINOv3Pipeline.embed_clips(list of pinned host clips) -> numpy clip embeddings + top-5",
+               "api": "DINOv3Pipeline.embed_clips(list of pinned host clips, sharded=ShardedReID) -> numpy clip embeddings + top-5",
                "host_affinity": numa,
-               "note": f"{distinct} distinct pinned clips cycled to form the {clips}-clip batch (all bytes are copied every step); "
-                       "re-ID in e2e is against the rank-local gallery shard"}
+               "h2d_only_gbs": h2d_only,
+               "h2d_only_frames_per_s": sum(h2d_only) * 1e9 / per,
+               "note": f"{distinct} distinct pinned clips cycled to form the {clips}-clip batch (all bytes are copied every step); re-ID "
+                       "runs against the row-sharded gallery (query all-gather, per-shard scan, candidate all-gather + merge inside the "
+                       "timed call).  h2d_only_gbs = per-rank rate of the same copies with no kernels launched (all ranks copying at "
+                       "once); h2d_only_frames_per_s = the e2e ceiling those rates imply"}
         del host
+
+    # ---- GPU comparison point (N = 1): the stock HF path on this GPU, bounded sample --------------------------------
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_base = hf_gpu_sample(args, dev, frames_dev, args.gpu_baseline_batches)
+        except Exception as e:        # noqa: BLE001 -- a comparison point must never take the bench line down
+            gpu_base = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         line = {
@@ -420,16 +543,38 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
             "clips_per_s": value / fpc,
             "vit_tflops": value * cfg.flops_per_frame(grid, grid) / 1e12,
-            "vit_frac_of_bf16_burst_peak": value / world * cfg.flops_per_frame(grid, grid) / 1e12 / 1623.1,
+            "vit_frac_of_bf16_burst_peak": value / world * cfg.flops_per_frame(grid, grid) / 1e12 / tf_burst,
             "resident_frames": resident,
             "roofline": roofline, "kernels": {n: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in k.items()}
                                               for n, k in kernels.items()},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "gpu_baseline": gpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if sharded_check is not None:
+            line["sharded_check"] = sharded_check
         emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_hf_gpu(args, rank: int, local_rank: int):
+    """`--impl hf_gpu`: the stock HF path on ONE GPU (rank 0), every step = one batch of --batch-frames resident frames."""
+    if rank != 0:
+        return
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = args.batch_frames
+    gen = torch.Generator(device=dev).manual_seed(1000)
+    frames_dev = torch.randint(0, 256, (n, args.height, args.width, 3), dtype=torch.uint8, device=dev, generator=gen)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    g = hf_gpu_sample(args, dev, frames_dev, max(1, args.steps))
+    clocks = sampler.stop()
+    emit_json({"impl": "hf_gpu", "metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 1,
+               "ms_per_step": n / g["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "data": "synthetic", "config": workload_config(args, 1), "gpu_baseline": g, "gpu_launches": 0, "clocks": clocks})
 
 
 _JSON_FD = None
@@ -462,6 +607,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "hf_gpu":
+        run_hf_gpu(args, rank, local_rank)
         return
     if world != args.gpus:
         if world == 1 and args.gpus > 1:

@@ -223,7 +223,8 @@ int32_t cre_set_cta_group(int32_t cta_group);
  * T <= 256, default; 0 = general kernel), "ln_fold" (1 = LayerNorm folded into the GEMMs, default; 0 = separate LayerNorm
  * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use CRE_EPI_RESID_LN3), "attention_split" (1 = split-S
  * kernel for 160 < T <= 208, default), "attention_poly" (0 | 1 | 2: share of that kernel's exponentials on the FMA pipe),
- * "attention_safe_order".  Every setting gives results inside the parity tolerances.  Unknown keys return -1. */
+ * "attention_split_mode" (bit 0: direct global stores of O, bit 1: PV of the second key half in one piece), "attention_split_delay"
+ * (SM cycles by which the second query-tile group of that kernel trails the first).  Every setting gives results inside the parity tolerances.  Unknown keys return -1. */
 int32_t cre_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus

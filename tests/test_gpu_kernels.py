@@ -379,7 +379,39 @@ def test_gallery_topk_empty_and_k_range(engine_small):
         s, i, dump = eng.gallery_topk(qv, gb, k=k, dump_scores=True)
         assert (i.cpu().numpy() == reid_ref.topk_rule(dump.cpu().numpy(), k)[1]).all()
     with pytest.raises(_lib.CreError):
-        eng.gallery_topk(qv, gb, k=9)
+        eng.gallery_topk(qv, gb, k=257)                    # > CRE_TOPK_LIMIT
+
+
+@pytest.mark.parametrize("q,n,k", [(1, 30011, 20), (2, 5000, 64), (33, 10007, 12), (130, 3000, 9), (64, 100000, 17), (3, 40, 256),
+                                   (1, 300, 256), (70, 700, 100)])
+def test_gallery_topk_beyond_one_pass(engine_small, q, n, k):
+    """k > 8 = ceil(k / 8) passes over the shard, each admitting only candidates that rank after the previous pass's last entry
+    (include/cre.h): both scan forms, planted exact ties that straddle a pass boundary, k > rows.  Bit-exact against the oracle's
+    (score desc, index asc) rule applied to the GPU's own score matrix."""
+    eng, dev = engine_small, engine_small.device
+    gen = torch.Generator(device=dev).manual_seed(q * 1000 + k)
+    g = torch.nn.functional.normalize(torch.randn(n, 768, device=dev, generator=gen), dim=1)
+    qv = torch.nn.functional.normalize(torch.randn(q, 768, device=dev, generator=gen), dim=1)
+    if n > 30:                                             # 12 identical rows: ties across the first pass boundary (entries 7 | 8)
+        dup = torch.randperm(n, device=dev, generator=gen)[:12]
+        g[dup] = g[dup[0]].clone()
+        qv[0] = torch.nn.functional.normalize(g[dup[0]] + 0.02 * torch.randn(768, device=dev, generator=gen), dim=0)
+    gb = g.to(torch.bfloat16).contiguous()
+    s, i, dump = eng.gallery_topk(qv, gb, k=k, row_base=50, dump_scores=True)
+    kk = min(k, n)
+    ref_top, ref_idx = reid_ref.topk_rule(dump.cpu().numpy(), kk, row_base=50)
+    assert (i.cpu().numpy()[:, :kk] == ref_idx).all() and (s.cpu().numpy()[:, :kk] == ref_top).all()
+    if kk < k:
+        assert (i.cpu().numpy()[:, kk:] == 0x7FFFFFFF).all() and np.isneginf(s.cpu().numpy()[:, kk:]).all()
+    if n > 30:
+        m = min(k, 12)                                     # the tied rows lead, in ascending index, whatever pass they fall in
+        assert i[0, :m].tolist() == sorted((dup + 50).tolist())[:m]
+    # sharded: per-shard top-k + merge == the whole scan
+    from vision_sam3_yolo_lameless_b200.sharded import shard_range
+    if 4 * k <= 4096 and n >= 8:
+        parts = [eng.gallery_topk(qv, gb[lo:hi].contiguous(), k=k, row_base=50 + lo) for lo, hi in (shard_range(n, r, 4) for r in range(4))]
+        ms, mi = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert torch.equal(mi, i) and torch.equal(ms, s)
 
 
 def test_sharded_topk_merge_equals_whole(engine_small):
@@ -412,3 +444,16 @@ def test_gallery_update_row(engine_small):
     np.testing.assert_allclose(gal[2].float().cpu().numpy(), reid_ref.momentum_update(old, new, 0.9), atol=1e-3)   # bf16 store: half-ulp 4.9e-4 at |x| in [0.125, 0.25)
     eng.gallery_update_row(gal, 4, uq, 0.0)
     np.testing.assert_allclose(gal[4].float().cpu().numpy(), reid_ref.l2_normalise(new), atol=1e-3)
+    # with an fp32 master copy the blend reads and writes IT (what the reference keeps in Qdrant, matcher.py:267-301): 50 updates
+    # stay within fp32 rounding of the fp64 recurrence, and the bf16 row is always the rounding of the master row
+    master = torch.nn.functional.normalize(torch.randn(6, 768, device=dev), dim=1)
+    gal2 = master.to(torch.bfloat16)
+    want = master[3].cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        new = rng.standard_normal(768)
+        eng.gallery_update_row(gal2, 3, torch.from_numpy(reid_ref.l2_normalise(new).astype(np.float32)).to(dev), 0.9, master=master)
+        want = reid_ref.momentum_update(want, new, 0.9)
+    np.testing.assert_allclose(master[3].cpu().numpy(), want, atol=2e-6)
+    assert torch.equal(gal2[3], master[3].to(torch.bfloat16))
+    assert torch.equal(gal2[[0, 1, 2, 4, 5]], master[[0, 1, 2, 4, 5]].to(torch.bfloat16)), "other rows untouched"

@@ -12,10 +12,12 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 VARIANTS = {
     "single_S": {"attention_split": 0},
-    "split_poly25": {"attention_split": 1, "attention_poly": 1},
-    "split_poly0": {"attention_split": 1, "attention_poly": 0},
-    "split_poly50": {"attention_split": 1, "attention_poly": 2},
-    "split_poly25_safe": {"attention_split": 1, "attention_poly": 1, "attention_safe_order": 1},
+    "split_delay0": {"attention_split_delay": 0},
+    "split_delay2400": {"attention_split_delay": 2400},
+    "split_delay3200": {"attention_split_delay": 3200},
+    "split_delay4000": {"attention_split_delay": 4000},
+    "split_delay3200_poly0": {"attention_split_delay": 3200, "attention_poly": 0},
+    "split_delay3200_pv1": {"attention_split_delay": 3200, "attention_split_mode": 2},
 }
 
 
@@ -43,14 +45,14 @@ def one(name):
         ref = (att @ vb.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(n * t, d)
         err = (out.float() - ref).abs()
         per_unit = err.reshape(n, t, heads, 64).amax(dim=(1, 3))
-        print(f"{name:18s} n={n:3d}: rel_err {err.max().item() / ref.abs().max().item():.3e}  nonfinite {(~torch.isfinite(out.float())).sum().item()}"
+        print(f"{name:22s} n={n:3d}: rel_err {err.max().item() / ref.abs().max().item():.3e}  nonfinite {(~torch.isfinite(out.float())).sum().item()}"
               f"  worst units {[tuple(int(x) for x in divmod(int(i), heads)) for i in per_unit.flatten().topk(3).indices]}", flush=True)
     for n in (600, 1130):
         qkv = (torch.randn(n * t, 3 * d, device=eng.device) * 0.5).to(torch.bfloat16)
         best = min(timeit(lambda: eng.attention(qkv, n, t, heads), iters=20) for _ in range(3))
         fl = 4.0 * t * t * 64 * heads * n
         gb = n * t * (3 * d + d) * 2 / 1e9
-        print(f"{name:18s} n={n:4d}: {best * 1e3:7.1f} us  {fl / best / 1e9:6.1f} TFLOP/s  {gb / best * 1e3:6.0f} GB/s (q,k,v read + out write)", flush=True)
+        print(f"{name:22s} n={n:4d}: {best * 1e3:7.1f} us  {fl / best / 1e9:6.1f} TFLOP/s  {gb / best * 1e3:6.0f} GB/s (q,k,v read + out write)", flush=True)
 
 
 if __name__ == "__main__":

@@ -879,8 +879,13 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_attention_poly(value);
         return 0;
     }
-    if (strcmp(key, "attention_safe_order") == 0) {
-        set_attention_safe_order(value);
+    if (strcmp(key, "attention_split_mode") == 0) {
+        set_attention_split_mode(value);
+        return 0;
+    }
+    if (strcmp(key, "attention_split_delay") == 0) {
+        CRE_REQUIRE(value >= 0 && value <= 100000, "set_tuning: attention_split_delay=%d cycles", value);
+        set_attention_split_delay(value);
         return 0;
     }
     if (strcmp(key, "preprocess_tma") == 0) {
@@ -912,6 +917,15 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     set_error("set_tuning: unknown key '%s'", key);
     return -1;
 }
+
+#ifdef CRE_ATTN_TRACE
+// tracing builds only (tools/attn_trace.py): a device buffer of 12 x 256 uint64 that CTA 0 of the split-S attention kernel fills
+// with (event << 56 | clock64) records; not part of include/cre.h
+int32_t cre_debug_set_attention_trace(void* buf_dev) {
+    set_attention_trace(static_cast<unsigned long long*>(buf_dev));
+    return 0;
+}
+#endif
 
 // 1 = one CTA per tile (cta_group::1), 2 = CTA pairs (cta_group::2) for the ViT GEMMs
 int32_t cre_set_cta_group(int32_t cg) {

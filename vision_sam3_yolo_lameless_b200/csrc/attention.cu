@@ -675,26 +675,32 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // The fast path above keeps two softmax chains per SM busy, but each chain is strictly serial -- S MMA -> softmax -> PV MMA ->
 // O read-back -- and TMEM (2 x (208 S + 64 O) > 512 columns) leaves no room to prefetch the next S.  The round-1 source-level
 // profile put 45 % of the softmax warps' time in their two waits for the tensor pipe.  Here the 208 keys of a unit are split
-// into halves h0 = keys [0, 128) and h1 = keys [128, KB), and consecutive units visit them in ALTERNATING order, which makes
-// every MMA except the last half's PV run under the exponentials of the other half:
+// into halves h0 = keys [0, 128) and h1 = keys [128, KB), which lets most of the tensor work run under the exponentials:
 //
-//   TMEM columns of group g (base 256 g):   [0, 128) S_h0   (P_h0 = bf16 pairs in [0, 64), written behind the read pointer)
+//   TMEM columns of group g (base 256 g):   [0, 128) S_h0   (P_h0 = bf16 pairs in [0, 64), written behind the read pointer;
+//                                                            O in [64, 128) once h0 has been exponentiated)
 //                                           [128, 128 + 16 n1) S_h1,   P_h1 in [256 - 8 n1, 256)   (n1 = (KB - 128) / 16 <= 5)
-//   O of an even unit lives in [64, 128)  (the part of h0's region that is free once h0 has been exponentiated),
-//   O of an odd unit in [128, 192)        (h1's region).
 //
-//   even unit i: softmax h0, then h1;  odd unit: softmax h1, then h0.  Per group the issuer runs, in program order,
-//       S_first(i)            straight behind PV_last(i - 1): that region was last READ by softmax_last(i - 1) (p_full) and holds
-//                             no live P (P_h0 is consumed by the in-order PV in front of it, P_h1 has its own columns)
-//       S_last(i)             after O(i - 1), which overlays that region, has been drained (tmem_free)
-//       PV_first(i)           after p_full(first); runs under softmax_last(i)
-//       PV_last(i), commit    after p_full(last): the only tensor work a softmax warp ever waits for
-//   so S_first(i + 1) is already in TMEM when the softmax warps come back from reading O(i).
+//   per group the issuer runs, in program order,
+//       S_h0(i)              after O(i - 1), which overlays h0's region, has been drained (tmem_free) -- the softmax warps are busy
+//                            scaling / storing O(i - 1) meanwhile
+//       PV_h0(i)             after the LAST block of P_h0 is published (O overlays S_h0: nothing may be written before h0 is read);
+//                            runs under softmax h1(i)
+//       PV_h1(i) by block    each 32- / 16-key block of P_h1 as soon as it is published: when the softmax warps finish, only the
+//                            last block's MMA is outstanding; commit -> o_full
+//       S_h1(i + 1)          straight behind it: h1's region was last READ by softmax h1(i) and P_h1 has its own columns
+//   so the order of the halves, the stabiliser (maximum over keys [0, 32)) and therefore every output bit are independent of where
+//   in a batch a frame sits.
 //
 // One issuer warp per group (blocking mbarrier waits instead of a polling loop over both groups), rows are exponentiated with
-// no clamp (overflow is caught by the row-sum flag, see "Exactness"), 32-key TMEM loads / 16-column stores.
+// no clamp (overflow is caught by the row-sum flag, see "Exactness"), 32-key TMEM loads / 16-column stores, O leaves through a
+// per-warp staging tile and a TMA store (3-D map: the rows of the second query tile beyond the frame's last token are clipped).
 // =====================================================================================================================
-constexpr int kFsThreads = 384;   // warp 0 TMA, warps 1-2 MMA issuers (group 0 / 1), warp 3 TMEM allocator, warps 4-11 softmax
+// warp 0 TMA producer, warp 2 TMEM allocator, warps 4-11 softmax (group = (warp - 4) / 4, TMEM lane quarter = warp % 4), MMA issuers =
+// warp 3 (group 0) and warp 11 (group 1).  A warp's scheduler is warp % 4: the issuers, which wake up ~20 times per unit, sit on
+// scheduler 3 -- the one with a single softmax warp (group 1's fourth quarter, query rows 224.., is never populated for T <= 208;
+// its warp is the issuer instead).  On schedulers 1 / 2 they cost the softmax warps there ~12 % (timeline trace, profiles/r02c_*).
+constexpr int kFsThreads = 384;
 constexpr int kFsTileBytes = 208 * 128;                     // Q, K or V of one unit: <= 208 rows x 64 bf16
 constexpr int kFsStageBytes = 3 * kFsTileBytes;             // 78 KB
 constexpr int kFsOutOff = 2 * kFsStageBytes;                // eight 32-row x 128-byte O staging tiles (one per softmax warp)
@@ -721,6 +727,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
 
 // NK (16 | 32) scores of one row -> exponentials -> running sum + packed bf16 pairs.  POLY: bit i set = pair i of every 8 runs on
 // the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0 (and is not computed).
+// neg_m2 includes + log2(1 + 2^-9): e = 2^(s log2e - m log2e) (1 + 2^-9), so that truncating e to bf16 rounds 2^(...) half-up.
 template <int NK, uint32_t POLY, bool MASK>
 __device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t (&pk)[NK / 2], int nvalid, uint64_t l2e2,
                                               uint64_t neg_m2, uint64_t& l2) {
@@ -745,7 +752,7 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t 
             if (j + 1 >= nvalid) e1 = 0.0f;
         }
         l2 = add2(l2, pack2(e0, e1));
-        pk[j >> 1] = pack_bf16x2_pos(e0, e1);
+        pk[j >> 1] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632u);     // truncation; the bias is in the exponent
     }
 }
 
@@ -754,8 +761,24 @@ struct FsParams {
     int k_col0, v_col0;
     int* any_flag;
     int* unit_flags;
-    int safe_order;    // 1: never issue an S MMA over P columns a queued PV MMA still reads (do not rely on in-order execution)
+    __nv_bfloat16* out;     // mode bit 0 only
+    int ld_out;
+    int mode;               // tuning (results identical): bit 0 = O through direct global stores, bit 1 = PV_h1 in one piece
+    int delay_cycles;       // group 1 starts this many SM cycles (about half a unit) after group 0: the two softmax warps of a
+                            // scheduler then sit in different phases -- one exponentiates while the other waits for its last PV
+                            // and drains O -- instead of fighting for the MUFU in lockstep and idling together (measured:
+                            // 333 -> 305 us per 1130-frame launch)
+    unsigned long long* trace;   // -DCRE_ATTN_TRACE builds only: [12 warps][256] (event id << 56 | clock) of CTA 0
 };
+#ifdef CRE_ATTN_TRACE
+#define FS_TRACE(ev)                                                                                   \
+    do {                                                                                               \
+        if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_n < 256)                          \
+            p.trace[warp * 256 + tr_n++] = (static_cast<unsigned long long>(ev) << 56) | (clock64() & 0x00ffffffffffffffull); \
+    } while (0)
+#else
+#define FS_TRACE(ev) do { } while (0)
+#endif
 
 template <uint32_t POLY>
 __global__ void __launch_bounds__(kFsThreads, 1)
@@ -766,17 +789,22 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
     auto s_k = [&](int s) { return smem_base + s * kFsStageBytes + kFsTileBytes; };
     auto s_v = [&](int s) { return smem_base + s * kFsStageBytes + 2 * kFsTileBytes; };
     const uint32_t bar_base = smem_base + kFsBarOff;
-    auto kv_full = [&](int s) { return bar_base + 8u * s; };
-    auto kv_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+    // Two rings of two slots each: Q + K (needed by the S MMAs only: free again ~1 000 cycles into the unit) and V (needed by the
+    // PV MMAs: free at the end of the unit).  Q / K of unit i + 2 are therefore in flight almost two units ahead of their use.
+    auto qk_full = [&](int s) { return bar_base + 8u * s; };
+    auto qk_empty = [&](int s) { return bar_base + 8u * (2 + s); };
     auto s_full = [&](int g, int h) { return bar_base + 8u * (4 + 2 * g + h); };
     auto o_full = [&](int g) { return bar_base + 8u * (8 + g); };
     auto tmem_free = [&](int g) { return bar_base + 8u * (10 + g); };
-    // P is handed over block by block (h0: four 32-key blocks; h1: up to three), one barrier per block and one phase per unit
-    auto p_full = [&](int g, int h, int b) { return bar_base + 8u * (12 + 7 * g + 4 * h + b); };
+    // P_h0 is handed over in one piece (O overlays S_h0: no PV before all of h0 is read), P_h1 block by block (up to three)
+    auto p_full = [&](int g, int h, int b) { return bar_base + 8u * (12 + 4 * g + (h == 0 ? 0 : 1 + b)); };
+    auto v_full = [&](int s) { return bar_base + 8u * (20 + s); };
+    auto v_empty = [&](int s) { return bar_base + 8u * (22 + s); };
     const uint32_t tmem_slot = bar_base + 8u * 26;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    [[maybe_unused]] int tr_n = 0;
     const int T = p.t, KB = p.kb;
     const int n1 = (KB - 128) >> 4;                    // 16-key steps of the second half (3..5)
     const int nf1 = (T - 128) >> 4, rem = T & 15;      // its full steps (2..5), keys in its partial step
@@ -792,16 +820,19 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(kv_full(i), 1);
-            mbar_init(kv_empty(i), 2);                 // one tcgen05.commit per issuer
+            mbar_init(qk_full(i), 1);
+            mbar_init(qk_empty(i), 2);                 // one tcgen05.commit per issuer
+            mbar_init(v_full(i), 1);
+            mbar_init(v_empty(i), 2);
             mbar_init(s_full(i, 0), 1);
             mbar_init(s_full(i, 1), 1);
             mbar_init(o_full(i), 1);
-            mbar_init(tmem_free(i), 4);
-            for (int b = 0; b < 7; ++b) mbar_init(p_full(i, 0, b), 4);
+            const int active = i == 0 ? 4 : (T - 128 + 31) >> 5;     // softmax warps of the group that hold query rows
+            mbar_init(tmem_free(i), active);
+            for (int b = 0; b < 4; ++b) mbar_init(p_full(i, 0, 0) + 8u * b, active);
         }
         fence_barrier_init();
-    } else if (warp == 3) {
+    } else if (warp == 2) {
         tmem_alloc<1>(tmem_slot, 512);
     }
     tc_fence_before();
@@ -817,65 +848,82 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
         for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
             const int s = i & 1;
             const int frame = u / p.heads, head = u - frame * p.heads;
-            mbar_wait(kv_empty(s), ((i >> 1) & 1) ^ 1u);
-            mbar_arrive_expect_tx(kv_full(s), 3 * KB * 128);
-            tma_load_2d<1>(&tmap_kv, kv_full(s), s_q(s), head * 64, frame * T, kEvictFirst);
-            tma_load_2d<1>(&tmap_kv, kv_full(s), s_k(s), p.k_col0 + head * 64, frame * T, kEvictFirst);
-            tma_load_2d<1>(&tmap_kv, kv_full(s), s_v(s), p.v_col0 + head * 64, frame * T, kEvictFirst);
+            mbar_wait(qk_empty(s), ((i >> 1) & 1) ^ 1u);
+            mbar_arrive_expect_tx(qk_full(s), 2 * KB * 128);
+            tma_load_2d<1>(&tmap_kv, qk_full(s), s_q(s), head * 64, frame * T, kEvictFirst);
+            tma_load_2d<1>(&tmap_kv, qk_full(s), s_k(s), p.k_col0 + head * 64, frame * T, kEvictFirst);
+            mbar_wait(v_empty(s), ((i >> 1) & 1) ^ 1u);
+            mbar_arrive_expect_tx(v_full(s), KB * 128);
+            tma_load_2d<1>(&tmap_kv, v_full(s), s_v(s), p.v_col0 + head * 64, frame * T, kEvictFirst);
         }
-    } else if ((warp == 1 || warp == 2) && lane == 0) {
+    } else if (warp == 3 || warp == 11) {
         // =============================== MMA issuer of group g ===============================
-        const int g = warp - 1;
+        if (lane != 0) goto fs_done;
+        const int g = warp == 3 ? 0 : 1;
         const uint32_t gb = tmem_base + g * 256;
         const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, 16 * n1);
         const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+        const uint32_t o_col = gb + 64u;
+        auto issue_s = [&](int s, int h) {
+            const uint64_t dq = umma_desc_k_sw128(s_q(s) + g * (128 * 128));
+            const uint64_t dk = umma_desc_k_sw128(s_k(s) + h * (128 * 128));
+            const uint32_t idesc = h == 0 ? idesc_s0 : idesc_s1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16<1>(gb + h * 128, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+            umma_commit<1>(s_full(g, h));
+        };
         int i = 0;
         for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
             const int s = i & 1;
             const uint32_t ph = i & 1;
-            const int first = i & 1, last = first ^ 1;           // which half goes first in this unit
-            const uint32_t o_col = gb + (first == 0 ? 64u : 128u);
-            const uint64_t dq = umma_desc_k_sw128(s_q(s) + g * (128 * 128));
-            auto issue_s = [&](int h) {
-                const uint64_t dk = umma_desc_k_sw128(s_k(s) + h * (128 * 128));
-                const uint32_t idesc = h == 0 ? idesc_s0 : idesc_s1;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16<1>(gb + h * 128, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-                umma_commit<1>(s_full(g, h));
-            };
-            // O (+)= P_h V_h, each block of P as soon as the softmax warps have published it
-            auto issue_pv = [&](int h, bool fresh) {
-                const uint32_t pa = gb + (h == 0 ? 0u : p1_col);
-                const int nb = h == 0 ? 4 : nb1;
-                for (int b = 0; b < nb; ++b) {
-                    const int k0 = h == 0 ? 2 * b : (b == 0 ? 0 : (b == 1 ? 2 : c3));
-                    const int k1 = h == 0 ? k0 + 2 : (b == 0 ? 2 : (b == 1 ? (wide ? 4 : 3) : c3 + 1));
-                    mbar_wait(p_full(g, h, b), ph);
-                    tc_fence_after();
-                    for (int ks = k0; ks < k1; ++ks)
-                        umma_bf16_ts(o_col, pa + 8 * ks, umma_desc_mn_sw128(s_v(s) + (h * 8 + ks) * 2048), idesc_o, !(fresh && ks == 0));
+            // S_h0 first: it is what the softmax warps wait for (they are scaling / storing O(i - 1) meanwhile); S_h1 -- not needed
+            // for another ~2 000 cycles -- goes right behind it
+            mbar_wait(qk_full(s), (i >> 1) & 1);
+            if (i == 0 && g == 1) {                             // group 1 trails group 0 (see FsParams::delay_cycles)
+                const long long t_go = clock64() + p.delay_cycles;
+                while (clock64() < t_go) __nanosleep(100);
+            }
+            FS_TRACE(1);
+            mbar_wait(tmem_free(g), ph ^ 1u);                   // O of the previous unit (it overlays S_h0) is in registers
+            tc_fence_after();
+            FS_TRACE(2);
+            issue_s(s, 0);
+            FS_TRACE(3);
+            issue_s(s, 1);                                      // h1's region was last read by softmax h1(i - 1); P_h1 has its own columns
+            umma_commit<1>(qk_empty(s));                        // Q / K slot free once both S MMA groups have retired
+            // O = P_h0 V_h0 once ALL of h0 has been exponentiated (O overlays S_h0's columns [64, 128))
+            mbar_wait(v_full(s), (i >> 1) & 1);
+            mbar_wait(p_full(g, 0, 0), ph);
+            tc_fence_after();
+            FS_TRACE(4);
+            for (int ks = 0; ks < 8; ++ks)
+                umma_bf16_ts(o_col, gb + 8 * ks, umma_desc_mn_sw128(s_v(s) + ks * 2048), idesc_o, ks != 0);
+            FS_TRACE(5);
+            // O += P_h1 V_h1, block by block as the softmax warps publish them
+            if (p.mode & 2)
+                for (int b = 0; b < nb1; ++b) mbar_wait(p_full(g, 1, b), ph);
+            for (int b = 0; b < nb1; ++b) {
+                const int k0 = b == 0 ? 0 : (b == 1 ? 2 : c3);
+                const int k1 = b == 0 ? 2 : (b == 1 ? (wide ? 4 : 3) : c3 + 1);
+                FS_TRACE(11);
+                if (!(p.mode & 2)) mbar_wait(p_full(g, 1, b), ph);
+                FS_TRACE(12);
+                tc_fence_after();
+                FS_TRACE(6 + b);
+                for (int ks = k0; ks < k1; ++ks) {
+                    umma_bf16_ts(o_col, gb + p1_col + 8 * ks, umma_desc_mn_sw128(s_v(s) + (8 + ks) * 2048), idesc_o, 1u);
+                    FS_TRACE(13);
                 }
-            };
-            mbar_wait(kv_full(s), (i >> 1) & 1);
-            // S_h0 overwrites the P_h0 columns the PV MMAs queued right in front of it read: the tensor pipe executes one thread's
-            // MMAs in issue order, so no wait is needed (safe_order waits for that PV to retire instead)
-            if (p.safe_order && first == 0) mbar_wait(o_full(g), ph ^ 1u);
-            tc_fence_after();
-            issue_s(first);
-            mbar_wait(tmem_free(g), ph ^ 1u);                   // O of the previous unit (it overlays this region) is in registers
-            tc_fence_after();
-            issue_s(last);
-            issue_pv(first, true);
-            issue_pv(last, false);
+            }
             umma_commit<1>(o_full(g));
-            umma_commit<1>(kv_empty(s));                        // this group is done with the smem stage
+            FS_TRACE(9);
+            umma_commit<1>(v_empty(s));                         // this group is done with the V slot
         }
-    } else if (warp >= 4) {
-        // =============================== softmax groups ===============================
+    } else if (warp >= 4 && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < T) {
+        // =============================== softmax groups (warps that hold query rows) ===============================
         const int g = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = g * 128 + quarter * 32 + lane;          // query token inside the frame
-        const bool warp_active = g * 128 + quarter * 32 < T;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 256;
         constexpr float kLog2e = 1.4426950408889634f;
         const uint64_t l2e2 = pack2(kLog2e, kLog2e);
@@ -896,7 +944,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
         int i = 0;
         for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
             const uint32_t ph = i & 1;
-            const int first = i & 1;
             uint64_t l2 = pack2(0.0f, 0.0f);
             uint64_t neg_m2 = pack2(0.0f, 0.0f);
             // stabiliser from the 32 scores in hand: m = their maximum
@@ -904,22 +951,18 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
                 float m = __uint_as_float(v[0]);
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                neg_m2 = pack2(-m * kLog2e, -m * kLog2e);
+                // + log2(1 + 2^-9): every exponential comes out scaled by 1 + 2^-9, i.e. carrying the half-ulp that turns the plain
+                // truncation to bf16 below into a rounding (no multiply per pair); the row sum carries the same factor, removed in 1 / l
+                const float nm = fmaf(-m, kLog2e, 2.8150654e-3f);
+                neg_m2 = pack2(nm, nm);
             };
 #pragma unroll 1
-            for (int step = 0; step < 2; ++step) {
-                const int h = step == 0 ? first : first ^ 1;
+            for (int h = 0; h < 2; ++h) {
+                FS_TRACE(20 + 2 * h);
                 mbar_wait(s_full(g, h), ph);
                 __syncwarp();
                 tc_fence_after();
-                if (!warp_active) {
-                    tc_fence_before();
-                    __syncwarp();
-                    const int nb = h == 0 ? 4 : nb1;
-                    if (lane == 0)
-                        for (int b = 0; b < nb; ++b) mbar_arrive(p_full(g, h, b));
-                    continue;
-                }
+                FS_TRACE(21 + 2 * h);
                 uint32_t va[32], vb[32];
                 uint32_t pk[16];
                 if (h == 0) {
@@ -927,25 +970,22 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
                     //      b, and block b is published (its store has long landed) just before block b + 1 is stored ----
                     tmem_ld32(t_row, va);
                     tmem_ld_wait();
-                    if (step == 0) set_m(va);
+                    set_m(va);
                     tmem_ld32(t_row + 32, vb);
                     softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
                     tmem_st16(t_row, pk);
                     tmem_ld_wait();
                     tmem_ld32(t_row + 64, va);
                     softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                    publish(0, 0);
                     tmem_st16(t_row + 16, pk);
                     tmem_ld_wait();
                     tmem_ld32(t_row + 96, vb);
                     softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                    publish(0, 1);
                     tmem_st16(t_row + 32, pk);
                     tmem_ld_wait();
                     softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                    publish(0, 2);
                     tmem_st16(t_row + 48, pk);
-                    publish(0, 3);
+                    publish(0, 0);
                 } else {
                     // ---- keys [128, KB): nf1 full 16-key steps (+ a partial one) as up to three blocks: 32 | 32 or 16 | 16 ----
                     const uint32_t s1 = t_row + 128, p1 = t_row + p1_col;
@@ -954,7 +994,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
                     uint32_t(&pk8)[8] = reinterpret_cast<uint32_t(&)[8]>(pk);
                     tmem_ld32(s1, va);
                     tmem_ld_wait();
-                    if (step == 0) set_m(va);
                     if (wide) tmem_ld32(s1 + 32, vb);
                     else if (n1 >= 3) tmem_ld16(s1 + 32, vb16);
                     softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
@@ -986,57 +1025,68 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
                 }
             }
 
+            FS_TRACE(24);
             mbar_wait(o_full(g), ph);
             __syncwarp();
             tc_fence_after();
-            if (warp_active) {
-                const uint32_t o_col = t_row + (first == 0 ? 64u : 128u);
-                uint32_t o[64];
-#pragma unroll
-                for (int c = 0; c < 64; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(o_col + c, v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[c + j] = v[j];
-                }
+            FS_TRACE(25);
+            {
+                uint32_t oa[32], ob[32];
+                tmem_ld32(t_row + 64, oa);
+                tmem_ld32(t_row + 96, ob);
                 tmem_ld_wait();
                 // O is in registers: hand the TMEM columns back, then scale, round and store through this warp's staging tile
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(tmem_free(g));
+                    FS_TRACE(26);
                     bulk_wait_read0();                  // the previous unit's bulk store has drained the staging tile
                 }
                 __syncwarp();
+                FS_TRACE(27);
                 float l_lo, l_hi;
                 unpack2(l2, l_lo, l_hi);
                 const float l_sum = l_lo + l_hi;
                 if (row < T && !(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, u);
-                const float inv = 1.0f / l_sum;
+                // the row sum carries the (1 + 2^-9) rounding bias of the exponentials (see neg_m2); P, truncated, does not
+                const float inv = __fdividef(1.001953125f, l_sum);
                 const uint64_t inv2 = pack2(inv, inv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                auto scaled = [&](const uint32_t (&o)[32], int j) {       // columns 8 j .. 8 j + 7 of this half -> four bf16 pairs
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float a, b;
                         unpack2(mul2(pack2(__uint_as_float(o[8 * j + 2 * e]), __uint_as_float(o[8 * j + 2 * e + 1])), inv2), a, b);
-                        w[e] = pack_bf16x2_alu(a, b);
+                        w[e] = pack_bf16x2(a, b);
                     }
-                    *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(j) ^ r7) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    return make_uint4(w[0], w[1], w[2], w[3]);
+                };
+                if (p.mode & 1) {
+                    if (row < T) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(frame * T + row) * p.ld_out + head * 64);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dst[j] = scaled(oa, j);
+                            dst[4 + j] = scaled(ob, j);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(j) ^ r7) << 4)) = scaled(oa, j);
+                        *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(4 + j) ^ r7) << 4)) = scaled(ob, j);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        // rows >= T of the box (the tail of the second query tile) fall outside the tensor map's row dimension: clipped
+                        tma_store_3d(&tmap_out, stage_u32, head * 64, g * 128 + quarter * 32, frame);
+                        bulk_commit();
+                    }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    // rows >= T of the box (the tail of the second query tile) fall outside the tensor map's row dimension: clipped
-                    tma_store_3d(&tmap_out, stage_u32, head * 64, g * 128 + quarter * 32, frame);
-                    bulk_commit();
-                }
-            } else {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_free(g));
             }
+            FS_TRACE(28);
             frame += step_frame;
             head += step_head;
             if (head >= p.heads) {
@@ -1047,9 +1097,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
         if (lane == 0) bulk_wait0();   // every bulk store of this warp has completed before the CTA may exit
     }
 
+fs_done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) {
+    if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, 512);
     }
@@ -1160,11 +1211,15 @@ attention_exact_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int k_col0
 static int g_attn_fast = 1;     // 0: general kernel for every T; 1: persistent kernels for T <= 256
 static int g_attn_split = 1;    // 1: split-S kernel for 160 < T <= 208; 0: the single-S fast kernel
 static int g_attn_poly = 1;     // split-S kernel: share of the exponentials on the FMA pipe (0: none, 1: 25 %, 2: 50 %)
-static int g_attn_safe = 0;
+static int g_attn_mode = 0;     // split-S kernel tuning bits (FsParams::mode)
 void set_attention_fast(int on) { g_attn_fast = on; }
 void set_attention_split(int on) { g_attn_split = on; }
 void set_attention_poly(int v) { g_attn_poly = v; }
-void set_attention_safe_order(int on) { g_attn_safe = on; }
+void set_attention_split_mode(int v) { g_attn_mode = v; }
+static int g_attn_delay = 3200;
+void set_attention_split_delay(int cycles) { g_attn_delay = cycles; }
+static unsigned long long* g_attn_trace = nullptr;   // -DCRE_ATTN_TRACE builds: device buffer handed in through cre_set_trace_buffer
+void set_attention_trace(unsigned long long* buf) { g_attn_trace = buf; }
 
 static int launch_exact(const AttnArgs& a, cudaStream_t stream) {
     if (a.unit_flags == nullptr) return 0;
@@ -1207,7 +1262,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         fp.v_col0 = a.v_col0;
         fp.any_flag = a.any_flag;
         fp.unit_flags = a.unit_flags;
-        fp.safe_order = g_attn_safe;
+        fp.out = static_cast<__nv_bfloat16*>(a.out);
+        fp.ld_out = a.heads * 64;
+        fp.mode = g_attn_mode;
+        fp.delay_cycles = g_attn_delay;
+        fp.trace = g_attn_trace;
         CUtensorMap tout;   // out as [frames][T][heads * 64]: a 32-row store box is clipped at the frame's last token
         rc = make_tmap_bf16_3d(&tout, a.out, a.heads * 64, a.t, a.n, a.heads * 64, static_cast<int64_t>(a.t) * a.heads * 64, 32);
         if (rc) return rc;

@@ -20,7 +20,9 @@ void set_gemm_debug(int mode);
 void set_attention_fast(int on);
 void set_attention_split(int on);
 void set_attention_poly(int v);
-void set_attention_safe_order(int on);
+void set_attention_split_mode(int v);
+void set_attention_split_delay(int cycles);
+void set_attention_trace(unsigned long long* buf);
 
 // Kernel ids reported by cre_profile_stop (include/cre.h enum cre_kernel_id)
 // RAII bracket around one kernel launch: bumps the launch counter and, when the profiler is on, records an

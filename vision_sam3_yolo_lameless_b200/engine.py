@@ -279,14 +279,16 @@ class ClipEmbedEngine:
             self.forward_patches(patches, chunk.shape[0], out=out[s:s + chunk.shape[0]])
         return out
 
-    def embed_host_frames(self, frames, bgr: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def embed_host_frames(self, frames, bgr: bool = True, out: Optional[torch.Tensor] = None, copy_only: bool = False) -> torch.Tensor:
         """HOST uint8 frames -> DEVICE f32 [n, D].  ``frames``: one [n, H, W, 3] numpy array / CPU tensor, or a list of
         them (e.g. one per clip; all the same H x W), embedded as if concatenated.
 
         Batches of max_frames are copied host->device on a side stream while the previous batch is being
         embedded (two device frame buffers, events both ways).  Pinned CPU tensors are copied in place;
         pageable input is staged through two pinned buffers first.  Returns after queueing; the caller
-        synchronises by reading the result (``.cpu()``) or on the current stream."""
+        synchronises by reading the result (``.cpu()``) or on the current stream.  A pinned staging slot is never
+        rewritten before the copy that last read it has finished -- also across calls (back-to-back calls with pageable input).
+        ``copy_only=True`` (bench.py's H2D probe) issues exactly the same copies, events and stream waits but launches no kernel."""
         srcs = list(frames) if isinstance(frames, (list, tuple)) else [frames]
         srcs = [torch.from_numpy(np.ascontiguousarray(f)) if isinstance(f, np.ndarray) else f for f in srcs]
         if len(srcs) == 1 and srcs[0].is_cuda:
@@ -320,8 +322,10 @@ class ClipEmbedEngine:
             b = i & 1
             m = min(cf, n - s)
             dev = st["dev"][b]
-            if not all_pinned and i >= 2:
-                st["copied"][b].synchronize()          # this pinned slot's previous H2D must have finished
+            if not all_pinned:
+                # this pinned slot's previous H2D -- of this call (i >= 2) or of an EARLIER call that returned after queueing --
+                # must have finished before the host overwrites it; an event that was never recorded is complete
+                st["copied"][b].synchronize()
             with torch.cuda.stream(st["stream"]):
                 if i >= 2:
                     st["stream"].wait_event(st["freed"][b])
@@ -340,7 +344,8 @@ class ClipEmbedEngine:
                     k += 1
                 st["copied"][b].record(st["stream"])
             compute.wait_event(st["copied"][b])
-            self.embed_frames(dev[: m * per].view(m, h, w, 3), bgr=bgr, out=out[s:s + m])
+            if not copy_only:
+                self.embed_frames(dev[: m * per].view(m, h, w, 3), bgr=bgr, out=out[s:s + m])
             st["freed"][b].record(compute)
         return out
 

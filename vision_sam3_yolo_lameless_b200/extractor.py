@@ -112,12 +112,19 @@ class DINOv3Pipeline:
         H2D copies are pipelined with the kernels inside the engine."""
         return self.engine.embed_host_frames(frames, bgr=bgr).cpu().numpy()
 
-    def embed_clips(self, frames, clip_offsets, bgr: bool = True, top_k: int = 0):
+    def embed_clips(self, frames, clip_offsets, bgr: bool = True, top_k: int = 0, sharded=None):
         """Many clips in one call: HOST frames uint8 [F, H, W, 3] (numpy or pinned CPU tensor), clip c = frames
         [clip_offsets[c], clip_offsets[c+1]).  Returns (clip_mean [Q, D], clip_unit [Q, D]) as numpy, plus
-        (scores [Q, k], ids) against the GPU gallery when top_k > 0 and gallery_backend == 'gpu'."""
+        (scores [Q, k], ids) against the GPU gallery when top_k > 0 and gallery_backend == 'gpu'.
+        ``sharded`` (a :class:`ShardedReID`, one process per GPU, every rank calling with the same number of clips): the search runs
+        against the ROW-SHARDED gallery instead -- all-gather of the queries, per-shard scan, all-gather + merge of the candidates
+        (sharded.py) -- and this rank's rows of the global result are returned."""
         emb = self.engine.embed_host_frames(frames, bgr=bgr)
         mean, unit = self.engine.pool_clips(emb, torch.as_tensor(np.asarray(clip_offsets, dtype=np.int32)))
+        if top_k > 0 and sharded is not None:
+            scores, idx = sharded.search(unit, k=top_k)
+            q, r = unit.shape[0], sharded.rank
+            return mean.cpu().numpy(), unit.cpu().numpy(), scores[r * q:(r + 1) * q].cpu().numpy(), idx[r * q:(r + 1) * q].cpu().numpy()
         if top_k > 0 and self.gallery is not None and len(self.gallery) > 0:
             scores, idx = self.engine.gallery_topk(unit, self.gallery.matrix[: len(self.gallery)], k=top_k)
             return mean.cpu().numpy(), unit.cpu().numpy(), scores.cpu().numpy(), idx.cpu().numpy()
