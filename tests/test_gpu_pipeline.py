@@ -102,6 +102,34 @@ def test_clip_embeddings_meet_cosine_gate(engine_b):
     assert torch.equal(eng.embed_host_frames(pinned), emb)
 
 
+def test_real_clip_vs_reference_golden(engine_b, golden, tmp_path):
+    """The clip the reference ships (1280 x 720 H.264, 125 frames at 25 fps) through DINOv3Pipeline.extract_video_embeddings: same
+    sampled frames / times / canonical frames as the reference's own run (tests/golden/canonical_clips.npz), every frame embedding at
+    cosine >= 0.999; K1 (the TMA variant: 720p qualifies) against the HF processor's pixel_values of the first decoded frame."""
+    import cv2
+    from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
+    eng, _ = engine_b
+    want = np.load(golden / "canonical_clips.npz")
+    name = str(want["clip_names"][0])
+    key = name.split("-")[0]
+    pipe = DINOv3Pipeline(eng, config=SUBJECTS, nats_client=fake_services.FakeNats(), qdrant_client=fake_services.FakeQdrant(),
+                          results_dir=tmp_path)
+    got = pipe.extract_video_embeddings(golden / name)
+    assert [e["frame"] for e in got["embeddings"]] == want[f"{key}_frames"].tolist() == [0, 25, 50, 75, 100]
+    assert [e["time"] for e in got["embeddings"]] == want[f"{key}_times"].tolist()
+    assert [e["frame"] for e in got["canonical_frames"]] == want[f"{key}_canonical"].tolist()
+    assert [got["total_frames"], got["fps"]] == want[f"{key}_meta"].tolist()
+    cos = common.cosine(np.array([e["embedding"] for e in got["embeddings"]]), want[f"{key}_embeddings"])
+    assert (cos >= COS_GATE).all(), cos
+    cap = cv2.VideoCapture(str(golden / name))
+    ok, frame = cap.read()
+    cap.release()
+    assert ok
+    patches = eng.preprocess(torch.from_numpy(frame[None]).to(eng.device), bgr=True)
+    ref = preprocess_ref.patchify(want["frame0_pixel_values"][None])
+    assert (patches.float().cpu() - torch.from_numpy(ref)).abs().max().item() < 1.2e-2      # bf16 rounding of |x| <= 2.64
+
+
 def test_process_video_vs_reference_transcript(engine_b, golden, tmp_path):
     from vision_sam3_yolo_lameless_b200.extractor import DINOv3Pipeline
     eng, _ = engine_b

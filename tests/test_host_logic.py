@@ -52,6 +52,23 @@ def test_extract_video_embeddings_matches_reference(stub, tmp_path, golden):
         pipe.extract_video_embeddings(tmp_path / "nope.avi")
 
 
+def test_extract_video_embeddings_on_the_shipped_clip(stub, tmp_path, golden):
+    """The reference's real clip (125 frames of 1280 x 720 H.264 at 25 fps): grab()-skipping + retrieve() into pinned staging picks the
+    same frames as the reference's read() loop (main.py:133-146) and decodes the same pixels -- the embeddings match its output."""
+    want = np.load(golden / "canonical_clips.npz")
+    name = str(want["clip_names"][0])
+    key = name.split("-")[0]
+    pipe, _, _ = make_pipeline(stub, tmp_path)
+    stub.calls.clear()
+    got = pipe.extract_video_embeddings(golden / name)
+    assert stub.calls == [("embed", (5, 720, 1280, 3))]
+    assert [e["frame"] for e in got["embeddings"]] == want[f"{key}_frames"].tolist()
+    assert [e["time"] for e in got["embeddings"]] == want[f"{key}_times"].tolist()
+    assert [e["frame"] for e in got["canonical_frames"]] == want[f"{key}_canonical"].tolist()
+    assert [got["total_frames"], got["fps"]] == want[f"{key}_meta"].tolist()
+    np.testing.assert_allclose(np.array([e["embedding"] for e in got["embeddings"]]), want[f"{key}_embeddings"], atol=2e-4)
+
+
 def test_extract_embedding_shapes(stub, tmp_path, golden):
     pipe, _, _ = make_pipeline(stub, tmp_path)
     want = np.load(golden / "embed_vitb.npz")

@@ -49,6 +49,30 @@ def test_vit_restatement_matches_reference_extract_embedding(golden, model_b):
         assert common.cosine(got, want[name]) > 0.999999
 
 
+def test_real_clip_oracle_matches_reference(golden, model_b):
+    """Real pixels (the clip the reference ships, 1280 x 720 H.264): the oracle's decode loop + per-frame path against the
+    reference's own extract_video_embeddings output, and the numpy antialias restatement against the HF processor on frame 0."""
+    import cv2
+
+    want = np.load(golden / "canonical_clips.npz")
+    name = str(want["clip_names"][0])
+    key = name.split("-")[0]
+    pipe = pipeline_ref.ReferencePipelineCPU(model_b)
+    got = pipe.extract_video_embeddings(golden / name)
+    assert [e["frame"] for e in got["embeddings"]] == want[f"{key}_frames"].tolist() == [0, 25, 50, 75, 100]
+    assert [e["time"] for e in got["embeddings"]] == want[f"{key}_times"].tolist()
+    assert [e["frame"] for e in got["canonical_frames"]] == want[f"{key}_canonical"].tolist()
+    assert [got["total_frames"], got["fps"]] == want[f"{key}_meta"].tolist() == [125, 25]
+    np.testing.assert_allclose(np.array([e["embedding"] for e in got["embeddings"]]), want[f"{key}_embeddings"], atol=2e-4)
+    assert pipeline_ref.sampled_frame_indices(125, 25.0) == [0, 25, 50, 75, 100]
+    cap = cv2.VideoCapture(str(golden / name))
+    ok, frame = cap.read()
+    cap.release()
+    assert ok and frame.shape == (720, 1280, 3)
+    pv = preprocess_ref.preprocess(frame[None], bgr=True)[0]
+    np.testing.assert_allclose(pv, want["frame0_pixel_values"], atol=3e-5, rtol=0)
+
+
 def test_gray_image_passthrough(golden, model_b):
     """main.py:98-101: 2-D input skips cvtColor; PIL 'L' image -> HF processor replicates to 3 channels."""
     want = np.load(golden / "embed_vitb.npz")["gray_224"]

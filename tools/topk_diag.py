@@ -15,6 +15,11 @@ for q, n, k in [(3, 40, 256), (3, 40, 48), (3, 40, 40), (3, 40, 41), (3, 300, 25
     gen = torch.Generator(device=dev).manual_seed(q * 1000 + k)
     g = torch.nn.functional.normalize(torch.randn(n, 768, device=dev, generator=gen), dim=1)
     qv = torch.nn.functional.normalize(torch.randn(q, 768, device=dev, generator=gen), dim=1)
+    if n > 30:
+        dup = torch.randperm(n, device=dev, generator=gen)[:12]
+        g[dup] = g[dup[0]].clone()
+        qv[0] = torch.nn.functional.normalize(g[dup[0]] + 0.02 * torch.randn(768, device=dev, generator=gen), dim=0)
+        print("dup rows", sorted((dup + 50).tolist()))
     gb = g.to(torch.bfloat16).contiguous()
     s, i, dump = eng.gallery_topk(qv, gb, k=k, row_base=50, dump_scores=True)
     kk = min(k, n)
@@ -25,5 +30,7 @@ for q, n, k in [(3, 40, 256), (3, 40, 48), (3, 40, 40), (3, 40, 41), (3, 300, 25
         r, c = bad[0]
         print("   got ", i[r, max(0, c - 3):c + 6].tolist(), [round(x, 4) for x in s[r, max(0, c - 3):c + 6].tolist()])
         print("   want", ref_idx[r, max(0, c - 3):c + 6].tolist(), [round(float(x), 4) for x in ref_top[r, max(0, c - 3):c + 6]])
+        print("   full got row", i[r, :kk].tolist())
+        print("   full want row", ref_idx[r].tolist())
     tail_ok = (i.cpu().numpy()[:, kk:] == 0x7FFFFFFF).all()
     print("   tail fill ok:", bool(tail_ok))

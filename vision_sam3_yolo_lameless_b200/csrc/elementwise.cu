@@ -639,14 +639,18 @@ gallery_scan_small_kernel(const float* __restrict__ queries, const __nv_bfloat16
                 if (lane < Q) {
                     if (dump != nullptr) dump[static_cast<size_t>(lane) * rows + r] = mine;
                     if (mine > ts[CRE_TOPK_MAX - 1] && (mine < cut_s || (mine == cut_s && row_base + r > cut_i))) {
+                        // insertion + unconditional shift of everything behind (see the EPI_TOPK epilogue: displaced entries must
+                        // pass entries of equal score)
                         float cs = mine;
                         int ci = row_base + r;
+                        bool shifting = false;
 #pragma unroll
                         for (int j = 0; j < CRE_TOPK_MAX; ++j) {
-                            if (cs > ts[j]) {
+                            if (shifting || cs > ts[j]) {
                                 const float t1 = ts[j]; const int t2 = ti[j];
                                 ts[j] = cs; ti[j] = ci;
                                 cs = t1; ci = t2;
+                                shifting = true;
                             }
                         }
                     }

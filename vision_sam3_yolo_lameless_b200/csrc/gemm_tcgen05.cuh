@@ -791,14 +791,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 const float s = x[j];
                                 // columns arrive in ascending index, so on ties the earlier (smaller) index stays ahead
                                 if (n < p.N && s > tk_s[kTopKMax - 1] && (s < cut_s || (s == cut_s && p.col_base + n > cut_i))) {
+                                    // insertion: find the first entry the candidate beats, then SHIFT everything behind it down --
+                                    // unconditionally: a displaced entry must also pass entries of EQUAL score (it has the smaller
+                                    // index), or a run of ties ends up out of index order and loses the wrong member at the tail
                                     float cs_ = s;
                                     int ci_ = p.col_base + n;
+                                    bool shifting = false;
 #pragma unroll
                                     for (int q = 0; q < kTopKMax; ++q) {
-                                        if (cs_ > tk_s[q]) {
+                                        if (shifting || cs_ > tk_s[q]) {
                                             const float ts = tk_s[q]; const int ti = tk_i[q];
                                             tk_s[q] = cs_; tk_i[q] = ci_;
                                             cs_ = ts; ci_ = ti;
+                                            shifting = true;
                                         }
                                     }
                                 }
