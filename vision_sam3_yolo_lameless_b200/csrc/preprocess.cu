@@ -40,12 +40,40 @@ struct PreParams {
     const int32_t* rois;
 };
 
-// byte j of `word` -> the float 1 + b * 2^-15 (bits 0x3F80bb00) with ONE byte-permute: no shift / mask / int->float
-// conversion per byte.  The vertical filter accumulates sum_k w_k * (1 + b_k * 2^-15) with packed FFMA2 and removes the
-// offset exactly afterwards (minus sum_k w_k, times 2^15): rounding error <= 0.02 byte units, 2e-4 after normalisation.
-__device__ __forceinline__ float byte_as_unit_float(uint32_t word, uint32_t selector) {
-    return __uint_as_float(__byte_perm(word, 0x3F800000u, selector));
+// Vertical pass, integer form (every K1 variant evaluates exactly this, so they agree bit for bit):
+//     w16_k = rint(w_k * 2^15)           the aten antialias weight of tap k as an unsigned 16-bit fixed-point number
+//     acc   = sum_k w16_k * b_k          exact in int32 (<= 255 * (2^15 + taps / 2) < 2^23)
+//     v     = float(acc) * (1 / float(sum_k w16_k))        one rounding; the weights are renormalised to sum to 1
+// Quantising the weights to 2^-16 moves a filtered pixel by at most 255 * taps * 2^-16 = 0.04 grey levels (1.7e-4 of the range, 7e-4
+// after normalisation: a tenth of the bf16 half-ulp of the output).  Two taps cost ONE IDP.2A per byte column on packed bytes --
+// the bytes of rows k and k + 1 interleaved by two byte-permutes per word -- instead of a byte-permute + half an FFMA2 per byte
+// and tap: 0.8 instead of 1.6 instructions per byte-tap in the stage that bounds the kernel.
+__device__ __forceinline__ uint32_t aa_weight16(float w) { return __float2uint_rn(w * 32768.0f); }
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t w2, uint32_t bytes, uint32_t acc) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(bytes), "r"(acc));
+    return d;
 }
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t w2, uint32_t bytes, uint32_t acc) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(bytes), "r"(acc));
+    return d;
+}
+// 16 byte columns x two taps: acc[j] += w16_a * row_a[j] + w16_b * row_b[j]   (w2 = w16_a | w16_b << 16)
+__device__ __forceinline__ void vtaps2(const uint4& qa, const uint4& qb, uint32_t w2, uint32_t (&acc)[16]) {
+    const uint32_t a[4] = {qa.x, qa.y, qa.z, qa.w}, b[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = __byte_perm(a[i], b[i], 0x5140u);     // (a0, b0, a1, b1)
+        const uint32_t hi = __byte_perm(a[i], b[i], 0x7362u);     // (a2, b2, a3, b3)
+        acc[4 * i] = dp2a_lo(w2, lo, acc[4 * i]);
+        acc[4 * i + 1] = dp2a_hi(w2, lo, acc[4 * i + 1]);
+        acc[4 * i + 2] = dp2a_lo(w2, hi, acc[4 * i + 2]);
+        acc[4 * i + 3] = dp2a_hi(w2, hi, acc[4 * i + 3]);
+    }
+}
+// acc (< 2^23) -> float without the XU-pipe conversion: 2^23 + acc is exact in fp32, so is the subtraction
+__device__ __forceinline__ float acc_to_float(uint32_t acc) { return __uint_as_float(acc | 0x4B000000u) - 8388608.0f; }
 
 // (x / 255 - mean) / std exactly as every K1 variant evaluates it (one definition so that the compiler contracts it the same way
 // everywhere: the variants must agree bit for bit)
@@ -87,48 +115,36 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
         const float* wy = t_yw + static_cast<size_t>(oy) * p.ykmax;
         const int col = b0 + v * 16;
         float acc[16];
+        uint32_t iacc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) iacc[i] = 0u;
+        uint32_t wtot = 0u;
         const uint8_t* src = fbase + static_cast<int64_t>(y0) * p.row_pitch + col;
         if (p.vec && (col + 16 <= row_bytes)) {
-            uint64_t acc2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc2[i] = pack2(0.0f, 0.0f);
-            float wsum = 0.0f;
-#pragma unroll 6
-            for (int k = 0; k < cnt; ++k) {
-                const float wk = __ldg(wy + k);
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(k) * p.row_pitch));
-                const uint64_t w2 = pack2(wk, wk);
-                wsum += wk;
-                const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc2[2 * i] = fma2(pack2(byte_as_unit_float(wds[i], 0x7604u), byte_as_unit_float(wds[i], 0x7614u)), w2, acc2[2 * i]);
-                    acc2[2 * i + 1] = fma2(pack2(byte_as_unit_float(wds[i], 0x7624u), byte_as_unit_float(wds[i], 0x7634u)), w2, acc2[2 * i + 1]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float lo, hi;
-                unpack2(acc2[i], lo, hi);
-                acc[2 * i] = (lo - wsum) * 32768.0f;
-                acc[2 * i + 1] = (hi - wsum) * 32768.0f;
+#pragma unroll 3
+            for (int k = 0; k < cnt; k += 2) {
+                const bool two = k + 1 < cnt;
+                const uint32_t wa = aa_weight16(__ldg(wy + k)), wb = two ? aa_weight16(__ldg(wy + k + 1)) : 0u;
+                const uint4 qa = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(k) * p.row_pitch));
+                const uint4 qb = two ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(k + 1) * p.row_pitch)) : qa;
+                wtot += wa + wb;
+                vtaps2(qa, qb, wa | (wb << 16), iacc);
             }
         } else {
-            // unaligned / ragged edge: byte loads, SAME arithmetic (1 + b * 2^-15, same FMA order) -> bit-identical results
-            float wsum = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+            // unaligned / ragged edge: byte loads, the same integer sums
             for (int k = 0; k < cnt; ++k) {
-                const float wk = __ldg(wy + k);
-                wsum += wk;
+                const uint32_t wk = aa_weight16(__ldg(wy + k));
+                wtot += wk;
                 const uint8_t* s8 = src + static_cast<int64_t>(k) * p.row_pitch;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (col + i < row_bytes)
-                        acc[i] = fmaf(__uint_as_float(0x3F800000u | (static_cast<uint32_t>(__ldg(s8 + i)) << 8)), wk, acc[i]);
+                    if (col + i < row_bytes) iacc[i] += wk * static_cast<uint32_t>(__ldg(s8 + i));
             }
+        }
+        {
+            const float inv = 1.0f / static_cast<float>(wtot);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = (col + i < row_bytes) ? (acc[i] - wsum) * 32768.0f : 0.0f;
+            for (int i = 0; i < 16; ++i) acc[i] = acc_to_float(iacc[i]) * inv;
         }
         float4* dst = reinterpret_cast<float4*>(vbuf + static_cast<size_t>(r) * p.sstride + v * 16);
 #pragma unroll
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kPreThreads, 2) preprocess_kernel(const PrePar
 // the antialias tables degenerate to the identity (weights {1, 0}), so K1 is normalise + patchify and purely HBM-bound
 // (3 B in, 6 B out per pixel).  Thread = one 16-pixel row of one patch: 48 contiguous input bytes (three 16-byte loads; a warp
 // covers two neighbouring patches, i.e. 96 contiguous bytes per image row) -> per channel 32 contiguous output bytes (16 threads
-// of a patch write 512 contiguous bytes).  Same arithmetic as the filtered path with identity taps -- 1 + b 2^-15 -> b exactly
+// of a patch write 512 contiguous bytes).  Same values as the filtered path with identity taps -- 2^15 b / 2^15 = b exactly
 // -> normalise_px -> bf16 -- so the result is bit-identical to preprocess_kernel on the same input.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) preprocess_identity_kernel(const PreParams p, int64_t total) {
@@ -190,10 +206,11 @@ __global__ void __launch_bounds__(256) preprocess_identity_kernel(const PreParam
     float v[48];   // byte 3 i + j = pixel i, memory channel j
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        v[4 * i] = fmaf(byte_as_unit_float(wds[i], 0x7604u), 32768.0f, -32768.0f);
-        v[4 * i + 1] = fmaf(byte_as_unit_float(wds[i], 0x7614u), 32768.0f, -32768.0f);
-        v[4 * i + 2] = fmaf(byte_as_unit_float(wds[i], 0x7624u), 32768.0f, -32768.0f);
-        v[4 * i + 3] = fmaf(byte_as_unit_float(wds[i], 0x7634u), 32768.0f, -32768.0f);
+        // byte j -> 2^23 + b (one byte-permute) -> b: what the integer vertical pass yields for identity taps {2^15, 0}
+        v[4 * i] = __uint_as_float(__byte_perm(wds[i], 0x4B000000u, 0x7650u)) - 8388608.0f;
+        v[4 * i + 1] = __uint_as_float(__byte_perm(wds[i], 0x4B000000u, 0x7651u)) - 8388608.0f;
+        v[4 * i + 2] = __uint_as_float(__byte_perm(wds[i], 0x4B000000u, 0x7652u)) - 8388608.0f;
+        v[4 * i + 3] = __uint_as_float(__byte_perm(wds[i], 0x4B000000u, 0x7653u)) - 8388608.0f;
     }
     __nv_bfloat16* o = p.out + patch * 768 + ky * 16;
 #pragma unroll
@@ -300,7 +317,7 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, 
 }
 
 __global__ void __launch_bounds__(kPtThreads, 1)
-preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles, int debug) {
+preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles) {
     extern __shared__ uint8_t smem_raw_[];
     const uint32_t base_u32 = (smem_u32(smem_raw_) + 127u) & ~127u;
     uint8_t* base = smem_raw_ + (base_u32 - smem_u32(smem_raw_));
@@ -317,6 +334,21 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     int* s_ycnt = s_ylo + oh;
     int* s_xlo = s_ycnt + oh;
     int* s_xcnt = s_xlo + ow;
+    // vertical taps in the integer form (see vtaps2): per output row its taps as 16-bit pairs, and 1 / (their sum)
+    const int ypairs = (p.ykmax + 1) >> 1;
+    uint32_t* s_yw16 = reinterpret_cast<uint32_t*>(s_xcnt + ow);
+    float* s_yinv = reinterpret_cast<float*>(s_yw16 + oh * ypairs);
+    for (int oy = threadIdx.x; oy < oh; oy += kPtThreads) {
+        const int cnt = __ldg(p.ycnt + oy);
+        uint32_t tot = 0u;
+        for (int kp = 0; kp < ypairs; ++kp) {
+            const uint32_t wa = 2 * kp < cnt ? aa_weight16(__ldg(p.yw + oy * p.ykmax + 2 * kp)) : 0u;
+            const uint32_t wb = 2 * kp + 1 < cnt ? aa_weight16(__ldg(p.yw + oy * p.ykmax + 2 * kp + 1)) : 0u;
+            s_yw16[oy * ypairs + kp] = wa | (wb << 16);
+            tot += wa + wb;
+        }
+        s_yinv[oy] = 1.0f / static_cast<float>(tot);
+    }
     for (int i = threadIdx.x; i < oh * p.ykmax; i += kPtThreads) s_yw[i] = __ldg(p.yw + i);
     for (int i = threadIdx.x; i < ow * p.xkmax; i += kPtThreads) s_xw[i] = __ldg(p.xw + i);
     for (int i = threadIdx.x; i < oh; i += kPtThreads) { s_ylo[i] = __ldg(p.ylo + i); s_ycnt[i] = __ldg(p.ycnt + i); }
@@ -357,7 +389,6 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
                 const int y_first = s_ylo[py * 16];
                 int* pr = params + (it & 3) * kPtParamInts;
                 pr[0] = frame; pr[1] = py; pr[2] = px; pr[3] = b0; pr[4] = y_first; pr[5] = (x_hi * 3 - b0 + 15) >> 4;
-                if (debug & 2) { mbar_arrive(raw_full(buf)); continue; }   // tuning: no loads
                 mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
                 for (int j = 0; j < nbox; ++j)
                     tma_load_3d(&tmap, raw_full(buf), base_u32 + buf * raw_bytes + j * rows_tile * 256, b0 + j * 256, y_first, frame);
@@ -379,35 +410,26 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
             float* vrow = vb0 + buf * vb_floats + static_cast<size_t>(r) * p.sstride;
             const int oy = py * 16 + r;
             const int y0 = s_ylo[oy] - y_first, cnt = s_ycnt[oy];
-            const float* wy = s_yw + oy * p.ykmax;
-            for (int v = lane; v < nvec && !(debug & 1); v += 32) {
+            const uint32_t* wy16 = s_yw16 + oy * ypairs;
+            const float inv = s_yinv[oy];
+            const int npair = (cnt + 1) >> 1;
+            for (int v = lane; v < nvec; v += 32) {
                 const uint8_t* src = raw + (v >> 4) * (rows_tile * 256) + y0 * 256 + (v & 15) * 16;
-                uint64_t acc2[8];
+                uint32_t iacc[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc2[i] = pack2(0.0f, 0.0f);
-                float wsum = 0.0f;
-#pragma unroll 4
-                for (int k = 0; k < cnt; ++k) {
-                    const float wk = wy[k];
-                    const uint4 q = *reinterpret_cast<const uint4*>(src + k * 256);
-                    const uint64_t w2 = pack2(wk, wk);
-                    wsum += wk;
-                    const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc2[2 * i] = fma2(pack2(byte_as_unit_float(wds[i], 0x7604u), byte_as_unit_float(wds[i], 0x7614u)), w2, acc2[2 * i]);
-                        acc2[2 * i + 1] = fma2(pack2(byte_as_unit_float(wds[i], 0x7624u), byte_as_unit_float(wds[i], 0x7634u)), w2, acc2[2 * i + 1]);
-                    }
+                for (int i = 0; i < 16; ++i) iacc[i] = 0u;
+#pragma unroll 3
+                for (int kp = 0; kp < npair; ++kp) {
+                    const uint4 qa = *reinterpret_cast<const uint4*>(src + (2 * kp) * 256);
+                    // an odd tap count pairs the last tap with weight 0: any in-bounds row will do
+                    const uint4 qb = *reinterpret_cast<const uint4*>(src + (2 * kp + (2 * kp + 1 < cnt ? 1 : 0)) * 256);
+                    vtaps2(qa, qb, wy16[kp], iacc);
                 }
-                // (acc - wsum) * 2^15 as one packed FMA: the scaling is exact, so this rounds exactly like the subtraction
-                const float nws = -wsum * 32768.0f;
-                const uint64_t k15 = pack2(32768.0f, 32768.0f), nws2 = pack2(nws, nws);
                 float4 f[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    unpack2(fma2(acc2[2 * i], k15, nws2), f[i].x, f[i].y);
-                    unpack2(fma2(acc2[2 * i + 1], k15, nws2), f[i].z, f[i].w);
-                }
+                for (int i = 0; i < 4; ++i)
+                    f[i] = make_float4(acc_to_float(iacc[4 * i]) * inv, acc_to_float(iacc[4 * i + 1]) * inv,
+                                       acc_to_float(iacc[4 * i + 2]) * inv, acc_to_float(iacc[4 * i + 3]) * inv);
                 // rotate the store order by `rot` (two select stages) -- lane l writes unit (i + rot) & 3 in store i
                 float4 g[4], h[4];
 #pragma unroll
@@ -445,7 +467,7 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
             const int frame = pr[0], py = pr[1], px = pr[2], b0 = pr[3];
             const float* vbuf = vb0 + buf * vb_floats;
             const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px;
-            if (!(debug & 1)) {
+            {
                 const int ox = px * 16 + kx;
                 const int x0 = s_xlo[ox], cnt = s_xcnt[ox];
                 const float* wx = s_xw + ox * p.xkmax;
@@ -472,8 +494,8 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     }
 }
 
-static int g_pre_tma = 1, g_pre_debug = 0, g_pre_identity = 1;
-void set_preprocess_tma(int on) { g_pre_tma = on & 1; g_pre_debug = on >> 1; }
+static int g_pre_tma = 1, g_pre_identity = 1;
+void set_preprocess_tma(int on) { g_pre_tma = on & 1; }
 void set_preprocess_identity(int on) { g_pre_identity = on; }
 
 // returns 1 if the TMA variant was launched, 0 if the input does not qualify, negative on error
@@ -491,11 +513,12 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     // small tiles are bound by the per-tile hand-offs, not by bytes: this variant costs ~1.45 us + 0.16 us/MB per frame, the direct-load
     // kernel ~1 us/MB.  Measured cross-over (600 frames; direct vs TMA us/frame): 540x960 1.67 / 1.75, 720x1280 2.70 / 1.95,
     // 1080x1920 4.11 / 2.42 -> at about 12x fewer output than input pixels
-    if (sy * sx < 12.0 && !(g_pre_debug & 4)) return 0;
+    if (sy * sx < 12.0) return 0;
     p.sstride = nvec_max * 16 + 4;
     const size_t smem = 2 * static_cast<size_t>(nbox) * rows_tile * 256 + 2 * static_cast<size_t>(16) * p.sstride * 4 +
                         4 * kPtParamInts * 4 + 64 + 128 +
-                        (static_cast<size_t>(a.gh) * 16 * (a.ty.kmax + 2) + static_cast<size_t>(a.gw) * 16 * (a.tx.kmax + 2)) * 4;
+                        (static_cast<size_t>(a.gh) * 16 * (a.ty.kmax + 2) + static_cast<size_t>(a.gw) * 16 * (a.tx.kmax + 2)) * 4 +
+                        static_cast<size_t>(a.gh) * 16 * ((a.ty.kmax + 1) / 2 + 1) * 4;
     if (smem > 227 * 1024) return 0;
     CUtensorMap tmap;
     int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows_tile);
@@ -509,7 +532,7 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     const int tiles = static_cast<int>(tiles64);
     const int grid = tiles < sms ? tiles : sms;
     LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
-    preprocess_tma_kernel<<<grid, kPtThreads, smem, stream>>>(tmap, p, rows_tile, nbox, tiles, g_pre_debug);
+    preprocess_tma_kernel<<<grid, kPtThreads, smem, stream>>>(tmap, p, rows_tile, nbox, tiles);
     CRE_CUDA_OK(cudaGetLastError());
     return 1;
 }
