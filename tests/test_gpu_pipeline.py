@@ -212,6 +212,21 @@ def test_matcher_near_thresholds_and_durable_store(engine_b, golden):
     print(f"largest similarity difference vs the reference transcript: {worst:.2e}")
 
 
+def test_sharded_matcher_on_two_gpus():
+    """SURVEY 8(e) behind the matcher on real hardware: tests/multigpu_matcher.py under torchrun with 2 ranks over NCCL (skipped on a
+    one-GPU box; profiles/r02*_multigpu_matcher.log holds the 2- and 8-GPU runs)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on the box (run tests/multigpu_matcher.py under torchrun; see profiles/)")
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(root / "tests" / "multigpu_matcher.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTIGPU_MATCHER_OK world=2" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_full_size_properties(engine_b):
     """BASELINE sizes, size-independent properties: (1) a 100k-row gallery scan returns, for queries that ARE gallery
     rows, that row first with score ~1; (2) permuting the clips permutes the result; (3) 8-way sharding + merge is

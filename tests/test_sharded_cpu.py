@@ -93,3 +93,69 @@ def test_sharded_topk_equals_single_shard(tmp_path, world, ragged):
         assert (i == ref_i[order]).all(), "sharded top-k indices differ from the single-shard rule"
         np.testing.assert_array_equal(s, ref_s[order])
     assert outs[0][1][list(outs[0][2]).index(0)].tolist()[:3] == [3, 77, 400]
+
+
+def _matcher_worker(rank, world, port, out_dir):
+    """Every rank drives a row-sharded CowReIDMatcher with the same calls (SPMD); arithmetic by the oracle-backed StubEngine."""
+    import asyncio
+    import json
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import GOLDEN, replay_reid_tight
+        from oracle import common, fake_services
+        from oracle.make_golden import reid_queries
+        from stub_engine import StubEngine
+        from vision_sam3_yolo_lameless_b200.gallery import ShardedGpuGallery
+        from vision_sam3_yolo_lameless_b200.reid import CowReIDMatcher
+
+        stub = StubEngine(common.hf_model(layers=1))
+        want = json.load(open(GOLDEN / "reid_scenario.json"))
+        qd = fake_services.FakeQdrant()
+        m = CowReIDMatcher(qdrant_url="fake://", engine=stub, qdrant_client=qd, sharded=True)
+        asyncio.run(m.connect())
+        assert isinstance(m.client, ShardedGpuGallery) and m.client.world == world
+        log = []
+        for k, ((name, q), step) in enumerate(zip(reid_queries(), want["steps"])):
+            got = m.match_or_create(np.asarray(q), video_id=f"video-{name}", track_id=k)
+            assert (got.cow_id, got.confidence, got.is_new_identity) == (step["cow_id"], step["confidence"], step["is_new"]), name
+            assert abs(got.similarity - step["similarity"]) < 4e-4, name
+            log.append([got.cow_id, got.similarity])
+        _, cands = m.match_embedding(np.asarray(reid_queries()[0][1]))
+        assert [c.cow_id for c in cands] == [c["cow_id"] for c in want["final_candidates"]]
+        # rows really are spread: global row r on rank r % world
+        assert m.client._local_rows() == len(range(rank, len(m.client), world))
+        # durable store: every rank that holds a client wrote every identity, at full precision (owner's master row, broadcast)
+        assert len(qd.collections["cow_identities"]["ids"]) == 4
+        # a second sharded matcher mirrors the store; more than 8 hits come back complete and ordered
+        m2 = CowReIDMatcher(qdrant_url="fake://", engine=stub, qdrant_client=qd, sharded=True)
+        asyncio.run(m2.connect())
+        assert m2.identity_counter == 4 and m2.match_embedding(np.asarray(reid_queries()[0][1]))[0].cow_id == "COW-0001"
+        # the near-threshold transcript with its durable-store check, sharded
+        class _Shim(CowReIDMatcher):
+            def __init__(self, **kw):
+                super().__init__(sharded=True, **kw)
+        import vision_sam3_yolo_lameless_b200.reid as reid_mod
+        orig = reid_mod.CowReIDMatcher
+        reid_mod.CowReIDMatcher = _Shim
+        try:
+            worst = replay_reid_tight(stub, GOLDEN, sim_tol=4e-4)
+        finally:
+            reid_mod.CowReIDMatcher = orig
+        json.dump({"log": log, "worst": worst}, open(os.path.join(out_dir, f"m{rank}.json"), "w"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_matcher_reproduces_reference_transcript(tmp_path, world):
+    """SURVEY 8(e) behind the reference-facing matcher: the gallery row-sharded over `world` ranks gives, on EVERY rank, the reference's
+    own match_or_create transcript (tests/golden/reid_scenario.json, reid_tight.npz) -- reads are collectives, writes run on the owner."""
+    import json
+    mp.spawn(_matcher_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    logs = [json.load(open(tmp_path / f"m{r}.json")) for r in range(world)]
+    assert all(l["log"] == logs[0]["log"] for l in logs), "every rank must report the same matches"

@@ -151,3 +151,107 @@ class GpuGallery:
                 hits.append(ScoredPoint(self.ids[i], float(s), self.payloads[i]))
             out.append(hits)
         return out
+
+
+class ShardedGpuGallery(GpuGallery):
+    """The same gallery ROW-SHARDED over the ranks of a process group (one process per GPU): SURVEY.md section 8(e) behind the
+    matcher / extractor interface instead of only inside bench.py.
+
+    Contract (SPMD, like every torch.distributed program): every rank constructs it and calls the SAME methods with the SAME
+    arguments in the SAME order -- e.g. each tracking-service replica consumes the same ``pipeline.dinov3`` subject.  Then
+
+    * host metadata (ids, payloads, global row numbers = insertion order) is replicated and identical everywhere;
+    * global row r lives on rank ``r % world`` at local row ``r // world`` (round-robin: ownership does not move when the gallery
+      grows, unlike a contiguous split of a growing N); a write -- create or momentum update (matcher.py:203-301) -- runs its kernel
+      on the OWNING rank only, in message order, and ``vector()`` broadcasts the owner's fp32 master row;
+    * ``search`` / ``search_batch`` are collectives: every rank scans its shard (K4, candidates carry GLOBAL row numbers), the
+      candidates are all-gathered and merged under (score desc, global row asc) -- ``ShardedReID.search_all`` -- so every rank returns
+      the same hits a single-device gallery would.
+    """
+
+    def __init__(self, engine: ClipEmbedEngine, dim: int, capacity: int = 4096, group=None, sharded_reid=None):
+        import torch.distributed as dist
+
+        from .sharded import ShardedReID
+
+        super().__init__(engine, dim, capacity)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # per-shard scan with global row numbers; the merge is the engine's (or whatever the injected ShardedReID uses)
+        self._reid = sharded_reid if sharded_reid is not None else ShardedReID(engine, group=group, local_topk=self._local_topk,
+                                                                                  merge=lambda s, i: engine.merge_topk(s, i))
+
+    # global row <-> (owner, local row)
+    def _owner(self, row: int) -> int:
+        return row % self.world
+
+    def _local_rows(self) -> int:
+        n = len(self.ids)
+        return (n - self.rank + self.world - 1) // self.world if n > self.rank else 0
+
+    def _local_topk(self, unit_queries: torch.Tensor, k: int):
+        n_local = self._local_rows()
+        s, i = self.engine.gallery_topk(unit_queries, self.matrix[:n_local], k=k)
+        valid = i != 0x7FFFFFFF
+        return s, torch.where(valid, i * self.world + self.rank, i)           # local row -> global row
+
+    def load(self, ids, vectors, payloads=None) -> None:
+        n = len(ids)
+        mine = list(range(self.rank, n, self.world))
+        self._grow((n + self.world - 1) // self.world + 1)
+        if mine:
+            v = vectors if isinstance(vectors, torch.Tensor) else torch.as_tensor(np.asarray(vectors, dtype=np.float32))
+            unit = self._unit(v[mine])
+            self.master[: len(mine)] = unit
+            self.matrix[: len(mine)] = unit
+        self.ids = list(ids)
+        self.payloads = [dict(p or {}) for p in payloads] if payloads is not None else [{} for _ in ids]
+        self._row_of = {pid: r for r, pid in enumerate(self.ids)}
+
+    def upsert(self, point_id, vector, payload=None, momentum: float = 0.0) -> int:
+        row = self._row_of.get(point_id)
+        if row is None:
+            row = len(self.ids)
+            self.ids.append(point_id)
+            self.payloads.append(dict(payload or {}))
+            self._row_of[point_id] = row
+            momentum = 0.0
+        elif payload is not None:
+            self.payloads[row] = dict(payload)
+        if self._owner(row) == self.rank:                    # the write itself: owning rank only
+            local = row // self.world
+            self._grow(local + 1)
+            unit = self._unit(np.asarray(vector, dtype=np.float32)[None, :])
+            self.engine.gallery_update_row(self.matrix, local, unit, momentum, master=self.master)
+        return row
+
+    def vector(self, point_id):
+        import torch.distributed as dist
+
+        row = self._row_of.get(point_id)
+        if row is None:
+            return None
+        owner = self._owner(row)
+        buf = self.master[row // self.world].clone() if owner == self.rank else torch.empty(self.dim, dtype=torch.float32,
+                                                                                            device=self.engine.device)
+        if self.world > 1:
+            src = dist.get_global_rank(self.group, owner) if self.group is not None else owner
+            dist.broadcast(buf, src=src, group=self.group)
+        return buf.cpu().numpy()
+
+    def search_batch(self, queries, k: int = 5):
+        k = int(k)
+        if k < 1:
+            raise ValueError(f"top_k={k}: must be >= 1")
+        if k > _lib.TOPK_LIMIT:
+            raise ValueError(f"top_k={k} exceeds the kernel limit ({_lib.TOPK_LIMIT}); the request is refused rather than truncated")
+        q = np.asarray(queries, dtype=np.float32)
+        n = len(self.ids)
+        if n == 0:
+            return [[] for _ in range(q.shape[0])]
+        unit = self._unit(q)
+        scores, idx = self._reid.search_all(unit, k=min(k, n))         # every rank holds the same queries: no query all-gather
+        scores, idx = scores.cpu().numpy(), idx.cpu().numpy()
+        return [[ScoredPoint(self.ids[i], float(s), self.payloads[i]) for s, i in zip(scores[r], idx[r]) if i < n and np.isfinite(s)]
+                for r in range(q.shape[0])]

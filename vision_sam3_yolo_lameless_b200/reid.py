@@ -21,7 +21,7 @@ from uuid import UUID, uuid4
 import numpy as np
 
 from .engine import ClipEmbedEngine
-from .gallery import GpuGallery
+from .gallery import GpuGallery, ShardedGpuGallery
 
 
 @dataclass
@@ -53,7 +53,11 @@ class CowReIDMatcher:
 
     def __init__(self, qdrant_url: str = "http://qdrant:6333", embedding_dim: int = 768,
                  auto_create_identities: bool = True, embedding_momentum: float = 0.9,
-                 engine: Optional[ClipEmbedEngine] = None, qdrant_client=None):
+                 engine: Optional[ClipEmbedEngine] = None, qdrant_client=None, sharded: bool = False, group=None):
+        """``sharded=True`` (one process per GPU, torch.distributed initialised): the gallery is row-sharded over the ranks of
+        ``group`` (:class:`ShardedGpuGallery`); every rank must then drive the matcher with the same calls in the same order."""
+        self.sharded = sharded
+        self.group = group
         self.qdrant_url = qdrant_url
         self.embedding_dim = embedding_dim
         self.auto_create_identities = auto_create_identities
@@ -68,7 +72,8 @@ class CowReIDMatcher:
         and mirror its points (matcher.py:80-102)."""
         if self.engine is None:
             raise RuntimeError("CowReIDMatcher needs a ClipEmbedEngine (no CPU fallback)")
-        self.client = GpuGallery(self.engine, self.embedding_dim)
+        self.client = (ShardedGpuGallery(self.engine, self.embedding_dim, group=self.group) if self.sharded
+                       else GpuGallery(self.engine, self.embedding_dim))
         if self.qdrant_client is not None:
             names = [c.name for c in self.qdrant_client.get_collections().collections]
             if self.COLLECTION_NAME not in names:
