@@ -14,12 +14,12 @@ timeout 300 $SMALL > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 timeout 300 $SMALL > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention|preprocess|layernorm|final_norm" -s 0 -c 11 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_tn|attention_split|preprocess|layernorm|final_norm" -s 0 -c 11 -f -o gpurun_out/prof_layer0 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 # the remaining kernels of the step (final norm + token mean, row statistics, prefix fill) ...
 timeout 300 $SMALL > gpurun_out/plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:"final_norm_mean|row_stats|fill_prefix" -c 3 -f -o gpurun_out/prof_tail $SMALL > gpurun_out/ncu_tail.log 2>&1
+    -k regex:"final_norm_mean|row_stats|fill_prefix|attention_exact" -c 4 -f -o gpurun_out/prof_tail $SMALL > gpurun_out/ncu_tail.log 2>&1
 echo "ncu tail rc=$?"
 # ... and K3 + both forms of K4 at the bench's sizes (second round of tools/topk_profile.py: 5 launches after the first 5)
 timeout 300 python tools/topk_profile.py > gpurun_out/plain4.log 2>&1 && \

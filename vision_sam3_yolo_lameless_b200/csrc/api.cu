@@ -188,7 +188,6 @@ struct cre_ctx {
     int device;
     int num_sms;
     uint8_t* fold_buf = nullptr;
-    int* scan_counter = nullptr;   // "CTAs finished" counter of the serving-form gallery scan (zero between calls)
     std::vector<FoldedLinear> fold_qkv, fold_up;
     std::map<std::pair<int, int>, DevTable> resize_tables;
     std::map<std::pair<int, int>, RopeTable> rope_tables;
@@ -201,12 +200,27 @@ struct cre_ctx {
 
 namespace {
 
-int get_resize_table(cre_ctx* ctx, int in, int out, DevTable* t) {
+// First use of an (input size, output size) pair builds its antialias table on the host and uploads it ON THE CALLER'S STREAM
+// (pageable source: the driver stages it before cudaMemcpyAsync returns, and the copy is ordered before the kernels that follow on
+// that stream -- also on cudaStreamNonBlocking streams).  That first call allocates (cudaMalloc: not capturable in a CUDA graph --
+// warm the sizes up before capturing).  The cache is bounded: beyond kMaxCachedTables distinct sizes it is flushed after a stream
+// synchronisation (a service sees a handful of camera resolutions; ROI crops do not go through this cache at all).
+constexpr size_t kMaxCachedTables = 64;
+int get_resize_table(cre_ctx* ctx, int in, int out, DevTable* t, cudaStream_t stream) {
     auto key = std::make_pair(in, out);
     auto it = ctx->resize_tables.find(key);
     if (it != ctx->resize_tables.end()) {
         *t = it->second;
         return 0;
+    }
+    if (ctx->resize_tables.size() >= kMaxCachedTables) {
+        CRE_CUDA_OK(cudaStreamSynchronize(stream));       // no queued kernel may still read a table that is about to be freed
+        for (auto& kv : ctx->resize_tables) {
+            cudaFree(kv.second.lo);
+            cudaFree(kv.second.cnt);
+            cudaFree(kv.second.w);
+        }
+        ctx->resize_tables.clear();
     }
     std::vector<int32_t> lo, cnt;
     std::vector<float> w;
@@ -219,9 +233,9 @@ int get_resize_table(cre_ctx* ctx, int in, int out, DevTable* t) {
     CRE_CUDA_OK(cudaMalloc(&d.lo, lo.size() * 4));
     CRE_CUDA_OK(cudaMalloc(&d.cnt, cnt.size() * 4));
     CRE_CUDA_OK(cudaMalloc(&d.w, w.size() * 4));
-    CRE_CUDA_OK(cudaMemcpy(d.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
-    CRE_CUDA_OK(cudaMemcpy(d.cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
-    CRE_CUDA_OK(cudaMemcpy(d.w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMemcpyAsync(d.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, stream));
+    CRE_CUDA_OK(cudaMemcpyAsync(d.cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, stream));
+    CRE_CUDA_OK(cudaMemcpyAsync(d.w, w.data(), w.size() * 4, cudaMemcpyHostToDevice, stream));
     ctx->resize_tables[key] = d;
     *t = d;
     return 0;
@@ -229,7 +243,7 @@ int get_resize_table(cre_ctx* ctx, int in, int out, DevTable* t) {
 
 // HF:modeling_dinov3_vit.py:95-121,153-200: patch-centre coordinates in [-1, 1], 16 inverse frequencies,
 // angles = 2*pi*coord*inv_freq laid out [y*f0..f15, x*f0..f15] and tiled twice; fp32 cos / sin.
-int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
+int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t, cudaStream_t stream) {
     auto key = std::make_pair(gh, gw);
     auto it = ctx->rope_tables.find(key);
     if (it != ctx->rope_tables.end()) {
@@ -257,7 +271,7 @@ int get_rope_table(cre_ctx* ctx, int gh, int gw, RopeTable* t) {
     }
     RopeTable r;
     CRE_CUDA_OK(cudaMalloc(&r.axis, tab.size() * 4));
-    CRE_CUDA_OK(cudaMemcpy(r.axis, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    CRE_CUDA_OK(cudaMemcpyAsync(r.axis, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, stream));   // caller's stream, see get_resize_table
     ctx->rope_tables[key] = r;
     *t = r;
     return 0;
@@ -355,13 +369,8 @@ int32_t cre_create(const cre_model_cfg* cfg, const void* packed_weights_dev, int
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     int rc = build_folded_weights(c);   // the packed blob must already hold the weights (it does: see engine.py)
-    if (rc == 0 && (cudaMalloc(&c->scan_counter, 256) != cudaSuccess || cudaMemset(c->scan_counter, 0, 256) != cudaSuccess)) {
-        set_error("cre_create: cannot allocate the scan counter");
-        rc = -2;
-    }
     if (rc) {
         cudaFree(c->fold_buf);
-        cudaFree(c->scan_counter);
         delete c;
         return rc;
     }
@@ -378,7 +387,6 @@ int32_t cre_destroy(cre_ctx* ctx) {
     }
     for (auto& kv : ctx->rope_tables) cudaFree(kv.second.axis);
     cudaFree(ctx->fold_buf);
-    cudaFree(ctx->scan_counter);
     delete ctx;
     return 0;
 }
@@ -416,9 +424,9 @@ int32_t cre_preprocess_patchify(cre_ctx* ctx, const uint8_t* frames_dev, int32_t
     }
     a.out = static_cast<__nv_bfloat16*>(out_patches_dev);
     DevTable ty, tx;
-    int rc = get_resize_table(ctx, h, resize_h, &ty);
+    int rc = get_resize_table(ctx, h, resize_h, &ty, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
-    rc = get_resize_table(ctx, w, resize_w, &tx);
+    rc = get_resize_table(ctx, w, resize_w, &tx, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
     a.ty = {ty.lo, ty.cnt, ty.w, ty.kmax, ty.in, ty.out};
     a.tx = {tx.lo, tx.cnt, tx.w, tx.kmax, tx.in, tx.out};
@@ -520,7 +528,7 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
     const int M = static_cast<int>(M64), D = c.hidden, F = c.mlp, PK = 3 * c.patch * c.patch;
     const int cg = g_default_cg;
     RopeTable rope;
-    int rc = get_rope_table(ctx, grid_h, grid_w, &rope);
+    int rc = get_rope_table(ctx, grid_h, grid_w, &rope, stream);
     if (rc) return rc;
 
     // attention overflow flags: one "any" slot per layer + the per-unit flags (which every layer leaves zeroed again)
@@ -667,26 +675,28 @@ int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k) {
     const int kp = k < CRE_TOPK_MAX ? k : CRE_TOPK_MAX;      // candidates kept per partial list and pass
     const int64_t a = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
     const int64_t part = align_up(static_cast<int64_t>(q) * kMaxSlots * kp * 4, 1024);
-    return a + 2 * part;
+    return a + 2 * part + 1024;      // + the "CTAs finished" counter of the serving-form scan (per call: two streams never share it)
 }
 
 // One pass of the gallery scan: the kp best candidates per query that come strictly AFTER (cut_s, cut_i) in the (score desc, index
 // asc) order (cut_s == NULL: no cutoff), written to out_* with row stride out_stride.
 static int gallery_topk_pass(cre_ctx* ctx, const float* queries_dev, int q, int dim, const void* gallery_dev, int rows, int row_base, int kp,
-                             uint8_t* sp, float* out_scores, int32_t* out_idx, int out_stride, const float* cut_s, const int32_t* cut_i,
+                             uint8_t* sp, int64_t counter_off, float* out_scores, int32_t* out_idx, int out_stride, const float* cut_s, const int32_t* cut_i,
                              float* dump_scores_dev, bool first_pass, cudaStream_t stream) {
     __nv_bfloat16* a_hilo = reinterpret_cast<__nv_bfloat16*>(sp);
     const int64_t a_bytes = align_up(static_cast<int64_t>(q) * 2 * dim * 2, 1024);
     const int64_t part_bytes = align_up(static_cast<int64_t>(q) * kMaxSlots * kp * 4, 1024);
     float* part_s = reinterpret_cast<float*>(sp + a_bytes);
     int32_t* part_i = reinterpret_cast<int32_t*>(sp + a_bytes + part_bytes);
+    int* counter = reinterpret_cast<int*>(sp + counter_off);
 
     // serving form (Q <= 2: one message = one query): HBM-streaming scan on the CUDA cores, one partial list per CTA
-    if (g_scan_small) {
+    if (g_scan_small && q <= 2) {
         int small_slots = 2 * ctx->num_sms;
         if (small_slots > kMaxSlots) small_slots = kMaxSlots;
+        if (first_pass) CRE_CUDA_OK(cudaMemsetAsync(counter, 0, 4, stream));   // the kernel's last CTA leaves it at 0 for the later passes
         const int took = launch_gallery_scan_small(queries_dev, q, dim, gallery_dev, rows, row_base, kp, part_s, part_i, small_slots,
-                                                   dump_scores_dev, ctx->scan_counter, out_scores, out_idx, out_stride, cut_s, cut_i, stream);
+                                                   dump_scores_dev, counter, out_scores, out_idx, out_stride, cut_s, cut_i, stream);
         if (took != 0) return took < 0 ? took : 0;     // the kernel's last CTA has merged the partial lists into the result
     }
     const int workers = gemm_workers(q, rows, 1, ctx->num_sms);
@@ -730,7 +740,7 @@ int32_t cre_gallery_topk(cre_ctx* ctx, const float* queries_dev, int32_t q, int3
     uint8_t* sp = static_cast<uint8_t*>(scratch_dev);
     for (int done = 0; done < k; done += CRE_TOPK_MAX) {
         const int kp = k - done < CRE_TOPK_MAX ? k - done : CRE_TOPK_MAX;
-        const int rc = gallery_topk_pass(ctx, queries_dev, q, dim, gallery_dev, rows, row_base, kp, sp, out_scores_dev + done, out_idx_dev + done,
+        const int rc = gallery_topk_pass(ctx, queries_dev, q, dim, gallery_dev, rows, row_base, kp, sp, need - 1024, out_scores_dev + done, out_idx_dev + done,
                                          k, done ? out_scores_dev + done - 1 : nullptr, done ? out_idx_dev + done - 1 : nullptr,
                                          done ? nullptr : dump_scores_dev, done == 0, stream);
         if (rc) return rc;
