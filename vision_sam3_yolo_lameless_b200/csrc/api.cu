@@ -533,8 +533,6 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
 
     // attention overflow flags: one "any" slot per layer + the per-unit flags (which every layer leaves zeroed again)
     CRE_CUDA_OK(cudaMemsetAsync(ws.attn_flags, 0, static_cast<size_t>(ws.attn_flag_bytes), stream));
-    rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
-    if (rc) return rc;
     {   // patch embedding: [n*P, 768] x [D, 768]^T + bias -> token rows prefix.. of x
         GemmParams p = base_params(n * P, D, PK);
         p.bias = ctx->w<float>(-1, CRE_B_PATCH);
@@ -546,6 +544,8 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
         rc = launch_gemm(EPI_PATCH, cg, patches_dev, PK, ctx->w<void>(-1, CRE_W_PATCH), PK, p, ctx->num_sms, stream);
         if (rc) return rc;
     }
+    rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
+    if (rc) return rc;
     const bool fold = g_ln_fold != 0;
     const int S = ln_slots(&c), SS = ln_stride(&c);
     if (fold) {   // seed of the folded chain: statistics + centred bf16 copy of the embedded tokens

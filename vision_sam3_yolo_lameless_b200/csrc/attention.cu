@@ -714,11 +714,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
 // two fp32 -> packed bf16x2, round-half-up in magnitude, on the ALU pipe (F2FP is an XU-pipe instruction, and the XU pipe -- the
 // exponentials -- is what bounds this kernel).  Same 2^-9 relative error bound as round-to-nearest-even; inf stays inf.
 __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {

@@ -113,12 +113,34 @@ static int make_tmap_out(CUtensorMap* out, bool bf16, void* base, int ldo, const
     return 0;
 }
 
+// EPI_PATCH: the token matrix x as [frame][token][col] fp32 -- 32-row x 32-column boxes, clipped at a frame's last token
+static int make_tmap_tokens(CUtensorMap* out, float* base, int ldo, const GemmParams& p) {
+    EncodeTiledFn fn = get_encode_fn();
+    CRE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CRE_REQUIRE(base != nullptr && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (static_cast<int64_t>(ldo) * 4) % 16 == 0,
+                "gemm: token matrix must be 16-byte aligned");
+    CRE_REQUIRE(p.patches_per_frame >= 32 && p.tokens_per_frame == p.patches_per_frame + p.prefix_tokens && p.M % p.patches_per_frame == 0,
+                "gemm: PATCH epilogue needs >= 32 patches per frame and M = frames * patches (M=%d, P=%d)", p.M, p.patches_per_frame);
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.tokens_per_frame),
+                          static_cast<cuuint64_t>(p.M / p.patches_per_frame)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldo) * 4, static_cast<cuuint64_t>(p.tokens_per_frame) * ldo * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (token matrix) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 template <int EPI, int CG, int STAGES = default_stages_epi(EPI, CG)>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                       cudaStream_t stream) {
     using Cfg = GemmCfg<EPI, CG, STAGES>;
     CUtensorMap tout = ta, tout2 = ta;   // placeholders for the epilogues that store directly
-    if constexpr (epi_tma_store(EPI)) {
+    if constexpr (EPI == EPI_PATCH) {
+        const int rc = make_tmap_tokens(&tout, p.out_f32, p.ldo, p);
+        if (rc) return rc;
+    } else if constexpr (epi_tma_store(EPI)) {
         const bool bf16 = epi_out_bf16(EPI);
         const int rc = make_tmap_out(&tout, bf16, bf16 ? static_cast<void*>(p.out_bf16) : static_cast<void*>(p.out_f32), p.ldo, p);
         if (rc) return rc;

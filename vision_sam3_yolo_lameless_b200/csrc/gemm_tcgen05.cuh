@@ -31,7 +31,7 @@ enum GemmEpi : int {
     EPI_QKV = 2,    // bias, rotary on q/k columns of patch tokens, q * q_scale -> bf16  (TMA store, [M, 3*hidden])
     EPI_GELU = 3,   // out_bf16 = gelu_erf(acc + bias)                                  (TMA store)
     EPI_RESID = 4,  // out_f32[m, n] += scale[n] * (acc + bias[n])                      (TMA reduce-add, in place)
-    EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]   (patch rows -> token rows, direct stores)
+    EPI_PATCH = 5,  // out_f32[token_row(m), n] = acc + bias[n]   (patch rows -> token rows; TMA stores into a [frame][token][col] map)
     EPI_TOPK = 6,   // running per-row top-k over the columns this CTA visits  (gallery scan)
     EPI_NONE = 7,   // accumulators are dropped (main-loop tuning only)
     EPI_RESID_LN = 8,  // v = x + scale * (acc + bias): x (TMA load -> store), bf16(v - pivot) and per-row LayerNorm partials
@@ -97,7 +97,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;  // one epilogue warp's staging tile: 32 rows x 128 bytes
 
 constexpr bool epi_tma_store(int epi) {
-    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID || epi_resid_ln(epi);
+    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_PATCH || epi_resid_ln(epi);
 }
 constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
@@ -208,6 +208,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
                  "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -737,7 +742,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (slot_id == 0) sn[0] = pivot;
                 }
             } else if constexpr (epi_tma_store(EPI)) {
-                // EPI_F32 / EPI_RESID: 32-column chunks, fp32 out (store / reduce-add)
+                // EPI_F32 / EPI_RESID / EPI_PATCH: 32-column chunks, fp32 out (store / reduce-add / store into the token-row map)
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = ncol0 + c * 32;
@@ -764,10 +769,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     for (int u = 0; u < 8; ++u)
                         stage_store(u, make_uint4(__float_as_uint(x[4 * u]), __float_as_uint(x[4 * u + 1]),
                                                   __float_as_uint(x[4 * u + 2]), __float_as_uint(x[4 * u + 3])));
-                    stage_commit(n0, row_base);
+                    if constexpr (EPI == EPI_PATCH) {
+                        // Patch row m = frame * P + r lands on token row prefix + r of its frame.  tmap_out is [frame][token][col]: the
+                        // slab's 32 rows go out as ONE box at (frame, prefix + r0); rows past the frame's last token are clipped by the
+                        // map (as are slab rows >= M: their frame index is out of range).  One slab in six runs into the next frame: its
+                        // rows >= s1 -- that frame's first patches -- are stored straight from registers.
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        const int f0 = row_base / p.patches_per_frame, r0 = row_base - f0 * p.patches_per_frame;
+                        const int s1 = p.patches_per_frame - r0;               // slab rows that belong to frame f0
+                        if (lane == 0) {
+                            tma_store_3d(&tmap_out, stage_u32, n0, p.prefix_tokens + r0, f0);
+                            bulk_commit();
+                        }
+                        if (lane >= s1 && row_ok) {
+                            float4* o = reinterpret_cast<float4*>(p.out_f32 + (static_cast<size_t>(f0 + 1) * p.tokens_per_frame +
+                                                                               p.prefix_tokens + (lane - s1)) * p.ldo + n0);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) o[j4] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                        }
+                    } else {
+                        stage_commit(n0, row_base);
+                    }
                 }
             } else {
-                // EPI_PATCH / EPI_TOPK: direct path
+                // EPI_TOPK: running per-row top-k, no output tile
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = ncol0 + c * 32;
@@ -808,20 +834,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                     }
                                 }
                             }
-                        }
-                    } else {  // EPI_PATCH
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + j4);
-                            x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
-                        }
-                        if (row_ok) {
-                            const size_t orow = static_cast<size_t>(row / p.patches_per_frame) * p.tokens_per_frame +
-                                                p.prefix_tokens + row % p.patches_per_frame;
-                            float4* o = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + n0);
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4)
-                                o[j4] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
                         }
                     }
                 }
