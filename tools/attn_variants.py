@@ -12,12 +12,13 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 VARIANTS = {
     "single_S": {"attention_split": 0},
+    "split_default": {},
     "split_delay0": {"attention_split_delay": 0},
     "split_delay2400": {"attention_split_delay": 2400},
-    "split_delay3200": {"attention_split_delay": 3200},
     "split_delay4000": {"attention_split_delay": 4000},
-    "split_delay3200_poly0": {"attention_split_delay": 3200, "attention_poly": 0},
-    "split_delay3200_pv1": {"attention_split_delay": 3200, "attention_split_mode": 2},
+    "split_poly0": {"attention_poly": 0},
+    "split_poly50": {"attention_poly": 2},
+    "split_pv1": {"attention_split_mode": 2},
 }
 
 
