@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--resize", type=int, default=224, help="model input size (configs[2]: 518 or 592 with --height/--width equal to it)")
     ap.add_argument("--cta-group", type=int, default=0, help="0 = library default")
     ap.add_argument("--ln-fold", type=int, default=-1, help="-1 = library default; 0 = separate LayerNorm launches")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=INT", help="library tuning knob for A/B runs (cre_set_tuning); repeatable")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -321,6 +322,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         set_cta_group(args.cta_group)
     if args.ln_fold >= 0:
         _lib.set_tuning("ln_fold", args.ln_fold)
+    for kv in args.tune:                         # A/B runs of a library knob (include/cre.h cre_set_tuning), e.g. --tune resid_split=0
+        key, _, val = kv.partition("=")
+        _lib.set_tuning(key, int(val))
 
     model = random_init_vit(args.model)
     cfg = VitConfig.from_hf(model.config)
@@ -454,7 +458,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "how": "CUDA events around every launch (cre_profile_start/stop) in one instrumented step after the timed region"}
         # the ViT forward alone (north_star's tensor-peak target is quoted "on the ViT-B/16 forward"): every launch between the
         # patch rows and the frame embeddings, i.e. the instrumented step minus K1, pooling and re-ID
-        fwd_names = [n for n in kernels if n in _lib.FLOP_KERNELS or n in ("row_stats", "layernorm", "final_norm_mean", "fill_prefix")]
+        fwd_names = [n for n in kernels if n in _lib.FLOP_KERNELS or n in ("row_stats", "layernorm", "final_norm_mean", "fill_prefix", "attention_exact")]
         fwd_ms = sum(kernels[n]["ms"] for n in fwd_names)
         fwd_tf = frames_total * cfg.flops_per_frame(grid, grid) / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
         roofline["vit_forward"] = {"tflops": fwd_tf, "frac_of_burst_peak": fwd_tf / tf_burst if fwd_tf else None,

@@ -160,7 +160,9 @@ enum cre_gemm_epilogue {
     CRE_EPI_RESID = 4, /* out_f32 += scale * (acc + bias)   (in place)  */
     CRE_EPI_NONE = 7,  /* accumulators dropped: main-loop timing only   */
     CRE_EPI_RESID_LN = 8, /* cre_gemm_ln only: x += scale * (acc + bias), bf16(x - pivot), LayerNorm statistics */
-    CRE_EPI_RESID_LN3 = 9 /* same results; one x tile in flight per warp, one pipeline stage more (long K) */
+    CRE_EPI_RESID_LN3 = 9, /* same results; one x tile in flight per warp, one pipeline stage more (long K) */
+    CRE_EPI_RESID_SP = 10, /* cre_gemm_ln only: the residual stream as two bf16 halves around the row pivot (what cre_vit_forward runs) */
+    CRE_EPI_RESID_SP3 = 11 /* same results; one chunk slot per warp, more pipeline stages (long K) */
 };
 /* D[m, n] = A[m, k] (bf16 row-major) * B[n, k]^T (bf16 row-major); k % 64 == 0; n % 64 == 0 for the bf16-out
  * epilogues, n % 32 == 0 for the fp32-out ones; out_dev 16-byte aligned (written by TMA).
@@ -178,8 +180,15 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
  *   cre_gemm_ln:         epilogue CRE_EPI_BF16 | CRE_EPI_GELU: out bf16 [m, n] = (gelu)(LN-folded A B^T), A = the centred bf16
  *                        rows, bias = c2, stats_in = their statistics rows (ln_dim = k);
  *                        epilogue CRE_EPI_RESID_LN (n == ln_dim, n % 256 == 0): out f32 [m, n] (in place) += scale * (A B^T + bias),
- *                        out_xb bf16 [m, n] = out - pivot (pivot = the row mean recorded in stats_in), stats_out = new rows. */
+ *                        out_xb bf16 [m, n] = out - pivot (pivot = the row mean recorded in stats_in), stats_out = new rows;
+ *                        epilogue CRE_EPI_RESID_SP (same shape rules): the residual stream x = pivot + hi + lo is held as
+ *                        hi = out_xb bf16 [m, n] and lo = out bf16 [m, n] (pivot = slot 0 of its statistics row); both are updated
+ *                        in place to the halves of x + scale * (A B^T + bias) around the NEW pivot (the row mean stats_in
+ *                        records), stats_out = new rows.  8 bytes of HBM traffic per element instead of RESID_LN's 10.
+ *   cre_row_stats_split: cre_row_stats + out_lo bf16 [rows, dim] = bf16((x - mean) - out_hi): seeds the split stream. */
 int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_xb_dev, float* out_stats_dev, void* stream);
+int32_t cre_row_stats_split(const float* x_dev, int32_t rows, int32_t dim, void* out_hi_dev, void* out_lo_dev, float* out_stats_dev,
+                            void* stream);
 int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
                             int32_t k, int32_t scaled_rows, float row_scale, void* out_w_dev, float* out_c1_dev, float* out_c2_dev,
                             void* stream);
@@ -209,7 +218,8 @@ enum cre_kernel_id {
     CRE_K_ATTENTION = 5, CRE_K_GEMM_RESID = 6, CRE_K_GEMM_GELU = 7, CRE_K_FINAL_NORM_MEAN = 8, CRE_K_POOL_CLIPS = 9,
     CRE_K_SPLIT_HI_LO = 10, CRE_K_FILL_TOPK = 11, CRE_K_GEMM_TOPK = 12, CRE_K_MERGE_TOPK = 13, CRE_K_GEMM_PLAIN = 14,
     CRE_K_GALLERY_UPDATE = 15, CRE_K_ROW_STATS = 16, CRE_K_FOLD_LN = 17, CRE_K_ROI_TABLES = 18, CRE_K_ATTENTION_EXACT = 19,
-    CRE_KERNEL_IDS = 20
+    CRE_K_GEMM_RESID_MLP = 20,   /* residual-update GEMMs with K > N (MLP down projection); CRE_K_GEMM_RESID = the attention-out projection */
+    CRE_KERNEL_IDS = 21
 };
 int64_t cre_kernel_launches(void);
 int32_t cre_profile_start(int32_t max_launches);
@@ -221,7 +231,8 @@ int32_t cre_set_cta_group(int32_t cta_group);
 /* Generic tuning knobs for the benchmark harness: "cta_group" (1 | 2), "gemm_stages" (0 = default, 3..6:
  * TMA pipeline depth of the cre_gemm_bf16 building block), "attention_fast" (1 = persistent TMEM-resident kernel for
  * T <= 256, default; 0 = general kernel), "ln_fold" (1 = LayerNorm folded into the GEMMs, default; 0 = separate LayerNorm
- * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use CRE_EPI_RESID_LN3), "attention_split" (1 = split-S
+ * launches), "resid_ln_deep" (bit 0 / bit 1: attention-out / MLP-down projection use the one-slot form CRE_EPI_RESID_LN3 / _SP3),
+ * "resid_split" (1 = residual stream as two bf16 halves, CRE_EPI_RESID_SP, default; 0 = fp32 stream + bf16 copy, CRE_EPI_RESID_LN), "attention_split" (1 = split-S
  * kernel for 160 < T <= 208, default), "attention_poly" (0 | 1 | 2: share of that kernel's exponentials on the FMA pipe),
  * "attention_split_mode" (bit 0: direct global stores of O, bit 1: PV of the second key half in one piece), "attention_split_delay"
  * (SM cycles by which the second query-tile group of that kernel trails the first).  Every setting gives results inside the parity tolerances.  Unknown keys return -1. */

@@ -165,6 +165,48 @@ def test_gemm_resid_layernorm_producer(engine_small, cg, epi, m, n, k):
     assert rel_err(out, want) < 8e-3
 
 
+@pytest.mark.parametrize("epi", [_lib.EPI_RESID_SP, _lib.EPI_RESID_SP3])
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(1000, 768, 768), (515, 768, 3072), (300, 1024, 1024), (1, 768, 64), (40021, 768, 768)])
+def test_gemm_resid_split_producer(engine_small, cg, epi, m, n, k):
+    """The residual stream as two bf16 halves around the row pivot (what cre_vit_forward runs): x = pivot + hi + lo.  Two chained
+    updates x += scale * (a W^T + b): the reconstructed stream stays within 2^-16 of the centred magnitude of the fp32 result (bf16
+    pair = 16 significant bits), the statistics describe the NEW x, the pivot moves to the previous row mean, hi alone is the
+    bf16 A operand of the next folded GEMM, and the folded consumer on (hi, stats) reproduces LN(x_new) W2^T."""
+    eng, dev = engine_small, engine_small.device
+    g = torch.Generator(device=dev).manual_seed(m * 3 + k)
+    x0 = torch.randn(m, n, device=dev, generator=g) * 2 + torch.randn(m, 1, device=dev, generator=g) * 3
+    x0[:, 7] += 60.0                                                                            # a massive-activation channel
+    hi, lo, stats = eng.row_stats_split(x0)
+    mean0 = x0.mean(dim=1, keepdim=True)
+    assert ((mean0 + hi.float() + lo.float()) - x0).abs().max() < 2.0 ** -15 * (x0 - mean0).abs().max()
+    ref = x0
+    for step in range(2):
+        a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+        bias, scale = torch.randn(n, device=dev, generator=g), torch.rand(n, device=dev, generator=g) + 0.5
+        prev_mean = ref.mean(dim=1, keepdim=True)
+        ref = ref + scale * (a.float() @ w.float().t() + bias)
+        hi, lo, stats = eng.gemm_ln(a, w, epi, stats, n, bias=bias, scale=scale, out=(hi, lo), cta_group=cg)
+        pivot, mean, var = _stats_combine(stats, n)
+        rd = ref.double().cpu()
+        assert (pivot - prev_mean.double().cpu()[:, 0]).abs().max() < 1e-4                      # pivot = the mean at the previous norm
+        assert (mean - rd.mean(dim=1)).abs().max() < 1e-4
+        assert ((var - rd.var(dim=1, unbiased=False)).abs() / rd.var(dim=1, unbiased=False)).max() < 1e-4
+        x = stats[:, :1] + (hi.float() + lo.float())
+        cen = (ref - prev_mean).abs().amax(dim=1, keepdim=True)
+        assert ((x - ref).abs() / cen).max() < (step + 1) * 2.0 ** -15 + 2e-6                     # split rounding + the fp32 update itself
+        assert rel_err(hi, ref - prev_mean) < 5e-3                                              # bf16 of x - pivot
+    n2 = 256
+    w2 = (torch.randn(n2, n, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    gamma, beta = torch.rand(n, device=dev, generator=g) + 0.5, torch.randn(n, device=dev, generator=g) * 0.3
+    b2 = torch.randn(n2, device=dev, generator=g)
+    wf, c1, c2 = eng.fold_ln_weights(w2, gamma, beta, b2)
+    out = eng.gemm_ln(hi, wf, _lib.EPI_BF16, stats, n, bias=c2, c1=c1, cta_group=cg)
+    want = torch.nn.functional.layer_norm(ref, (n,), gamma, beta, 1e-5) @ w2.float().t() + b2
+    assert rel_err(out, want) < 8e-3
+
+
 def _attention_case(engine, t, n, heads, q_scale=0.125, plant=None, seed=None):
     """qkv with N(0,1) q / k / v (q times q_scale) -> (kernel output, fp32 softmax reference of HF:modeling_dinov3_vit.py:210-235
     on the same bf16 inputs).  plant = (key, boost): that key's logit is lifted `boost` nats above every other key of every row."""

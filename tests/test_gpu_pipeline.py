@@ -20,10 +20,11 @@ SUBJECTS = {"nats": {"subjects": {"pipeline_dinov3": "pipeline.dinov3", "video_p
             "qdrant": {"collection_name": "cow_embeddings"}}
 
 
-@pytest.mark.parametrize("ln_fold", [1, 0])
+@pytest.mark.parametrize("ln_fold,resid_split", [(1, 1), (1, 0), (0, 0)])
 @pytest.mark.parametrize("cg", [1, 2])
-def test_forward_tokens_vs_fp32_oracle(engine_b, cg, ln_fold):
-    """Both block formulations (LayerNorm folded into the GEMMs = default; separate LayerNorm launches) and both tile shapes."""
+def test_forward_tokens_vs_fp32_oracle(engine_b, cg, ln_fold, resid_split):
+    """All three block formulations (LayerNorm folded into the GEMMs with the residual stream as two bf16 halves = default; folded
+    with an fp32 stream; separate LayerNorm launches) and both tile shapes."""
     from vision_sam3_yolo_lameless_b200 import _lib
     from vision_sam3_yolo_lameless_b200.engine import set_cta_group
     eng, model = engine_b
@@ -32,12 +33,14 @@ def test_forward_tokens_vs_fp32_oracle(engine_b, cg, ln_fold):
     ref_tok = vit_ref.vit_forward(model.state_dict(), torch.from_numpy(pv), heads=12, layers=12)
     set_cta_group(cg)
     _lib.set_tuning("ln_fold", ln_fold)
+    _lib.set_tuning("resid_split", resid_split)
     try:
         patches = eng.preprocess(torch.from_numpy(fr).to(eng.device), bgr=True)
         emb, tok = eng.forward_patches(patches, 5, want_tokens=True)
     finally:
         set_cta_group(2)
         _lib.set_tuning("ln_fold", 1)
+        _lib.set_tuning("resid_split", 1)
     tok, emb = tok.cpu(), emb.cpu()
     assert torch.isfinite(tok).all()
     assert ((tok - ref_tok).abs().max() / ref_tok.abs().max()).item() < 2e-2        # bf16 operands through 12 layers

@@ -26,12 +26,12 @@ BF16_KINDS = {W_PATCH, W_QKV, W_O, W_UP, W_DOWN}
 # enum cre_kernel_id
 KERNEL_NAMES = ["preprocess", "fill_prefix", "gemm_patch", "layernorm", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu",
                 "final_norm_mean", "pool_clips", "split_hi_lo", "fill_topk", "gemm_topk", "merge_topk", "gemm_plain",
-                "gallery_update", "row_stats", "fold_ln_weights", "roi_tables", "attention_exact"]
+                "gallery_update", "row_stats", "fold_ln_weights", "roi_tables", "attention_exact", "gemm_resid_mlp"]
 # kernels whose `work` is FLOPs (tensor-bound); the others report bytes (HBM-bound)
-FLOP_KERNELS = {"gemm_patch", "gemm_qkv", "attention", "gemm_resid", "gemm_gelu", "gemm_plain"}
+FLOP_KERNELS = {"gemm_patch", "gemm_qkv", "attention", "gemm_resid", "gemm_resid_mlp", "gemm_gelu", "gemm_plain"}
 
 # enum cre_gemm_epilogue
-EPI_BF16, EPI_F32, EPI_GELU, EPI_RESID, EPI_NONE, EPI_RESID_LN, EPI_RESID_LN3 = 0, 1, 3, 4, 7, 8, 9
+EPI_BF16, EPI_F32, EPI_GELU, EPI_RESID, EPI_NONE, EPI_RESID_LN, EPI_RESID_LN3, EPI_RESID_SP, EPI_RESID_SP3 = 0, 1, 3, 4, 7, 8, 9, 10, 11
 
 
 class CreError(RuntimeError):
@@ -77,6 +77,7 @@ PROTOTYPES = {
     "cre_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "cre_layernorm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "cre_row_stats": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "cre_row_stats_split": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cre_fold_ln_weights": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "cre_gemm_ln": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "cre_attention": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),

@@ -111,7 +111,8 @@ struct Workspace {
     __nv_bfloat16* h;    // [M, D] LayerNorm output / attention output
     __nv_bfloat16* qkv;  // [M, 3D] q (pre-scaled, rotated) | k (rotated) | v
     __nv_bfloat16* mlp;  // [M, F]
-    __nv_bfloat16* xb;   // [M, D] bf16(x - row pivot): A operand of the LayerNorm-folded GEMMs
+    __nv_bfloat16* xb;   // [M, D] bf16(x - row pivot): A operand of the LayerNorm-folded GEMMs = HIGH half of the split residual stream
+    __nv_bfloat16* xl;   // [M, D] bf16(x - row pivot - xb): its LOW half (resid_split = 1: x itself is only the patch embedding's output)
     float* stats[2];     // [M, ln_stride] LayerNorm statistics rows (ping-pong between the two norms of a block)
     int* attn_flags;     // [layers] x [64-int "any" slot] then [frames * heads] unit flags: attention overflow tracking
     int64_t attn_flag_bytes;
@@ -131,6 +132,7 @@ Workspace carve(const cre_model_cfg* c, int frames, int gh, int gw, void* base) 
     w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * 2));
     w.mlp = reinterpret_cast<__nv_bfloat16*>(take(M * F * 2));
     w.xb = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+    w.xl = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
     w.stats[0] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
     w.stats[1] = reinterpret_cast<float*>(take(M * ln_stride(c) * 4));
     w.attn_flag_bytes = (64LL * c->layers + static_cast<int64_t>(frames) * c->heads) * 4;
@@ -291,6 +293,8 @@ GemmParams base_params(int M, int N, int K) {
 int g_default_cg = 2;  // CTA pairs: less smem traffic per FLOP, measured 3-5 % faster in the full step
 constexpr float kQScale = 0.125f;   // head_dim^-0.5, head_dim = 64 (HF:modeling_dinov3_vit.py:284); folded into the q rows
 int g_resid_ln_deep = 2;   // bit 0: attention-out projection, bit 1: MLP down projection use EPI_RESID_LN3 (1 x tile, 5 stages)
+int g_resid_split = 1; // 1 (with ln_fold): the residual stream lives in HBM as two bf16 halves around the row pivot (EPI_RESID_SP);
+                       // 0: fp32 stream + a bf16 copy (EPI_RESID_LN)
 int g_ln_fold = 1;     // 1: LayerNorm folded into the GEMMs (no LayerNorm kernel in the blocks); 0: separate LayerNorm launches
 
 // LN1 -> q/k/v and LN2 -> up projections of every layer, folded once
@@ -547,9 +551,10 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
     rc = launch_fill_prefix(ws.x, ctx->w<float>(-1, CRE_PREFIX), n, T, prefix, D, stream);
     if (rc) return rc;
     const bool fold = g_ln_fold != 0;
+    const bool split = fold && g_resid_split != 0;
     const int S = ln_slots(&c), SS = ln_stride(&c);
-    if (fold) {   // seed of the folded chain: statistics + centred bf16 copy of the embedded tokens
-        rc = launch_row_stats(ws.x, M, D, SS, ws.xb, ws.stats[0], stream);
+    if (fold) {   // seed of the folded chain: statistics + centred bf16 copy of the embedded tokens (split: + its low half)
+        rc = launch_row_stats(ws.x, M, D, SS, ws.xb, split ? ws.xl : nullptr, ws.stats[0], stream);
         if (rc) return rc;
     }
     for (int l = 0; l < c.layers; ++l) {
@@ -603,14 +608,16 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             p.ldo = D;
             if (fold) {
                 p.out_bf16 = ws.xb;
+                p.x_lo = ws.xl;
                 p.ldo2 = D;
                 p.ln_stats_in = ws.stats[0];
                 p.ln_stats_out = ws.stats[1];
                 p.ln_slots = S;
                 p.ln_stride = SS;
             }
-            rc = launch_gemm(fold ? ((g_resid_ln_deep & 1) ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.h, D, ctx->w<void>(l, CRE_W_O), D, p,
-                             ctx->num_sms, stream);
+            const bool deep = (g_resid_ln_deep & 1) != 0;
+            rc = launch_gemm(split ? (deep ? EPI_RESID_SP3 : EPI_RESID_SP) : fold ? (deep ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.h, D,
+                             ctx->w<void>(l, CRE_W_O), D, p, ctx->num_sms, stream);
             if (rc) return rc;
         }
         if (!fold) {
@@ -634,7 +641,7 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             if (rc) return rc;
         }
         {   // MLP down projection; the last block feeds the final norm (fp32 x only)
-            const bool ln_out = fold && l + 1 < c.layers;
+            const bool ln_out = split || (fold && l + 1 < c.layers);   // split: the final norm reads the halves too
             GemmParams p = base_params(M, D, F);
             p.bias = ctx->w<float>(l, CRE_B_DOWN);
             p.scale = ctx->w<float>(l, CRE_LS2);
@@ -642,19 +649,21 @@ int32_t cre_vit_forward(cre_ctx* ctx, const void* patches_dev, int32_t n, int32_
             p.ldo = D;
             if (ln_out) {
                 p.out_bf16 = ws.xb;
+                p.x_lo = ws.xl;
                 p.ldo2 = D;
                 p.ln_stats_in = ws.stats[1];
                 p.ln_stats_out = ws.stats[0];
                 p.ln_slots = S;
                 p.ln_stride = SS;
             }
-            rc = launch_gemm(ln_out ? ((g_resid_ln_deep & 2) ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.mlp, F, ctx->w<void>(l, CRE_W_DOWN), F,
-                             p, ctx->num_sms, stream);
+            const bool deep = (g_resid_ln_deep & 2) != 0;
+            rc = launch_gemm(split ? (deep ? EPI_RESID_SP3 : EPI_RESID_SP) : ln_out ? (deep ? EPI_RESID_LN3 : EPI_RESID_LN) : EPI_RESID, cg, ws.mlp,
+                             F, ctx->w<void>(l, CRE_W_DOWN), F, p, ctx->num_sms, stream);
             if (rc) return rc;
         }
     }
-    return launch_final_norm_mean(ws.x, ctx->w<float>(-1, CRE_LN_F_G), ctx->w<float>(-1, CRE_LN_F_B), n, T, D, c.ln_eps,
-                                  out_frame_emb_dev, out_tokens_dev, stream);
+    return launch_final_norm_mean(split ? nullptr : ws.x, ws.xb, ws.xl, ws.stats[0], SS, ctx->w<float>(-1, CRE_LN_F_G),
+                                  ctx->w<float>(-1, CRE_LN_F_B), n, T, D, c.ln_eps, out_frame_emb_dev, out_tokens_dev, stream);
 }
 
 int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_dev, int32_t clips, int32_t dim,
@@ -781,8 +790,15 @@ int32_t cre_gemm_bf16(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_
 
 int32_t cre_row_stats(const float* x_dev, int32_t rows, int32_t dim, void* out_xb_dev, float* out_stats_dev, void* stream) {
     CRE_REQUIRE(x_dev != nullptr && out_xb_dev != nullptr && out_stats_dev != nullptr, "row_stats: NULL argument");
-    return launch_row_stats(x_dev, rows, dim, 2 * (dim / 128) + 4, static_cast<__nv_bfloat16*>(out_xb_dev), out_stats_dev,
+    return launch_row_stats(x_dev, rows, dim, 2 * (dim / 128) + 4, static_cast<__nv_bfloat16*>(out_xb_dev), nullptr, out_stats_dev,
                             static_cast<cudaStream_t>(stream));
+}
+
+int32_t cre_row_stats_split(const float* x_dev, int32_t rows, int32_t dim, void* out_hi_dev, void* out_lo_dev, float* out_stats_dev,
+                            void* stream) {
+    CRE_REQUIRE(x_dev != nullptr && out_hi_dev != nullptr && out_lo_dev != nullptr && out_stats_dev != nullptr, "row_stats_split: NULL argument");
+    return launch_row_stats(x_dev, rows, dim, 2 * (dim / 128) + 4, static_cast<__nv_bfloat16*>(out_hi_dev),
+                            static_cast<__nv_bfloat16*>(out_lo_dev), out_stats_dev, static_cast<cudaStream_t>(stream));
 }
 
 int32_t cre_fold_ln_weights(const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev, int32_t n,
@@ -799,8 +815,8 @@ int32_t cre_gemm_ln(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t 
                     float ln_eps, void* out_dev, void* out_xb_dev, float* stats_out_dev, int32_t cta_group, void* stream) {
     CRE_REQUIRE(ctx != nullptr && a_dev != nullptr && b_dev != nullptr && out_dev != nullptr && stats_in_dev != nullptr,
                 "gemm_ln: NULL argument");
-    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID_LN || epilogue == CRE_EPI_RESID_LN3,
-                "gemm_ln: epilogue %d is not exposed", epilogue);
+    CRE_REQUIRE(epilogue == CRE_EPI_BF16 || epilogue == CRE_EPI_GELU || epilogue == CRE_EPI_RESID_LN || epilogue == CRE_EPI_RESID_LN3 ||
+                    epilogue == CRE_EPI_RESID_SP || epilogue == CRE_EPI_RESID_SP3, "gemm_ln: epilogue %d is not exposed", epilogue);
     CRE_REQUIRE(ln_dim > 0 && ln_dim % 128 == 0 && ln_dim / 128 <= 8, "gemm_ln: ln_dim=%d", ln_dim);
     GemmParams p = base_params(m, n, k);
     p.bias = bias_dev;
@@ -816,6 +832,11 @@ int32_t cre_gemm_ln(cre_ctx* ctx, const void* a_dev, const void* b_dev, int32_t 
         CRE_REQUIRE(out_xb_dev != nullptr && stats_out_dev != nullptr && n == ln_dim, "gemm_ln: RESID_LN needs out_xb, stats_out and n == ln_dim");
         p.out_f32 = static_cast<float*>(out_dev);
         p.out_bf16 = static_cast<__nv_bfloat16*>(out_xb_dev);
+        p.ldo2 = n;
+    } else if (epilogue == CRE_EPI_RESID_SP || epilogue == CRE_EPI_RESID_SP3) {
+        CRE_REQUIRE(out_xb_dev != nullptr && stats_out_dev != nullptr && n == ln_dim, "gemm_ln: RESID_SP needs both halves, stats_out and n == ln_dim");
+        p.x_lo = static_cast<__nv_bfloat16*>(out_dev);          // low half, in place
+        p.out_bf16 = static_cast<__nv_bfloat16*>(out_xb_dev);   // high half, in place
         p.ldo2 = n;
     } else {
         p.out_bf16 = static_cast<__nv_bfloat16*>(out_dev);
@@ -916,6 +937,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     }
     if (strcmp(key, "ln_fold") == 0) {
         g_ln_fold = value != 0;
+        return 0;
+    }
+    if (strcmp(key, "resid_split") == 0) {
+        g_resid_split = value != 0;
         return 0;
     }
 #ifdef CRE_TUNING

@@ -101,11 +101,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2_pos(float lo, float hi) {
     unpack2(mul2(pack2(lo, hi), pack2(1.001953125f, 1.001953125f)), a, b);
     return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632u);
 }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 
 // UMMA shared-memory descriptor for an MN-major operand tile stored [k][64 elements] with 128-byte rows and the
 // 128B swizzle (exactly what a TMA box of 64 bf16 columns x k rows produces): the 64 MN elements of one k are
@@ -173,7 +168,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t tmem_o = tmem_base + kAttnKbMax;   // O accumulator columns [192, 256)
 
     const int q_row0 = frame * T + mtile * 128;
     if (tid == 0) {
@@ -197,18 +191,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int nchunk16 = KB >> 4;
     const int c_lo = side == 0 ? 0 : (nchunk16 + 1) >> 1, c_hi = side == 0 ? (nchunk16 + 1) >> 1 : nchunk16;   // this thread's chunks
 
-    // thread 0: S = Q K^T of one key block into TMEM columns [0, KB)
+    // Warp 0 doubles as TMA producer and MMA issuer.  The whole warp takes these branches (every lane polls the mbarrier) and one
+    // elected lane issues: converged, with warp-uniform operands (the shuffled TMEM base), descriptors and coordinates live in uniform
+    // registers -- from a divergent `tid == 0` branch every tcgen05.mma cost an election loop + four R2UR broadcasts (~90 cycles), and
+    // the 12 + 4 MMAs of a key block held back this warp's own softmax and, through S(kb + 1), everybody else's.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tmem_o_u = tmem_u + kAttnKbMax;   // O accumulator columns [192, 256)
+    // S = Q K^T of one key block into TMEM columns [0, KB)
     auto issue_s = [&](uint32_t k_phase) {
         mbar_wait(bar_k, k_phase);
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(128, KB);
-        const uint64_t dq = umma_desc_k_sw128(s_q);
-        const uint64_t dk = umma_desc_k_sw128(s_k);
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(128, KB);
+            const uint64_t dq = umma_desc_k_sw128(s_q);
+            const uint64_t dk = umma_desc_k_sw128(s_k);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-        umma_commit<1>(bar_s);
+            for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_u, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+            umma_commit<1>(bar_s);
+        }
+        __syncwarp();
     };
-    if (tid == 0) {
+    if (warp == 0) {
         mbar_wait(bar_q, 0);
         issue_s(0);
     }
@@ -222,9 +225,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
         tc_fence_after();
         // S is in TMEM: the K buffer is free -> stream the next block's K in behind the exponentials
-        if (tid == 0 && kb + 1 < p.nblocks) {
-            mbar_arrive_expect_tx(bar_k, KB * 128);
-            tma_load_2d<1>(&tmap_kv, bar_k, s_k, p.k_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+        if (warp == 0 && kb + 1 < p.nblocks) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_k, KB * 128);
+                tma_load_2d<1>(&tmap_kv, bar_k, s_k, p.k_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+            }
+            __syncwarp();
         }
         const int nfull = valid >> 4, rem = valid & 15;
         if (kb == 0) {
@@ -300,23 +306,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_before();
         __syncthreads();
 
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_v, ph);
-            const uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
-            for (int ks = 0; ks < nchunk16; ++ks) {
-                const uint64_t dp = umma_desc_k_sw128(s_p + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
-                const uint64_t dv = umma_desc_mn_sw128(s_v + ks * 2048);   // 16 keys = two 8-row atoms
-                umma_bf16<1>(tmem_o, dp, dv, idesc, (kb | ks) != 0);
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
+                for (int ks = 0; ks < nchunk16; ++ks) {
+                    const uint64_t dp = umma_desc_k_sw128(s_p + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
+                    const uint64_t dv = umma_desc_mn_sw128(s_v + ks * 2048);   // 16 keys = two 8-row atoms
+                    umma_bf16<1>(tmem_o_u, dp, dv, idesc, (kb | ks) != 0);
+                }
+                umma_commit<1>(bar_o);
             }
-            umma_commit<1>(bar_o);
+            __syncwarp();
             if (kb + 1 < p.nblocks) {
                 // every thread has read S(kb) (the __syncthreads above): queue the next S right behind P V, then refill V once
                 // P V has retired
                 issue_s(ph ^ 1u);
                 mbar_wait(bar_o, ph);
-                mbar_arrive_expect_tx(bar_v, KB * 128);
-                tma_load_2d<1>(&tmap_kv, bar_v, s_v, p.v_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_v, KB * 128);
+                    tma_load_2d<1>(&tmap_kv, bar_v, s_v, p.v_col0 + head * 64, frame * T + key0 + KB, kEvictNormal);
+                }
+                __syncwarp();
             }
         }
     }
@@ -853,9 +865,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
         }
     } else if (warp == 3 || warp == 11) {
         // =============================== MMA issuer of group g ===============================
-        if (lane != 0) goto fs_done;
-        const int g = warp == 3 ? 0 : 1;
-        const uint32_t gb = tmem_base + g * 256;
+        // The WHOLE warp walks the loop (every lane polls the mbarriers) and one elected lane issues: with the warp converged and every
+        // operand derived from provably warp-uniform values (the shuffles below), the descriptors, TMEM and barrier addresses live in
+        // uniform registers and a tcgen05.mma costs its own issue slot plus a uniform add or two.  Issued from a divergent `lane == 0`
+        // branch instead, each MMA was preceded by an election loop and four R2UR broadcasts (~15 dependent instructions, ~90 cycles:
+        // 21 MMAs + 7 waits per unit kept this thread ~1 000 cycles behind the softmax warps, timeline trace r02c).
+        const int g = __shfl_sync(0xffffffffu, warp, 0) == 3 ? 0 : 1;
+        const uint32_t gb = __shfl_sync(0xffffffffu, tmem_base, 0) + g * 256;
         const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, 16 * n1);
         const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
         const uint32_t o_col = gb + 64u;
@@ -882,17 +898,24 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
             mbar_wait(tmem_free(g), ph ^ 1u);                   // O of the previous unit (it overlays S_h0) is in registers
             tc_fence_after();
             FS_TRACE(2);
-            issue_s(s, 0);
+            if (elect_one()) {
+                issue_s(s, 0);
+                issue_s(s, 1);                                  // h1's region was last read by softmax h1(i - 1); P_h1 has its own columns
+                umma_commit<1>(qk_empty(s));                    // Q / K slot free once both S MMA groups have retired
+            }
+            __syncwarp();
             FS_TRACE(3);
-            issue_s(s, 1);                                      // h1's region was last read by softmax h1(i - 1); P_h1 has its own columns
-            umma_commit<1>(qk_empty(s));                        // Q / K slot free once both S MMA groups have retired
             // O = P_h0 V_h0 once ALL of h0 has been exponentiated (O overlays S_h0's columns [64, 128))
             mbar_wait(v_full(s), (i >> 1) & 1);
             mbar_wait(p_full(g, 0, 0), ph);
             tc_fence_after();
             FS_TRACE(4);
-            for (int ks = 0; ks < 8; ++ks)
-                umma_bf16_ts(o_col, gb + 8 * ks, umma_desc_mn_sw128(s_v(s) + ks * 2048), idesc_o, ks != 0);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16_ts(o_col, gb + 8 * ks, umma_desc_mn_sw128(s_v(s) + ks * 2048), idesc_o, ks != 0);
+            }
+            __syncwarp();
             FS_TRACE(5);
             // O += P_h1 V_h1, block by block as the softmax warps publish them
             if (p.mode & 2)
@@ -900,19 +923,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
             for (int b = 0; b < nb1; ++b) {
                 const int k0 = b == 0 ? 0 : (b == 1 ? 2 : c3);
                 const int k1 = b == 0 ? 2 : (b == 1 ? (wide ? 4 : 3) : c3 + 1);
-                FS_TRACE(11);
                 if (!(p.mode & 2)) mbar_wait(p_full(g, 1, b), ph);
-                FS_TRACE(12);
                 tc_fence_after();
                 FS_TRACE(6 + b);
-                for (int ks = k0; ks < k1; ++ks) {
-                    umma_bf16_ts(o_col, gb + p1_col + 8 * ks, umma_desc_mn_sw128(s_v(s) + (8 + ks) * 2048), idesc_o, 1u);
-                    FS_TRACE(13);
+                if (elect_one()) {
+                    for (int ks = k0; ks < k1; ++ks)
+                        umma_bf16_ts(o_col, gb + p1_col + 8 * ks, umma_desc_mn_sw128(s_v(s) + (8 + ks) * 2048), idesc_o, 1u);
+                    if (b == nb1 - 1) {
+                        umma_commit<1>(o_full(g));
+                        umma_commit<1>(v_empty(s));             // this group is done with the V slot
+                    }
                 }
+                __syncwarp();
             }
-            umma_commit<1>(o_full(g));
             FS_TRACE(9);
-            umma_commit<1>(v_empty(s));                         // this group is done with the V slot
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < T) {
         // =============================== softmax groups (warps that hold query rows) ===============================
@@ -1092,7 +1116,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
         if (lane == 0) bulk_wait0();   // every bulk store of this warp has completed before the CTA may exit
     }
 
-fs_done:
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {

@@ -78,7 +78,8 @@ int launch_layernorm_bf16(const float* x, const float* g, const float* b, int ro
 // ---------------------------------------------------------------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, int rows, int stride,
-                                                        __nv_bfloat16* __restrict__ xb, float* __restrict__ stats) {
+                                                        __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xl,
+                                                        float* __restrict__ stats) {
     constexpr int V = DIM / 128;
     constexpr int S = DIM / 128;   // statistics slots
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -99,7 +100,12 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
     for (int i = 0; i < V; ++i) {
         const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
         q += (a * a + c * c) + (d * d + e * e);
-        o[lane + 32 * i] = make_uint2(pack_bf16x2(a, c), pack_bf16x2(d, e));
+        const uint32_t h0 = pack_bf16x2(a, c), h1 = pack_bf16x2(d, e);
+        o[lane + 32 * i] = make_uint2(h0, h1);
+        if (xl != nullptr)    // split residual stream: the low half, bf16((x - mean) - hi)
+            reinterpret_cast<uint2*>(xl + static_cast<size_t>(row) * DIM)[lane + 32 * i] =
+                make_uint2(pack_bf16x2(a - __uint_as_float(h0 << 16), c - __uint_as_float(h0 & 0xffff0000u)),
+                           pack_bf16x2(d - __uint_as_float(h1 << 16), e - __uint_as_float(h1 & 0xffff0000u)));
     }
     const float m2 = warp_sum(q);
     float* sr = stats + static_cast<size_t>(row) * stride;
@@ -107,13 +113,14 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
     if (lane < S) *reinterpret_cast<float2*>(sr + 4 + 2 * lane) = make_float2(mean, m2 * (1.0f / S));
 }
 
-int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, float* stats, cudaStream_t stream) {
+int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, __nv_bfloat16* xl, float* stats,
+                     cudaStream_t stream) {
     CRE_REQUIRE(rows > 0, "row_stats: no rows");
     CRE_REQUIRE(stride >= 2 * (dim / 128) + 4 && stride % 2 == 0, "row_stats: statistics stride %d too small for dim %d", stride, dim);
     const int grid = (rows + 7) / 8;
-    LaunchScope scope(CRE_K_ROW_STATS, 6.0 * rows * dim, stream);
-    if (dim == 768) row_stats_kernel<768><<<grid, 256, 0, stream>>>(x, rows, stride, xb, stats);
-    else if (dim == 1024) row_stats_kernel<1024><<<grid, 256, 0, stream>>>(x, rows, stride, xb, stats);
+    LaunchScope scope(CRE_K_ROW_STATS, (xl != nullptr ? 8.0 : 6.0) * rows * dim, stream);
+    if (dim == 768) row_stats_kernel<768><<<grid, 256, 0, stream>>>(x, rows, stride, xb, xl, stats);
+    else if (dim == 1024) row_stats_kernel<1024><<<grid, 256, 0, stream>>>(x, rows, stride, xb, xl, stats);
     else {
         set_error("row_stats: unsupported dim %d (768 or 1024)", dim);
         return -3;
@@ -166,8 +173,12 @@ int launch_fold_ln_weights(const __nv_bfloat16* w, const float* gamma, const flo
 // services/dinov3-pipeline/app/main.py:113 last_hidden_state.mean(dim=1)).  One CTA per frame,
 // warps stride over the frame's tokens and keep a per-warp partial sum in registers.
 // ---------------------------------------------------------------------------------------------
-template <int DIM>
-__global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __restrict__ x, const float* __restrict__ g,
+// SPLIT: the residual stream arrives as its two bf16 halves + the pivot in slot 0 of the row's statistics (EPI_RESID_SP):
+// x = pivot + (hi + lo); the same 4 bytes per element as the fp32 stream.
+template <int DIM, bool SPLIT>
+__global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xh,
+                                                              const __nv_bfloat16* __restrict__ xl, const float* __restrict__ stats,
+                                                              int stats_stride, const float* __restrict__ g,
                                                               const float* __restrict__ b, int t, float eps,
                                                               float* __restrict__ frame_emb,
                                                               float* __restrict__ tokens_out) {
@@ -180,13 +191,28 @@ __global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __res
     for (int i = 0; i < V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tok = warp; tok < t; tok += 8) {
         const size_t row = static_cast<size_t>(frame) * t + tok;
-        const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
         float4 v[V];
         float s = 0.0f;
+        if constexpr (SPLIT) {
+            const uint2* hr = reinterpret_cast<const uint2*>(xh + row * DIM);
+            const uint2* lr = reinterpret_cast<const uint2*>(xl + row * DIM);
+            const float pivot = __ldg(stats + row * stats_stride);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            v[i] = xr[lane + 32 * i];
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            for (int i = 0; i < V; ++i) {
+                const uint2 h = hr[lane + 32 * i], l = lr[lane + 32 * i];
+                v[i].x = pivot + (__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16));
+                v[i].y = pivot + (__uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u));
+                v[i].z = pivot + (__uint_as_float(h.y << 16) + __uint_as_float(l.y << 16));
+                v[i].w = pivot + (__uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        } else {
+            const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                v[i] = xr[lane + 32 * i];
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
         }
         const float mean = warp_sum(s) * (1.0f / DIM);
         float q = 0.0f;
@@ -225,12 +251,17 @@ __global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __res
     }
 }
 
-int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
-                           float* frame_emb, float* tokens_out, cudaStream_t stream) {
+int launch_final_norm_mean(const float* x, const __nv_bfloat16* xh, const __nv_bfloat16* xl, const float* stats, int stats_stride,
+                           const float* g, const float* b, int frames, int t, int dim, float eps, float* frame_emb, float* tokens_out,
+                           cudaStream_t stream) {
     CRE_REQUIRE(frames > 0 && t > 0, "final_norm_mean: empty input");
+    const bool split = x == nullptr;
+    CRE_REQUIRE(!split || (xh != nullptr && xl != nullptr && stats != nullptr), "final_norm_mean: neither x nor its split halves given");
     LaunchScope scope(CRE_K_FINAL_NORM_MEAN, 4.0 * frames * t * dim * (tokens_out != nullptr ? 2.0 : 1.0), stream);
-    if (dim == 768) final_norm_mean_kernel<768><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
-    else if (dim == 1024) final_norm_mean_kernel<1024><<<frames, 256, 0, stream>>>(x, g, b, t, eps, frame_emb, tokens_out);
+    if (dim == 768 && split) final_norm_mean_kernel<768, true><<<frames, 256, 0, stream>>>(x, xh, xl, stats, stats_stride, g, b, t, eps, frame_emb, tokens_out);
+    else if (dim == 768) final_norm_mean_kernel<768, false><<<frames, 256, 0, stream>>>(x, xh, xl, stats, stats_stride, g, b, t, eps, frame_emb, tokens_out);
+    else if (dim == 1024 && split) final_norm_mean_kernel<1024, true><<<frames, 256, 0, stream>>>(x, xh, xl, stats, stats_stride, g, b, t, eps, frame_emb, tokens_out);
+    else if (dim == 1024) final_norm_mean_kernel<1024, false><<<frames, 256, 0, stream>>>(x, xh, xl, stats, stats_stride, g, b, t, eps, frame_emb, tokens_out);
     else {
         set_error("final_norm_mean: unsupported dim %d", dim);
         return -3;

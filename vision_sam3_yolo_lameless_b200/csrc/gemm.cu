@@ -140,6 +140,11 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     if constexpr (EPI == EPI_PATCH) {
         const int rc = make_tmap_tokens(&tout, p.out_f32, p.ldo, p);
         if (rc) return rc;
+    } else if constexpr (epi_resid_sp(EPI)) {   // both halves of the split residual stream: loaded and stored through the same maps
+        int rc = make_tmap_out(&tout, true, p.out_bf16, p.ldo2, p);
+        if (rc) return rc;
+        rc = make_tmap_out(&tout2, true, p.x_lo, p.ldo2, p);
+        if (rc) return rc;
     } else if constexpr (epi_tma_store(EPI)) {
         const bool bf16 = epi_out_bf16(EPI);
         const int rc = make_tmap_out(&tout, bf16, bf16 ? static_cast<void*>(p.out_bf16) : static_cast<void*>(p.out_f32), p.ldo, p);
@@ -170,7 +175,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    constexpr int kid = EPI == EPI_PATCH ? CRE_K_GEMM_PATCH : EPI == EPI_QKV ? CRE_K_GEMM_QKV : (EPI == EPI_RESID || epi_resid_ln(EPI)) ? CRE_K_GEMM_RESID
+    const int kid = (EPI == EPI_RESID || epi_resid_x(EPI)) && p.K > p.N ? CRE_K_GEMM_RESID_MLP : EPI == EPI_PATCH ? CRE_K_GEMM_PATCH : EPI == EPI_QKV ? CRE_K_GEMM_QKV : (EPI == EPI_RESID || epi_resid_x(EPI)) ? CRE_K_GEMM_RESID
                       : EPI == EPI_GELU ? CRE_K_GEMM_GELU : EPI == EPI_TOPK ? CRE_K_GEMM_TOPK : CRE_K_GEMM_PLAIN;
     // work: FLOPs, except the gallery scan which is bound by reading the bf16 gallery once (bytes)
     const double work = EPI == EPI_TOPK ? 2.0 * p.N * p.b_k_extent : 2.0 * p.M * static_cast<double>(p.N) * p.K;
@@ -221,13 +226,14 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
     CRE_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
     CRE_REQUIRE(epi != EPI_TOPK || p.K == 2 * p.b_k_extent, "gemm: TOPK expects A = [hi | lo] with K = 2 * b_k_extent (K=%d, extent=%d)", p.K,
                 p.b_k_extent);
-    if (epi_resid_ln(epi)) {
+    if (epi_resid_sp(epi)) CRE_REQUIRE(p.out_bf16 != nullptr && p.x_lo != nullptr, "gemm: RESID_SP needs both halves of the residual stream");
+    if (epi_resid_x(epi)) {
         CRE_REQUIRE(p.N % kBlockN == 0 && p.N / 128 == p.ln_slots && p.ln_slots <= 8 && p.ln_stride >= 2 * p.ln_slots + kLnStatsPad,
                     "gemm: RESID_LN needs N %% 256 == 0 and N / 128 = ln_slots <= 8 (N=%d slots=%d stride=%d)", p.N, p.ln_slots, p.ln_stride);
         CRE_REQUIRE(p.ln_stats_in != nullptr && p.ln_stats_out != nullptr && p.bias != nullptr && p.scale != nullptr,
                     "gemm: RESID_LN needs statistics in/out, bias and scale");
     }
-    if (p.ln_stats_in != nullptr && !epi_resid_ln(epi))
+    if (p.ln_stats_in != nullptr && !epi_resid_x(epi))
         CRE_REQUIRE(p.c1 != nullptr && p.bias != nullptr && p.ln_slots >= 1 && p.ln_slots <= 8, "gemm: folded LayerNorm needs c1, bias and 1..8 slots");
 #ifdef CRE_TUNING
     if (g_debug_mode != 0 && (epi == EPI_NONE || g_debug_mode >= 4)) {
@@ -271,6 +277,8 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         CRE_CASE(EPI_RESID)
         CRE_CASE(EPI_RESID_LN)
         CRE_CASE(EPI_RESID_LN3)
+        CRE_CASE(EPI_RESID_SP)
+        CRE_CASE(EPI_RESID_SP3)
         CRE_CASE(EPI_PATCH)
         CRE_CASE(EPI_NONE)
         case EPI_TOPK:

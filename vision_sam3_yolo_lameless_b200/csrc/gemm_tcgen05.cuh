@@ -37,8 +37,15 @@ enum GemmEpi : int {
     EPI_RESID_LN = 8,  // v = x + scale * (acc + bias): x (TMA load -> store), bf16(v - pivot) and per-row LayerNorm partials
     EPI_RESID_LN3 = 9, // same with ONE x tile per epilogue warp and one pipeline stage more (long-K GEMMs: a tile's main loop
                        // is long enough to hide the x round trips; measured against three x tiles + one stage fewer: slower)
+    EPI_RESID_SP = 10, // split residual stream: x = pivot + hi + lo with hi = bf16(x - pivot) (the A operand of the folded GEMMs) and
+                       // lo = bf16(x - pivot - hi); v = x + scale * (acc + bias) is re-split around the row's new pivot.  Both halves
+                       // come in and go out as 32 x 64 bf16 TMA boxes: 8 bytes per element instead of the 10 of RESID_LN
+                       // (fp32 in, fp32 + bf16 out), no fp32 copy of x in HBM at all.  Two chunk slots per epilogue warp.
+    EPI_RESID_SP3 = 11,// same results with ONE chunk slot per epilogue warp and more pipeline stages (long-K GEMMs)
 };
 constexpr bool epi_resid_ln(int epi) { return epi == EPI_RESID_LN || epi == EPI_RESID_LN3; }
+constexpr bool epi_resid_sp(int epi) { return epi == EPI_RESID_SP || epi == EPI_RESID_SP3; }
+constexpr bool epi_resid_x(int epi) { return epi_resid_ln(epi) || epi_resid_sp(epi); }   // x tiles fetched by the epilogue warps
 
 constexpr int kTopKMax = 8;
 
@@ -60,6 +67,7 @@ struct GemmParams {
     int ln_stride;       // floats per statistics row = 2 * ln_slots + 4
     float ln_eps;
     int ldo2;            // EPI_RESID_LN: row stride of out_bf16
+    __nv_bfloat16* x_lo; // EPI_RESID_SP: low half of the split residual stream (the high half is out_bf16); row stride ldo2
     // EPI_QKV
     const float* rope_axis;  // [(grid_h + grid_w), 52] fp32: per-axis {cos[16], sin[16], -sin[16]} rows (y positions, then x positions)
     int grid_h, grid_w;
@@ -97,7 +105,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;  // one epilogue warp's staging tile: 32 rows x 128 bytes
 
 constexpr bool epi_tma_store(int epi) {
-    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_PATCH || epi_resid_ln(epi);
+    return epi == EPI_BF16 || epi == EPI_F32 || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_PATCH || epi_resid_x(epi);
 }
 constexpr bool epi_out_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_QKV || epi == EPI_GELU; }
 constexpr int default_stages(int cg) { return cg == 1 ? 4 : 6; }
@@ -105,12 +113,14 @@ constexpr int kRopeRowFloats = 52;           // per axis position: cos[16] | sin
 constexpr int kRopeTableBytes = 16 * 1024;   // up to 78 axis rows (grid_h + grid_w), e.g. 37 + 37 at 592 x 592
 // the QKV kernel trades one pipeline stage for the rotary table in shared memory
 // EPI_RESID_LN keeps 2 (LN3: 1) x tiles + the bf16 tile, 4 KB each, per epilogue warp
-constexpr int ln_x_slots(int epi) { return epi == EPI_RESID_LN3 ? 1 : 2; }
-constexpr int ln_warp_bytes(int epi) { return (ln_x_slots(epi) + 1) * kEpiStageBytes; }
+// EPI_RESID_SP keeps 2 (SP3: 1) chunk slots = (hi tile, lo tile) pairs, 8 KB each, per epilogue warp
+constexpr int ln_x_slots(int epi) { return epi == EPI_RESID_LN3 || epi == EPI_RESID_SP3 ? 1 : 2; }
+constexpr int ln_warp_bytes(int epi) { return epi_resid_sp(epi) ? ln_x_slots(epi) * 2 * kEpiStageBytes : (ln_x_slots(epi) + 1) * kEpiStageBytes; }
 constexpr int kLnStatsPad = 4;               // floats before the partials in one statistics row: [pivot, -, -, -]
 constexpr int default_stages_epi(int epi, int cg) {
     return epi == EPI_RESID_LN ? (cg == 1 ? 2 : 4) : epi == EPI_RESID_LN3 ? (cg == 1 ? 3 : 5)
-                                                   : default_stages(cg) - (epi == EPI_QKV || epi == EPI_TOPK ? 1 : 0);
+         : epi == EPI_RESID_SP ? (cg == 1 ? 2 : 3) : epi == EPI_RESID_SP3 ? (cg == 1 ? 3 : 5)
+                               : default_stages(cg) - (epi == EPI_QKV || epi == EPI_TOPK ? 1 : 0);
 }
 
 template <int EPI, int CG, int STAGES>
@@ -120,7 +130,7 @@ struct GemmCfg {
     static constexpr int kSmemA = kBlockM * kBlockK * 2 * (EPI == EPI_TOPK ? 2 : 1);   // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
-    static constexpr int kEpiBytes = epi_resid_ln(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
+    static constexpr int kEpiBytes = epi_resid_x(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
     static constexpr int kTableOff = kEpiOff + kEpiBytes;
     static constexpr int kTableBytes = EPI == EPI_QKV ? kRopeTableBytes : 0;
     static constexpr int kBarOff = kTableOff + kTableBytes;
@@ -141,6 +151,11 @@ __device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
@@ -262,7 +277,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if constexpr (epi_tma_store(EPI)) tma_prefetch_desc(&tmap_out);
-        if constexpr (epi_resid_ln(EPI)) tma_prefetch_desc(&tmap_out2);
+        if constexpr (epi_resid_x(EPI)) tma_prefetch_desc(&tmap_out2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -273,7 +288,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(tmem_full_bar(s), 1);
             mbar_init(tmem_empty_bar(s), kEpiWarps * CG);
         }
-        if constexpr (epi_resid_ln(EPI))
+        if constexpr (epi_resid_x(EPI))
             for (int s = 0; s < 4 * kEpiWarps; ++s) mbar_init(bar_base + 256u + 8u * s, 1);
         fence_barrier_init();
     } else if (warp == 2) {
@@ -312,7 +327,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // gallery tile (the HBM / L2 stream that bounds this kernel) is fetched ONCE and multiplied twice
     const int num_kb = (EPI == EPI_TOPK ? p.b_k_extent : p.K) / kBlockK;
 
-    if (warp == 0 && lane == 0) {
+    // Producer and MMA issuer: the WHOLE warp walks the loop (every lane polls the mbarrier) and one elected lane issues.  With the warp
+    // converged and every operand derived from provably warp-uniform values (kernel parameters, loop counters, the shuffled TMEM base),
+    // descriptors, coordinates and barrier addresses live in uniform registers: a tcgen05.mma / TMA load costs its own issue slot plus
+    // a uniform add or two.  Issued from a divergent `lane == 0` branch instead, every one of them was preceded by an election loop and
+    // four R2UR broadcasts (~15 dependent instructions on a scheduler the epilogue warps keep busy).
+    if (warp == 0) {
         // =============================== TMA producer ===============================
         int stage = 0;
         uint32_t phase = 0;
@@ -322,36 +342,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int col0 = nt * kBlockN + static_cast<int>(cta_rank) * (kBlockN / CG);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t fb = full_bar(stage);
-                if constexpr (CG == 1) {
-                    mbar_arrive_expect_tx(fb, Cfg::kSmemA + Cfg::kSmemB);
-                } else {
-                    // the leader's barrier tracks both halves of the stage: 2 arrivals + the bytes of both CTAs
-                    if (is_leader) mbar_arrive_expect_tx(fb, 2 * (Cfg::kSmemA + Cfg::kSmemB));
-                    else mbar_arrive_remote(fb, 0);
-                }
-                const int ka = kb * kBlockK;
-                const int kbb = ka % p.b_k_extent;
-                if (gemm_dbg(p) & 32) {
-                    // tuning: pull the A box kPrefetchKb k-blocks ahead (next tile's first boxes at the tail) into L2
-                    int pkb = kb + kPrefetchKb, prow = row0;
-                    if (pkb >= num_kb) {
-                        pkb -= num_kb;
-                        const int tn = t + t_step;
-                        prow = tn < t_end ? ((tn / num_nt) * CG + static_cast<int>(cta_rank)) * kBlockM : -1;
+                if (elect_one()) {
+                    const uint32_t fb = full_bar(stage);
+                    if constexpr (CG == 1) {
+                        mbar_arrive_expect_tx(fb, Cfg::kSmemA + Cfg::kSmemB);
+                    } else {
+                        // the leader's barrier tracks both halves of the stage: 2 arrivals + the bytes of both CTAs
+                        if (is_leader) mbar_arrive_expect_tx(fb, 2 * (Cfg::kSmemA + Cfg::kSmemB));
+                        else mbar_arrive_remote(fb, 0);
                     }
-                    if (prow >= 0) tma_prefetch_2d(&tmap_a, pkb * kBlockK, prow);
+                    const int ka = kb * kBlockK;
+                    const int kbb = ka % p.b_k_extent;
+                    if (gemm_dbg(p) & 32) {
+                        // tuning: pull the A box kPrefetchKb k-blocks ahead (next tile's first boxes at the tail) into L2
+                        int pkb = kb + kPrefetchKb, prow = row0;
+                        if (pkb >= num_kb) {
+                            pkb -= num_kb;
+                            const int tn = t + t_step;
+                            prow = tn < t_end ? ((tn / num_nt) * CG + static_cast<int>(cta_rank)) * kBlockM : -1;
+                        }
+                        if (prow >= 0) tma_prefetch_2d(&tmap_a, pkb * kBlockK, prow);
+                    }
+                    tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA, ka, row0, kEvictNormal);
+                    if constexpr (EPI == EPI_TOPK)
+                        tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2, ka + p.b_k_extent, row0, kEvictNormal);
+                    tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, EPI == EPI_TOPK ? kEvictNormal : kEvictLast);
                 }
-                tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA, ka, row0, kEvictNormal);
-                if constexpr (EPI == EPI_TOPK)
-                    tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2, ka + p.b_k_extent, row0, kEvictNormal);
-                tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, EPI == EPI_TOPK ? kEvictNormal : kEvictLast);
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0 && is_leader) {
+    } else if (warp == 1 && is_leader) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, kBlockN);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -360,25 +384,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * kBlockN;
+            const uint32_t tmem_d = tmem_u + as * kBlockN;
             for (int kb = 0; kb < num_kb; ++kb) {
                 if (gemm_dbg(p) != 1) mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint64_t da = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA);
-                const uint64_t db = umma_desc_k_sw128(smem_b + stage * Cfg::kSmemB);
-                if (gemm_dbg(p) != 2) {
+                if (elect_one()) {
+                    const uint64_t da = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA);
+                    const uint64_t db = umma_desc_k_sw128(smem_b + stage * Cfg::kSmemB);
+                    if (gemm_dbg(p) != 2) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
-                        umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        if constexpr (EPI == EPI_TOPK) {   // + lo(query) . gallery into the same accumulator
-                            const uint64_t da_lo = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2);
-                            umma_bf16<CG>(tmem_d, da_lo + 2 * k, db + 2 * k, idesc, 1u);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
+                            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            if constexpr (EPI == EPI_TOPK) {   // + lo(query) . gallery into the same accumulator
+                                const uint64_t da_lo = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2);
+                                umma_bf16<CG>(tmem_d, da_lo + 2 * k, db + 2 * k, idesc, 1u);
+                            }
                         }
                     }
+                    umma_commit<CG>(empty_bar(stage));
+                    if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(as));
                 }
-                umma_commit<CG>(empty_bar(stage));
-                if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(as));
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -395,7 +422,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int half = (warp - 4) >> 2;      // which 128 accumulator columns
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         // this warp's staging tile (TMA-store epilogues): row r at r*128, 16-byte unit u at (u ^ (r & 7))
-        constexpr int kWarpStage = epi_resid_ln(EPI) ? ln_warp_bytes(EPI) : kEpiStageBytes;
+        constexpr int kWarpStage = epi_resid_x(EPI) ? ln_warp_bytes(EPI) : kEpiStageBytes;
         constexpr int XS = ln_x_slots(EPI);
         const uint32_t stage_u32 = smem_base + Cfg::kEpiOff + (warp - 4) * kWarpStage;
         uint8_t* stage_row = smem_raw + (stage_u32 - smem_u32(smem_raw)) + lane * 128;
@@ -455,16 +482,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         [[maybe_unused]] int xg = 0;         // running chunk counter of this warp: chunk xg lives in slot xg % XS
         auto xbar = [&](int s) { return bar_base + 256u + 8u * static_cast<uint32_t>((warp - 4) * 4 + s); };
         auto x_issue = [&](int s, int col, int rowb) {   // lane 0: arm the slot's barrier and fetch one 32 x 32 fp32 box of x
-            mbar_arrive_expect_tx(xbar(s), kEpiStageBytes);
-            tma_load_2d<1>(&tmap_out, xbar(s), stage_u32 + s * kEpiStageBytes, col, rowb, kEvictNormal);
+            if constexpr (epi_resid_sp(EPI)) {           // ... or the 32 x 64 bf16 boxes of its two halves
+                mbar_arrive_expect_tx(xbar(s), 2 * kEpiStageBytes);
+                tma_load_2d<1>(&tmap_out, xbar(s), stage_u32 + s * 2 * kEpiStageBytes, col, rowb, kEvictNormal);
+                tma_load_2d<1>(&tmap_out2, xbar(s), stage_u32 + s * 2 * kEpiStageBytes + kEpiStageBytes, col, rowb, kEvictNormal);
+            } else {
+                mbar_arrive_expect_tx(xbar(s), kEpiStageBytes);
+                tma_load_2d<1>(&tmap_out, xbar(s), stage_u32 + s * kEpiStageBytes, col, rowb, kEvictNormal);
+            }
         };
-        if constexpr (epi_resid_ln(EPI)) {
+        if constexpr (epi_resid_x(EPI)) {
             if (lane == 0 && t_begin < t_end) {
                 const int mt0 = t_begin / num_nt, nt0 = t_begin % num_nt;
                 const int rb0 = (mt0 * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
                 const int nc0 = nt0 * kBlockN + half * 128;
                 x_issue(0, nc0, rb0);
-                if constexpr (XS > 1) x_issue(1, nc0 + 32, rb0);
+                if constexpr (XS > 1) x_issue(1, nc0 + (epi_resid_sp(EPI) ? 64 : 32), rb0);
             }
             __syncwarp();
         }
@@ -732,6 +765,132 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         if (ob == 1) tma_store_2d(&tmap_out2, stage_u32 + XS * kEpiStageBytes, n0 - 32, row_base);
                         bulk_commit();
                         bulk_wait_read0();   // the chunk XS ahead reuses THIS slot once its store has drained
+                        x_ahead(c, s);
+                    }
+                    __syncwarp();
+                }
+                if (row_ok) {
+                    float* sn = p.ln_stats_out + static_cast<size_t>(row) * p.ln_stride;
+                    *reinterpret_cast<float2*>(sn + kLnStatsPad + 2 * slot_id) = make_float2(mean_r, m2_r);
+                    if (slot_id == 0) sn[0] = pivot;
+                }
+            } else if constexpr (epi_resid_sp(EPI)) {
+                // Split residual stream, 64-column chunks: the chunk's hi / lo tiles arrive by TMA in this warp's slot ring,
+                // x = p_old + (hi + lo) (p_old = the pivot the halves were written with, slot 0 of the incoming statistics row),
+                // v = x + scale * (acc + bias), and v - p_new (p_new = the row mean those statistics record) is split again IN
+                // PLACE: hi' = bf16(v - p_new), lo' = bf16((v - p_new) - hi') -- 16 significant bits relative to the centred value.
+                // Both tiles leave by TMA store; the row's (mean, M2) over this warp's 128 columns is merged 32 columns at a time.
+                const int slot_id = nt * 2 + half;
+                float p_old = 0.0f, pivot = 0.0f;
+                if (row_ok) {
+                    const float* so = p.ln_stats_in + static_cast<size_t>(row) * p.ln_stride;
+                    p_old = so[0];
+                    float ms = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < p.ln_slots) ms += so[kLnStatsPad + 2 * i];
+                    pivot = ms / static_cast<float>(p.ln_slots);
+                }
+                const uint64_t p_old2 = pack2(p_old, p_old), npiv2 = pack2(-pivot, -pivot);
+                float mean_r = 0.0f, m2_r = 0.0f;
+                auto x_ahead = [&](int c, int slot) {   // lane 0: the chunk XS ahead (this tile, or the head of this worker's next tile)
+                    int c2 = c + XS, nrow = row_base, ncol = ncol0;
+                    if (c2 >= 2) {
+                        const int tn = t + t_step;
+                        if (tn >= t_end) return;
+                        c2 -= 2;
+                        const int nmt = tn / num_nt, nnt = tn % num_nt;
+                        nrow = (nmt * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
+                        ncol = nnt * kBlockN + half * 128;
+                    }
+                    x_issue(slot, ncol + c2 * 64, nrow);
+                };
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c, ++xg) {
+                    const int s = xg % XS;
+                    uint8_t* hrow = stage_row + s * 2 * kEpiStageBytes;
+                    uint8_t* lrow = hrow + kEpiStageBytes;
+                    uint32_t a[32], b[32];
+                    tmem_ld32(taddr + c * 64, a);
+                    tmem_ld32(taddr + c * 64 + 32, b);
+                    mbar_wait(xbar(s), static_cast<uint32_t>(xg / XS) & 1u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int n0 = ncol0 + c * 64 + hh * 32;
+                        const uint32_t(&acc)[32] = hh == 0 ? a : b;
+                        uint64_t v[16];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t off = (static_cast<uint32_t>(hh * 4 + u) ^ r7) << 4;
+                            const uint4 hv = *reinterpret_cast<const uint4*>(hrow + off);
+                            const uint4 lv = *reinterpret_cast<const uint4*>(lrow + off);
+                            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + 2 * u);
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_v + n0) + 2 * u + 1);
+                            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_v + n0) + 2 * u);
+                            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_v + n0) + 2 * u + 1);
+                            const uint64_t bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
+                            const uint64_t ss[4] = {pack2(s0.x, s0.y), pack2(s0.z, s0.w), pack2(s1.x, s1.y), pack2(s1.z, s1.w)};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint64_t xh = pack2(__uint_as_float(hw[e] << 16), __uint_as_float(hw[e] & 0xffff0000u));
+                                const uint64_t xl = pack2(__uint_as_float(lw[e] << 16), __uint_as_float(lw[e] & 0xffff0000u));
+                                const uint64_t x2 = add2(p_old2, add2(xh, xl));
+                                const uint64_t t2 = add2(pack2(__uint_as_float(acc[8 * u + 2 * e]), __uint_as_float(acc[8 * u + 2 * e + 1])), bb[e]);
+                                v[4 * u + e] = fma2(ss[e], t2, x2);
+                            }
+                        }
+                        // statistics of these 32 columns (two passes over registers), then Chan's merge with the running pair
+                        uint64_t sa = v[0], sb = v[1];
+#pragma unroll
+                        for (int j = 2; j < 16; j += 2) { sa = add2(sa, v[j]); sb = add2(sb, v[j + 1]); }
+                        float s_lo, s_hi;
+                        unpack2(add2(sa, sb), s_lo, s_hi);
+                        const float mc = (s_lo + s_hi) * (1.0f / 32.0f);
+                        const uint64_t nmc2 = pack2(-mc, -mc);
+                        uint64_t qa = pack2(0.0f, 0.0f), qb = qa;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const uint64_t d0 = add2(v[j], nmc2), d1 = add2(v[j + 1], nmc2);
+                            qa = fma2(d0, d0, qa);
+                            qb = fma2(d1, d1, qb);
+                        }
+                        float q_lo, q_hi;
+                        unpack2(add2(qa, qb), q_lo, q_hi);
+                        const int kc = 2 * c + hh;               // 32-column groups merged so far
+                        const float delta = mc - mean_r;
+                        const float inv = 1.0f / static_cast<float>(kc + 1);
+                        mean_r = fmaf(delta, inv, mean_r);
+                        m2_r += (q_lo + q_hi) + delta * delta * (32.0f * static_cast<float>(kc) * inv);
+                        // re-split around the new pivot, in place (a thread only ever touches its own row of the two tiles)
+                        const uint64_t neg1 = pack2(-1.0f, -1.0f);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint64_t d2 = add2(v[4 * u + e], npiv2);
+                                float d0, d1, r0, r1;
+                                unpack2(d2, d0, d1);
+                                hw[e] = pack_bf16x2(d0, d1);
+                                const uint64_t hf = pack2(__uint_as_float(hw[e] << 16), __uint_as_float(hw[e] & 0xffff0000u));
+                                unpack2(fma2(hf, neg1, d2), r0, r1);
+                                lw[e] = pack_bf16x2(r0, r1);
+                            }
+                            const uint32_t off = (static_cast<uint32_t>(hh * 4 + u) ^ r7) << 4;
+                            *reinterpret_cast<uint4*>(hrow + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(lrow + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int n0 = ncol0 + c * 64;
+                        tma_store_2d(&tmap_out, stage_u32 + s * 2 * kEpiStageBytes, n0, row_base);
+                        tma_store_2d(&tmap_out2, stage_u32 + s * 2 * kEpiStageBytes + kEpiStageBytes, n0, row_base);
+                        bulk_commit();
+                        bulk_wait_read0();   // the chunk XS ahead reuses THIS slot once its stores have drained
                         x_ahead(c, s);
                     }
                     __syncwarp();

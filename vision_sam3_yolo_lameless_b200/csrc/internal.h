@@ -75,12 +75,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int launch_layernorm_bf16(const float* x, const float* g, const float* b, int rows, int dim, float eps,
                           __nv_bfloat16* out, cudaStream_t stream);
 // LayerNorm folding: seed statistics + centred bf16 copy of x; weight folding at context creation (elementwise.cu)
-int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, float* stats, cudaStream_t stream);
+int launch_row_stats(const float* x, int rows, int dim, int stride, __nv_bfloat16* xb, __nv_bfloat16* xl, float* stats,
+                     cudaStream_t stream);
 int launch_fold_ln_weights(const __nv_bfloat16* w, const float* gamma, const float* beta, const float* bias, int n_rows, int k,
                            int scaled_rows, float row_scale, __nv_bfloat16* wf, float* c1, float* c2, cudaStream_t stream);
 // final LayerNorm + mean over the t tokens of each frame; tokens_out optional
-int launch_final_norm_mean(const float* x, const float* g, const float* b, int frames, int t, int dim, float eps,
-                           float* frame_emb, float* tokens_out, cudaStream_t stream);
+// x == NULL: the split residual stream (xh + xl + the pivot in slot 0 of every statistics row)
+int launch_final_norm_mean(const float* x, const __nv_bfloat16* xh, const __nv_bfloat16* xl, const float* stats, int stats_stride,
+                           const float* g, const float* b, int frames, int t, int dim, float eps, float* frame_emb, float* tokens_out,
+                           cudaStream_t stream);
 int launch_fill_prefix(float* x, const float* prefix, int frames, int t, int prefix_tokens, int dim,
                        cudaStream_t stream);
 int launch_pool_clips(const float* frame_emb, const int32_t* offs, int clips, int dim, float* out_mean,

@@ -421,6 +421,16 @@ class ClipEmbedEngine:
         _lib.check(self.lib.cre_row_stats(x.data_ptr(), rows, dim, xb.data_ptr(), stats.data_ptr(), self._stream()), "cre_row_stats")
         return xb, stats
 
+    def row_stats_split(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """f32 [rows, dim] -> (hi = bf16(x - row mean), lo = bf16(x - row mean - hi), statistics rows): the split residual stream."""
+        rows, dim = x.shape
+        hi = torch.empty((rows, dim), dtype=torch.bfloat16, device=self.device)
+        lo = torch.empty_like(hi)
+        stats = torch.zeros((rows, 2 * (dim // 128) + 4), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cre_row_stats_split(x.data_ptr(), rows, dim, hi.data_ptr(), lo.data_ptr(), stats.data_ptr(), self._stream()),
+                   "cre_row_stats_split")
+        return hi, lo, stats
+
     def fold_ln_weights(self, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None,
                         scaled_rows: int = 0, row_scale: float = 1.0):
         """bf16 W [n, k] + LayerNorm (gamma, beta) [k] + bias [n] -> (bf16 W * gamma, c1 = its row sums, c2 = bias + W beta)."""
@@ -436,7 +446,8 @@ class ClipEmbedEngine:
     def gemm_ln(self, a: torch.Tensor, b: torch.Tensor, epilogue: int, stats_in: torch.Tensor, ln_dim: int, bias=None, c1=None,
                 scale=None, out: Optional[torch.Tensor] = None, eps: float = 1e-5, cta_group: int = 2):
         """LayerNorm-folded GEMM building block (include/cre.h cre_gemm_ln).  EPI_BF16 / EPI_GELU: returns bf16 [m, n].
-        EPI_RESID_LN: `out` f32 [m, n] is updated in place; returns (out, bf16 out - pivot, new statistics rows)."""
+        EPI_RESID_LN: `out` f32 [m, n] is updated in place; returns (out, bf16 out - pivot, new statistics rows).
+        EPI_RESID_SP: `out` = (hi, lo) bf16 [m, n] halves of the residual stream, updated in place; returns (hi, lo, new rows)."""
         m, k = a.shape
         n = b.shape[0]
         if epilogue in (_lib.EPI_RESID_LN, _lib.EPI_RESID_LN3):
@@ -446,6 +457,13 @@ class ClipEmbedEngine:
                                             stats_in.data_ptr(), ln_dim, eps, out.data_ptr(), xb.data_ptr(), stats_out.data_ptr(),
                                             cta_group, self._stream()), "cre_gemm_ln")
             return out, xb, stats_out
+        if epilogue in (_lib.EPI_RESID_SP, _lib.EPI_RESID_SP3):
+            hi, lo = out                                       # both halves are updated in place
+            stats_out = torch.zeros_like(stats_in)
+            _lib.check(self.lib.cre_gemm_ln(self._ctx, a.data_ptr(), b.data_ptr(), m, n, k, epilogue, _ptr(bias), None, _ptr(scale),
+                                            stats_in.data_ptr(), ln_dim, eps, lo.data_ptr(), hi.data_ptr(), stats_out.data_ptr(),
+                                            cta_group, self._stream()), "cre_gemm_ln")
+            return hi, lo, stats_out
         if out is None:
             out = torch.zeros((m, n), dtype=torch.bfloat16, device=self.device)
         _lib.check(self.lib.cre_gemm_ln(self._ctx, a.data_ptr(), b.data_ptr(), m, n, k, epilogue, _ptr(bias), _ptr(c1), None,
