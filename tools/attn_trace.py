@@ -46,7 +46,7 @@ def events(warp):
 # one table per unit: every softmax warp's milestones next to the issuers'
 soft = {w: events(w) for w in range(4, 11)}
 iss = {w: events(w) for w in (3, 11)}
-for unit in (2, 3, 4):
+for unit in (5, 6):
     print(f"=== unit {unit} (cycles since kernel start)")
     for w, ev in soft.items():
         per = [ev[i:i + 9] for i in range(0, len(ev), 9)]

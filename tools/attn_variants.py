@@ -60,7 +60,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "one":
         one(sys.argv[2])
     else:
-        for name in VARIANTS:
+        names = sys.argv[2].split(",") if len(sys.argv) > 2 and sys.argv[1] == "only" else list(VARIANTS)
+        for name in names:
             r = subprocess.run([sys.executable, __file__, "one", name], capture_output=True, text=True, timeout=240)
             sys.stdout.write(r.stdout)
             if r.returncode != 0:

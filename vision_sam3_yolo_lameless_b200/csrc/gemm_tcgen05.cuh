@@ -480,6 +480,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
         // EPI_RESID_LN: x-tile ring (XS 4 KB slots per warp, one mbarrier each), XS loads ahead of the chunk in hand
         [[maybe_unused]] int xg = 0;         // running chunk counter of this warp: chunk xg lives in slot xg % XS
+        [[maybe_unused]] int sp_pend_slot = -1, sp_pend_col = 0, sp_pend_row = 0;   // EPI_RESID_SP, lane 0: slot refill not yet issued
         auto xbar = [&](int s) { return bar_base + 256u + 8u * static_cast<uint32_t>((warp - 4) * 4 + s); };
         auto x_issue = [&](int s, int col, int rowb) {   // lane 0: arm the slot's barrier and fetch one 32 x 32 fp32 box of x
             if constexpr (epi_resid_sp(EPI)) {           // ... or the 32 x 64 bf16 boxes of its two halves
@@ -542,6 +543,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         cut_s = p.cut_scores[static_cast<size_t>(row) * p.cut_stride];
                         cut_i = p.cut_idx[static_cast<size_t>(row) * p.cut_stride];
                     }
+                }
+            }
+            // residual epilogues: the row's previous statistics (-> pivots) are fetched BEFORE waiting for the accumulator, so their
+            // DRAM round trip hides under the tile's main loop (it was 7 % of the epilogue warps' samples in the attention-out projection)
+            [[maybe_unused]] float ln_p_old = 0.0f, ln_pivot = 0.0f;
+            if constexpr (epi_resid_x(EPI)) {
+                if (row_ok) {
+                    const float* so = p.ln_stats_in + static_cast<size_t>(row) * p.ln_stride;
+                    ln_p_old = so[0];
+                    float ms = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < p.ln_slots) ms += so[kLnStatsPad + 2 * i];
+                    ln_pivot = ms / static_cast<float>(p.ln_slots);
                 }
             }
             mbar_wait(tmem_full_bar(as), aphase);
@@ -685,15 +700,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // back through the same slot (TMA store), bf16(v - pivot) through the 64-column tile (TMA store every
                 // second chunk), and the row's (mean, M2) over this warp's 128 columns is merged chunk by chunk.
                 const int slot_id = nt * 2 + half;
-                float pivot = 0.0f;
-                if (row_ok) {   // pivot = the row's mean at the previous LayerNorm (any value near the mean would do)
-                    const float* so = p.ln_stats_in + static_cast<size_t>(row) * p.ln_stride + kLnStatsPad;
-                    float ms = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < p.ln_slots) ms += so[2 * i];
-                    pivot = ms / static_cast<float>(p.ln_slots);
-                }
+                const float pivot = ln_pivot;   // the row's mean at the previous LayerNorm (any value near the mean would do)
                 float mean_r = 0.0f, m2_r = 0.0f;
                 uint8_t* orow = stage_row + XS * kEpiStageBytes;
                 // lane 0: fetch the x tile XS chunks ahead (this tile, or the head of this worker's next tile) into `slot`
@@ -781,44 +788,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // PLACE: hi' = bf16(v - p_new), lo' = bf16((v - p_new) - hi') -- 16 significant bits relative to the centred value.
                 // Both tiles leave by TMA store; the row's (mean, M2) over this warp's 128 columns is merged 32 columns at a time.
                 const int slot_id = nt * 2 + half;
-                float p_old = 0.0f, pivot = 0.0f;
-                if (row_ok) {
-                    const float* so = p.ln_stats_in + static_cast<size_t>(row) * p.ln_stride;
-                    p_old = so[0];
-                    float ms = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < p.ln_slots) ms += so[kLnStatsPad + 2 * i];
-                    pivot = ms / static_cast<float>(p.ln_slots);
-                }
+                const float p_old = ln_p_old, pivot = ln_pivot;
                 const uint64_t p_old2 = pack2(p_old, p_old), npiv2 = pack2(-pivot, -pivot);
                 float mean_r = 0.0f, m2_r = 0.0f;
-                auto x_ahead = [&](int c, int slot) {   // lane 0: the chunk XS ahead (this tile, or the head of this worker's next tile)
-                    int c2 = c + XS, nrow = row_base, ncol = ncol0;
+                // lane 0: coordinates of the chunk XS ahead (this tile, or the head of this worker's next tile); false = none left
+                auto x_target = [&](int c, int& ncol, int& nrow) {
+                    int c2 = c + XS;
+                    nrow = row_base;
+                    ncol = ncol0;
                     if (c2 >= 2) {
                         const int tn = t + t_step;
-                        if (tn >= t_end) return;
+                        if (tn >= t_end) return false;
                         c2 -= 2;
                         const int nmt = tn / num_nt, nnt = tn % num_nt;
                         nrow = (nmt * CG + static_cast<int>(cta_rank)) * kBlockM + quarter * 32;
                         ncol = nnt * kBlockN + half * 128;
                     }
-                    x_issue(slot, ncol + c2 * 64, nrow);
+                    ncol += c2 * 64;
+                    return true;
                 };
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c, ++xg) {
                     const int s = xg % XS;
                     uint8_t* hrow = stage_row + s * 2 * kEpiStageBytes;
                     uint8_t* lrow = hrow + kEpiStageBytes;
-                    uint32_t a[32], b[32];
-                    tmem_ld32(taddr + c * 64, a);
-                    tmem_ld32(taddr + c * 64 + 32, b);
+                    uint32_t acc[32];
+                    tmem_ld32(taddr + c * 64, acc);
                     mbar_wait(xbar(s), static_cast<uint32_t>(xg / XS) & 1u);
                     tmem_ld_wait();
+                    if constexpr (XS > 1) {
+                        // the refill of the OTHER slot, left pending by the previous chunk: its stores have had this chunk's two waits to
+                        // drain, so lane 0 no longer stalls the warp on them (8.5 % of the epilogue warps' samples in the attention-out
+                        // projection), and the load still has a whole chunk of arithmetic to land
+                        if (lane == 0 && sp_pend_slot >= 0) {
+                            bulk_wait_read0();
+                            x_issue(sp_pend_slot, sp_pend_col, sp_pend_row);
+                            sp_pend_slot = -1;
+                        }
+                    }
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int n0 = ncol0 + c * 64 + hh * 32;
-                        const uint32_t(&acc)[32] = hh == 0 ? a : b;
                         uint64_t v[16];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -841,6 +851,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 v[4 * u + e] = fma2(ss[e], t2, x2);
                             }
                         }
+                        // the accumulators are consumed: the second half's TMEM read flies under the statistics and the re-split
+                        if (hh == 0) tmem_ld32(taddr + c * 64 + 32, acc);
                         // statistics of these 32 columns (two passes over registers), then Chan's merge with the running pair
                         uint64_t sa = v[0], sb = v[1];
 #pragma unroll
@@ -882,6 +894,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             *reinterpret_cast<uint4*>(hrow + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                             *reinterpret_cast<uint4*>(lrow + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
+                        if (hh == 0) tmem_ld_wait();
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -890,8 +903,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tma_store_2d(&tmap_out, stage_u32 + s * 2 * kEpiStageBytes, n0, row_base);
                         tma_store_2d(&tmap_out2, stage_u32 + s * 2 * kEpiStageBytes + kEpiStageBytes, n0, row_base);
                         bulk_commit();
-                        bulk_wait_read0();   // the chunk XS ahead reuses THIS slot once its stores have drained
-                        x_ahead(c, s);
+                        int ncol, nrow;
+                        const bool more = x_target(c, ncol, nrow);   // the chunk XS ahead reuses THIS slot once its stores have drained
+                        if constexpr (XS > 1) {
+                            if (more) { sp_pend_slot = s; sp_pend_col = ncol; sp_pend_row = nrow; }
+                        } else {
+                            bulk_wait_read0();
+                            if (more) x_issue(s, ncol, nrow);
+                        }
                     }
                     __syncwarp();
                 }
