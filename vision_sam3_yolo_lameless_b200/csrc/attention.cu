@@ -147,7 +147,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint8_t* p_gen = smem_raw + (s_p - smem_u32(smem_raw));  // generic pointer to the P region
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform control flow / registers in the role branches)
     const int quarter = warp & 3, side = warp >> 2;        // TMEM lane quarter; which half of every key block
     const int row = quarter * 32 + (tid & 31);             // query row inside the tile
     const int mtile = blockIdx.x, head = blockIdx.y, frame = blockIdx.z;
@@ -438,7 +438,7 @@ attention_fast_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t tmem_slot = bar_base + 8u * 12;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     const int T = p.t, KB = p.kb;
 
     if (warp == 0 && lane == 0) {
@@ -810,7 +810,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
     const uint32_t tmem_slot = bar_base + 8u * 26;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     [[maybe_unused]] int tr_n = 0;
     const int T = p.t, KB = p.kb;
     const int n1 = (KB - 128) >> 4;                    // 16-key steps of the second half (3..5)

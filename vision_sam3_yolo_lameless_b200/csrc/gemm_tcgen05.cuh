@@ -266,7 +266,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: provably warp-uniform, so that the role branches below are uniform control flow for the compiler
+    // (uniform-datapath address / descriptor math inside them instead of R2UR broadcasts per TMA, MMA and parameter load)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 1) ? 0u : cluster_ctarank();
     const bool is_leader = cta_rank == 0;

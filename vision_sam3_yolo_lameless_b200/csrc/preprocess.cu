@@ -357,7 +357,7 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     auto raw_empty = [&](int b) { return bar0 + 16u + 8u * b; };
     auto vb_full = [&](int b) { return bar0 + 32u + 8u * b; };
     auto vb_empty = [&](int b) { return bar0 + 48u + 8u * b; };
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
     const int per_frame = p.gh * p.gw;
     const int step = gridDim.x;
 
