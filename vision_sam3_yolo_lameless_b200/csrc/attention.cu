@@ -102,6 +102,37 @@ __device__ __forceinline__ uint32_t pack_bf16x2_pos(float lo, float hi) {
     return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632u);
 }
 
+// NK (16 | 32) scores of one row -> exponentials -> running sum + packed bf16 pairs.  POLY: bit i set = pair i of every 8 runs on
+// the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0 (and is not computed).
+// neg_m2 includes + log2(1 + 2^-9): e = 2^(s log2e - m log2e) (1 + 2^-9), so that truncating e to bf16 rounds 2^(...) half-up.
+template <int NK, uint32_t POLY, bool MASK>
+__device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t (&pk)[NK / 2], int nvalid, uint64_t l2e2,
+                                              uint64_t neg_m2, uint64_t& l2) {
+#pragma unroll
+    for (int j = 0; j < NK; j += 2) {
+        if constexpr (MASK) {
+            if (j >= nvalid) {       // warp-uniform
+                pk[j >> 1] = 0u;
+                continue;
+            }
+        }
+        float x0, x1, e0, e1;
+        unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
+        if ((POLY >> ((j >> 1) & 7)) & 1) {
+            // the exponent-field add of exp2_poly2 wraps beyond 2^128: clamp, so that an overflowing row ends as inf / NaN (flagged)
+            exp2_poly2(pack2(fminf(x0, 128.0f), fminf(x1, 128.0f)), e0, e1);
+        } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+        }
+        if constexpr (MASK) {
+            if (j + 1 >= nvalid) e1 = 0.0f;
+        }
+        l2 = add2(l2, pack2(e0, e1));
+        pk[j >> 1] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632u);     // truncation; the bias is in the exponent
+    }
+}
+
 // UMMA shared-memory descriptor for an MN-major operand tile stored [k][64 elements] with 128-byte rows and the
 // 128B swizzle (exactly what a TMA box of 64 bf16 columns x k rows produces): the 64 MN elements of one k are
 // contiguous, 8 consecutive k form a 1024-byte swizzle atom, atoms along k are SBO = 1024 bytes apart.
@@ -245,34 +276,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int j = 0; j < 16; ++j)
                     if (c * 16 + j < npre) m = fmaxf(m, __uint_as_float(v[j]));
             }
-            neg_m2 = pack2(-m * kLog2e, -m * kLog2e);
+            const float nm = fmaf(-m, kLog2e, 2.8150654e-3f);   // + log2(1 + 2^-9): see softmax_block
+            neg_m2 = pack2(nm, nm);
         }
 
         // ---- P = exp2(S*log2e - m*log2e), row sum, bf16 P into the swizzled K-major smem tile; the TMEM read of chunk c + 1 is
         //      in flight while chunk c is exponentiated ----
         const int nk = nfull + (rem != 0 ? 1 : 0);          // chunks holding at least one valid key
         auto softmax_chunk = [&](int c, const uint32_t (&v)[16]) {
+            // all on the MUFU (this kernel is bound by issue slots, not by the XU pipe); no clamp, bf16 by truncation with the rounding
+            // bias folded into the exponent (softmax_block): an overflowing row shows in its sum and its unit is recomputed exactly
             uint32_t pk[8];
-            float e[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float x0, x1;
-                unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
-                x0 = fminf(x0, 120.0f);
-                x1 = fminf(x1, 120.0f);
-                e[j] = ex2_approx(x0);          // all on the MUFU: this kernel is bound by issue slots, not by the XU pipe
-                e[j + 1] = ex2_approx(x1);
-            }
-            if (c == nfull) {   // partial chunk: keys >= valid belong to another frame
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j >= rem) e[j] = 0.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                l2 = add2(l2, pack2(e[j], e[j + 1]));
-                pk[j >> 1] = pack_bf16x2_pos(e[j], e[j + 1]);
-            }
+            if (c == nfull) softmax_block<16, 0u, true>(v, pk, rem, l2e2, neg_m2, l2);   // partial chunk: keys >= valid belong to another frame
+            else softmax_block<16, 0u, false>(v, pk, 16, l2e2, neg_m2, l2);
             const uint32_t u0 = (static_cast<uint32_t>(c) & 3u) << 1;  // first 16-byte unit inside the 128-byte row
             uint8_t* base = p_row + (c >> 2) * (128 * 128);            // 64-key smem chunk
             *reinterpret_cast<uint4*>(base + ((u0 ^ r7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -345,7 +361,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     const float l_row = l_x[row] + l_x[128 + row];
     if (tok < T && !(l_row < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, frame * p.heads + head);
-    const float inv = 1.0f / l_row;
+    const float inv = 1.001953125f / l_row;                 // the row sum carries the (1 + 2^-9) bias of the exponentials, P does not
     uint32_t o[32];                                         // this thread's half of the 64 output dims
 #pragma unroll
     for (int c = 0; c < 32; c += 16) {
@@ -730,37 +746,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 // exponentials -- is what bounds this kernel).  Same 2^-9 relative error bound as round-to-nearest-even; inf stays inf.
 __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632u);
-}
-
-// NK (16 | 32) scores of one row -> exponentials -> running sum + packed bf16 pairs.  POLY: bit i set = pair i of every 8 runs on
-// the FMA / ALU pipes instead of the MUFU.  MASK: keys >= nvalid belong to the next frame, their P is 0 (and is not computed).
-// neg_m2 includes + log2(1 + 2^-9): e = 2^(s log2e - m log2e) (1 + 2^-9), so that truncating e to bf16 rounds 2^(...) half-up.
-template <int NK, uint32_t POLY, bool MASK>
-__device__ __forceinline__ void softmax_block(const uint32_t (&v)[NK], uint32_t (&pk)[NK / 2], int nvalid, uint64_t l2e2,
-                                              uint64_t neg_m2, uint64_t& l2) {
-#pragma unroll
-    for (int j = 0; j < NK; j += 2) {
-        if constexpr (MASK) {
-            if (j >= nvalid) {       // warp-uniform
-                pk[j >> 1] = 0u;
-                continue;
-            }
-        }
-        float x0, x1, e0, e1;
-        unpack2(fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e2, neg_m2), x0, x1);
-        if ((POLY >> ((j >> 1) & 7)) & 1) {
-            // the exponent-field add of exp2_poly2 wraps beyond 2^128: clamp, so that an overflowing row ends as inf / NaN (flagged)
-            exp2_poly2(pack2(fminf(x0, 128.0f), fminf(x1, 128.0f)), e0, e1);
-        } else {
-            e0 = ex2_approx(x0);
-            e1 = ex2_approx(x1);
-        }
-        if constexpr (MASK) {
-            if (j + 1 >= nvalid) e1 = 0.0f;
-        }
-        l2 = add2(l2, pack2(e0, e1));
-        pk[j >> 1] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632u);     // truncation; the bias is in the exponent
-    }
 }
 
 struct FsParams {
