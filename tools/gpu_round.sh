@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import os, torch; print('cpus', os.cpu_count(), 'threads', torch.get_num_threads())" >> gpurun_out/gpu.txt 2>&1
 free -g >> gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+# (GPU parity tests: tools/gpu_quick2.sh)
+
 timeout 600 python bench.py --steps 3 --warmup 3 --breakdown > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -30 gpurun_out/bench.err; cat gpurun_out/bench.json
 SMALL="python bench.py --clips 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --gallery-rows 100000"
