@@ -40,9 +40,8 @@ def main():
     x0 = torch.randn(m, n, device=dev)
     hi, lo, stats = eng.row_stats_split(x0)
     bias, scale = torch.randn(n, device=dev) * 0.1, torch.rand(n, device=dev) * 0.1
-    for k, name in ((768, "attention-out"), (3072, "mlp-down")):
-        if k not in args.k:
-            continue
+    for k in args.k:
+        name = {768: "attention-out", 3072: "mlp-down"}.get(k, f"K={k}")
         a = (torch.randn(m, k, device=dev) * 0.1).to(torch.bfloat16)
         w = (torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16)
         flops = 2.0 * m * n * k
