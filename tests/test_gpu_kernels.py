@@ -290,6 +290,24 @@ def test_preprocess_no_resize_kernel_bit_identical(engine_small, bgr):
     assert (fast.float().cpu() - torch.from_numpy(ref)).abs().max().item() < 1.2e-2
 
 
+@pytest.mark.parametrize("h,w", [(1080, 1920), (720, 1280), (2160, 3840), (1000, 1500)])
+def test_preprocess_variants_bit_identical(engine_small, h, w):
+    """The three filtering kernels -- direct-load (0), TMA-staged one row per warp (1), TMA-staged row pairs (2, the default) -- evaluate
+    the same integer vertical pass and the same horizontal FMA chain: identical bits, BGR and RGB, noise frames (every tap matters)."""
+    dev = engine_small.device
+    fr = torch.from_numpy(common.noise_frames(3, h, w, seed=h + w)).to(dev)
+    outs = {}
+    try:
+        for mode in (0, 1, 2):
+            _lib.set_tuning("preprocess_tma", mode)
+            outs[mode] = (engine_small.preprocess(fr, bgr=True).clone(), engine_small.preprocess(fr, bgr=False).clone())
+    finally:
+        _lib.set_tuning("preprocess_tma", 2)
+    for mode in (1, 2):
+        for a, b in zip(outs[0], outs[mode]):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16)), mode
+
+
 def test_preprocess_vs_hf_processor_golden(engine_small, golden):
     from oracle.make_golden import PREPROCESS_CASES, frames_for
     want = np.load(golden / "preprocess.npz")

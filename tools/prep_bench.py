@@ -10,7 +10,7 @@ from gemm_tune import timeit
 model = random_init_vit(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=600)
 from vision_sam3_yolo_lameless_b200 import _lib
-modes = [int(a) for a in sys.argv[1:]] or [1, 0]       # preprocess_tma values: 1 = TMA-staged, 0 = direct-load kernel; +2 / +4 = debug bits
+modes = [int(a) for a in sys.argv[1:]] or [2, 1, 0]    # preprocess_tma values: 2 = TMA-staged row pairs (default), 1 = TMA-staged, 0 = direct-load kernel
 import os
 SIZES = [(600, 1080, 1920), (600, 720, 1280), (600, 224, 224)]
 if os.environ.get("PREP_SIZES"):          # e.g. PREP_SIZES=540x960,480x640
@@ -22,4 +22,4 @@ for (n, h, w) in SIZES:
         ms = timeit(lambda: eng.preprocess(fr), iters=10)
         b = n * (h * w * 3 + 196 * 1536)
         print(f"preprocess[mode {mode}] {n}x{h}x{w}: {ms:.3f} ms  {ms / n * 1e3:.2f} us/frame  {b / ms / 1e6:.0f} GB/s", flush=True)
-_lib.set_tuning("preprocess_tma", 1)
+_lib.set_tuning("preprocess_tma", 2)

@@ -298,11 +298,11 @@ constexpr int kPtColWarp0 = 1, kPtRowWarp0 = 1 + kPtColWarps;
 
 // wait with back-off: the waiting roles (column warps, scheduler) would otherwise spend the row warps' issue slots on polling
 // (ncu: 28 % of the kernel's executed instructions were mbarrier polls)
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns = 200) {
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         if (mbar_try_wait(bar, parity)) return;
-        __nanosleep(200);
+        __nanosleep(ns);
     }
     __trap();
 }
@@ -494,8 +494,252 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
     }
 }
 
-static int g_pre_tma = 1, g_pre_identity = 1;
-void set_preprocess_tma(int on) { g_pre_tma = on & 1; }
+// =====================================================================================================================
+// TMA-staged variant, second form (the default): same roles, same arithmetic, same bits -- laid out for the shared-memory pipe, which
+// is what bounds the first form (ncu r02c: 78.6 % of the pipe's wavefronts, 30 % of them bank conflicts; issue slots 66 %).
+//
+//   * pass 1, one warp = TWO adjacent output rows.  Their tap windows overlap by ~55 % (window 2 x support, row pitch = scale), so the
+//     raw rows of the union are read, and byte-interleaved, once for both (-25 % raw reads).  The 16-bit weight pairs of both rows are
+//     tabulated per output-row pair on the union's pair grid (exact integer accumulation: the grouping of taps cannot change a bit).
+//     A lane owns the 4-byte columns lane + 32 j: four conflict-free 128-byte LDS.32 per raw row instead of one 512-byte LDS.128.
+//   * the intermediate is a row-PAIR matrix of float2 (row 2 rp, row 2 rp + 1) per byte column; a lane's four columns = two 16-byte
+//     stores whose halves swap (in registers) for lanes with bit 2 set: every quarter-warp then covers all 32 banks.
+//   * pass 2, one thread = one output column of one row pair: one LDS.64 per tap and channel feeds two FMA chains (the weight is
+//     shared), so the horizontal pass issues half the loads; a half-warp = the 16 columns of ONE row pair.
+//   * the two row-warp octets / column-warp quartets each own every other tile (= one buffer of each ring) and run concurrently.
+// =====================================================================================================================
+constexpr int kP2ParamInts = 8, kP2ParamSlots = 8;
+// 16 row warps = 8 output-row pairs x 2 column halves of the tile; 4 column warps = 8 row pairs x 16 output columns
+constexpr int kP2RowWarps = 16, kP2ColWarps = 4;
+constexpr int kP2Threads = (kP2RowWarps + kP2ColWarps + 1) * 32;
+constexpr int kP2ColWarp0 = 1, kP2RowWarp0 = 1 + kP2ColWarps;
+__device__ __forceinline__ uint32_t lds32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+__global__ void __launch_bounds__(kP2Threads, 1)
+preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles, int upairs, int nst) {
+    extern __shared__ uint8_t smem_raw_[];
+    const uint32_t base_u32 = (smem_u32(smem_raw_) + 127u) & ~127u;
+    uint8_t* base = smem_raw_ + (base_u32 - smem_u32(smem_raw_));
+    const int raw_bytes = nbox * rows_tile * 256;
+    const int vb_bytes = 8 * p.sstride * 8;                       // 8 row pairs x sstride float2 columns
+    // raw ring: nst (2 or 3) tiles deep -- with pass 1 at ~0.8 us per tile a two-deep ring exposes the TMA latency; intermediate ring: 2
+    uint8_t* vb0 = base + nst * raw_bytes;
+    int* params = reinterpret_cast<int*>(base + nst * raw_bytes + 2 * vb_bytes);             // [kP2ParamSlots][kP2ParamInts]
+    const uint32_t bar0 = base_u32 + nst * raw_bytes + 2 * vb_bytes + kP2ParamSlots * kP2ParamInts * 4;
+    const int oh = p.gh * 16, ow = p.gw * 16;
+    float* s_xw = reinterpret_cast<float*>(base + nst * raw_bytes + 2 * vb_bytes + kP2ParamSlots * kP2ParamInts * 4 + 128);
+    float* s_yinv = s_xw + ow * p.xkmax;
+    int* s_ylo = reinterpret_cast<int*>(s_yinv + oh);
+    int* s_xlo = s_ylo + oh;
+    int* s_xcnt = s_xlo + ow;
+    int* s_unp = s_xcnt + ow;                                     // union tap pairs per output-row pair
+    uint2* s_uw = reinterpret_cast<uint2*>(s_unp + ((oh / 2 + 1) & ~1));   // [oh / 2][upairs]: (row a, row b) weight pairs on the union's grid
+    // per output-row pair P = (rows 2P, 2P + 1): union window = rows [ylo[2P], max(end_a, end_b)); pair jp covers union rows 2 jp, 2 jp + 1
+    for (int P = threadIdx.x; P < oh / 2; P += kP2Threads) {
+        const int ya = __ldg(p.ylo + 2 * P), ca = __ldg(p.ycnt + 2 * P);
+        const int yb = __ldg(p.ylo + 2 * P + 1), cb = __ldg(p.ycnt + 2 * P + 1);
+        const int d = yb - ya;                                   // >= 0: the windows move down with the output row
+        const int ulen = max(ca, d + cb);
+        const int np = (ulen + 1) >> 1;
+        // pairs [0, ja) carry weight of row a, pairs [jb, np) of row b: three branch-free tap loops (a only | both | b only)
+        const int ja = (ca + 1) >> 1, jb = min(d >> 1, np);
+        s_unp[P] = np | (ja << 8) | (jb << 16);
+        uint32_t ta = 0u, tb = 0u;
+        for (int jp = 0; jp < upairs; ++jp) {
+            uint32_t w[4];                                       // a(2 jp), a(2 jp + 1), b(2 jp), b(2 jp + 1)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = 2 * jp + (e & 1);
+                const int k = e < 2 ? u : u - d;
+                const int cnt = e < 2 ? ca : cb;
+                const float* wy = p.yw + static_cast<size_t>(2 * P + (e >> 1)) * p.ykmax;
+                w[e] = (k >= 0 && k < cnt) ? aa_weight16(__ldg(wy + k)) : 0u;
+            }
+            s_uw[P * upairs + jp] = make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
+            ta += w[0] + w[1];
+            tb += w[2] + w[3];
+        }
+        s_yinv[2 * P] = 1.0f / static_cast<float>(ta);
+        s_yinv[2 * P + 1] = 1.0f / static_cast<float>(tb);
+    }
+    for (int i = threadIdx.x; i < ow * p.xkmax; i += kP2Threads) s_xw[i] = __ldg(p.xw + i);
+    for (int i = threadIdx.x; i < oh; i += kP2Threads) s_ylo[i] = __ldg(p.ylo + i);
+    for (int i = threadIdx.x; i < ow; i += kP2Threads) { s_xlo[i] = __ldg(p.xlo + i); s_xcnt[i] = __ldg(p.xcnt + i); }
+    auto raw_full = [&](int b) { return bar0 + 8u * b; };                // b < nst <= 4
+    auto raw_empty = [&](int b) { return bar0 + 32u + 8u * b; };
+    auto vb_full = [&](int b) { return bar0 + 64u + 8u * b; };
+    auto vb_empty = [&](int b) { return bar0 + 80u + 8u * b; };
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
+    const int per_frame = p.gh * p.gw;
+    const int step = gridDim.x;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int b = 0; b < nst; ++b) {
+            mbar_init(raw_full(b), 1);
+            mbar_init(raw_empty(b), kP2RowWarps);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(vb_full(b), kP2RowWarps);
+            mbar_init(vb_empty(b), kP2ColWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // =============================== scheduler + TMA producer ===============================
+        if (lane == 0) {
+            int it = 0, buf = 0, use = 0;                 // ring slot of tile `it` and how often the slot has been used before
+            for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+                if (use >= 1) mbar_wait_backoff(raw_empty(buf), static_cast<uint32_t>(use - 1) & 1u, 40);
+                const int frame = tile / per_frame, rem = tile - frame * per_frame;
+                const int py = rem / p.gw, px = rem - py * p.gw;
+                const int ox0 = px * 16;
+                const int x_lo = s_xlo[ox0];
+                const int x_hi = s_xlo[ox0 + 15] + s_xcnt[ox0 + 15];
+                const int b0 = (x_lo * 3) & ~15;
+                const int y_first = s_ylo[py * 16];
+                int* pr = params + (it & (kP2ParamSlots - 1)) * kP2ParamInts;
+                pr[0] = frame; pr[1] = py; pr[2] = px; pr[3] = b0; pr[4] = y_first; pr[5] = (x_hi * 3 - b0 + 15) >> 4;
+                mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
+                for (int j = 0; j < nbox; ++j)
+                    tma_load_3d(&tmap, raw_full(buf), base_u32 + buf * raw_bytes + j * rows_tile * 256, b0 + j * 256, y_first, frame);
+                if (++buf == nst) { buf = 0; ++use; }
+            }
+        }
+    } else if (warp >= kP2RowWarp0) {
+        // =============================== pass 1: vertical filter, warp = one output-row pair x one column half ===============================
+        const int rp = (warp - kP2RowWarp0) & 7, half = (warp - kP2RowWarp0) >> 3;
+        const int sel = (lane >> 2) & 1;               // lanes whose two 16-byte stores go out in swapped order
+        int it = 0, buf = 0, use = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+            const int vbuf = it & 1;
+            const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+            mbar_wait_backoff(raw_full(buf), static_cast<uint32_t>(use) & 1u, 20);
+            const int* pr = params + (it & (kP2ParamSlots - 1)) * kP2ParamInts;
+            const int py = pr[1], y_first = pr[4], ncol4 = pr[5] * 4;
+            if (it >= 2) mbar_wait_backoff(vb_empty(vbuf), ph ^ 1u, 20);
+            const uint8_t* raw = base + buf * raw_bytes;
+            float* vrow = reinterpret_cast<float*>(vb0 + vbuf * vb_bytes) + static_cast<size_t>(rp) * p.sstride * 2;
+            const int P = py * 8 + rp;
+            const uint2* uw = s_uw + P * upairs;
+            const int unp = s_unp[P];
+            const int np = unp & 0xff, ja = (unp >> 8) & 0xff, jb = unp >> 16;
+            const int y0 = s_ylo[2 * P] - y_first;
+            const float inv_a = s_yinv[2 * P], inv_b = s_yinv[2 * P + 1];
+            // one pass = 512 byte columns of the tile; this warp's half of it = the 4-byte columns 64 half + lane + 32 j, j = 0, 1
+            for (int c4_0 = 64 * half + lane; c4_0 < ncol4; c4_0 += 128) {
+                uint32_t acc_a[8], acc_b[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { acc_a[i] = 0u; acc_b[i] = 0u; }
+                // byte offset of the lane's column group j inside a raw row of the ring; a group beyond the staged boxes (only possible
+                // beyond the tile's last column: never stored) reads group 0 instead of branching
+                int off0, off1;
+                {
+                    const int cb0 = 4 * c4_0, cb1 = 4 * (c4_0 + 32);
+                    off0 = (cb0 >> 8) * (rows_tile * 256) + (cb0 & 255);
+                    off1 = cb1 < nbox * 256 ? (cb1 >> 8) * (rows_tile * 256) + (cb1 & 255) : off0;
+                }
+                const uint8_t* rowp = raw + y0 * 256;                       // union row 2 jp
+                const int last = (rows_tile - 1 - y0) * 256;                // byte offset of the tile's last row from rowp(jp = 0)
+                auto taps = [&](int jp, bool do_a, bool do_b) {
+                    const uint2 w = uw[jp];
+                    // an odd union length pairs its last row with weight 0: any in-bounds row will do
+                    const int o0 = jp * 512, o1 = min(o0 + 256, last);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int off = j == 0 ? off0 : off1;
+                        const uint32_t a = lds32(rowp + o0 + off), b = lds32(rowp + o1 + off);
+                        const uint32_t lo = __byte_perm(a, b, 0x5140u);     // (a0, b0, a1, b1)
+                        const uint32_t hi = __byte_perm(a, b, 0x7362u);     // (a2, b2, a3, b3)
+                        if (do_a) {
+                            acc_a[4 * j] = dp2a_lo(w.x, lo, acc_a[4 * j]);
+                            acc_a[4 * j + 1] = dp2a_hi(w.x, lo, acc_a[4 * j + 1]);
+                            acc_a[4 * j + 2] = dp2a_lo(w.x, hi, acc_a[4 * j + 2]);
+                            acc_a[4 * j + 3] = dp2a_hi(w.x, hi, acc_a[4 * j + 3]);
+                        }
+                        if (do_b) {
+                            acc_b[4 * j] = dp2a_lo(w.y, lo, acc_b[4 * j]);
+                            acc_b[4 * j + 1] = dp2a_hi(w.y, lo, acc_b[4 * j + 1]);
+                            acc_b[4 * j + 2] = dp2a_lo(w.y, hi, acc_b[4 * j + 2]);
+                            acc_b[4 * j + 3] = dp2a_hi(w.y, hi, acc_b[4 * j + 3]);
+                        }
+                    }
+                };
+                int jp = 0;
+                const int j_both0 = min(jb, ja);
+                for (; jp < j_both0; ++jp) taps(jp, true, false);           // rows only row a reaches
+#pragma unroll 2
+                for (; jp < ja; ++jp) taps(jp, true, true);                 // the overlap of the two windows
+                for (; jp < jb; ++jp) { }                                   // (windows that do not touch: nothing to add)
+                for (; jp < np; ++jp) taps(jp, false, true);                // rows only row b reaches
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c4 = c4_0 + 32 * j;
+                    if (c4 >= ncol4) continue;
+                    float fa[4], fb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        fa[i] = acc_to_float(acc_a[4 * j + i]) * inv_a;
+                        fb[i] = acc_to_float(acc_b[4 * j + i]) * inv_b;
+                    }
+                    // columns (0, 1) and (2, 3) as float2 pairs at their natural places; lanes with bit 2 set store them in the other order
+                    const float4 q0 = make_float4(fa[0], fb[0], fa[1], fb[1]), q1 = make_float4(fa[2], fb[2], fa[3], fb[3]);
+                    float4* dst = reinterpret_cast<float4*>(vrow + 8 * c4);          // 4 columns x float2 = 32 bytes
+                    dst[sel] = sel ? q1 : q0;
+                    dst[sel ^ 1] = sel ? q0 : q1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(raw_empty(buf));
+                mbar_arrive(vb_full(vbuf));
+            }
+            if (++buf == nst) { buf = 0; ++use; }
+        }
+    } else {
+        // =============================== pass 2: horizontal filter + normalise + patchify, thread = output column of a row pair ===============================
+        const int wq = warp - kP2ColWarp0;
+        const int kx = lane & 15, rp = 2 * wq + (lane >> 4);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
+            const int grp = it & 1;                       // ring slot
+            mbar_wait_backoff(vb_full(grp), static_cast<uint32_t>(it >> 1) & 1u, 40);
+            const int* pr = params + (it & (kP2ParamSlots - 1)) * kP2ParamInts;
+            const int frame = pr[0], py = pr[1], px = pr[2], b0 = pr[3];
+            const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px;
+            {
+                const int ox = px * 16 + kx;
+                const int x0 = s_xlo[ox], cnt = s_xcnt[ox];
+                const float* wx = s_xw + ox * p.xkmax;
+                const float2* src = reinterpret_cast<const float2*>(vb0 + grp * vb_bytes) + static_cast<size_t>(rp) * p.sstride + (x0 * 3 - b0);
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const float w = wx[k];
+                    const float2 v0 = src[3 * k], v1 = src[3 * k + 1], v2 = src[3 * k + 2];
+                    a0 = fmaf(w, v0.x, a0); c0 = fmaf(w, v0.y, c0);
+                    a1 = fmaf(w, v1.x, a1); c1 = fmaf(w, v1.y, c1);
+                    a2 = fmaf(w, v2.x, a2); c2 = fmaf(w, v2.y, c2);
+                }
+                const float sa[3] = {a0, a1, a2}, sc[3] = {c0, c1, c2};   // memory channel order; rows 2 rp and 2 rp + 1
+                __nv_bfloat16* o = p.out + patch * 768 + (2 * rp) * 16 + kx;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = p.bgr ? 2 - j : j;  // output (RGB) channel of memory channel j
+                    o[c * 256] = __float2bfloat16_rn(normalise_px(sa[j], p.mean[c], p.inv_std[c]));
+                    o[c * 256 + 16] = __float2bfloat16_rn(normalise_px(sc[j], p.mean[c], p.inv_std[c]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(vb_empty(grp));
+        }
+    }
+}
+
+static int g_pre_tma = 2, g_pre_identity = 1;   // 0: direct-load kernel, 1: TMA-staged (first form), 2: TMA-staged, row pairs (default)
+void set_preprocess_tma(int on) { g_pre_tma = on; }
 void set_preprocess_identity(int on) { g_pre_identity = on; }
 
 // returns 1 if the TMA variant was launched, 0 if the input does not qualify, negative on error
@@ -515,15 +759,6 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     // 1080x1920 4.11 / 2.42 -> at about 12x fewer output than input pixels
     if (sy * sx < 12.0) return 0;
     p.sstride = nvec_max * 16 + 4;
-    const size_t smem = 2 * static_cast<size_t>(nbox) * rows_tile * 256 + 2 * static_cast<size_t>(16) * p.sstride * 4 +
-                        4 * kPtParamInts * 4 + 64 + 128 +
-                        (static_cast<size_t>(a.gh) * 16 * (a.ty.kmax + 2) + static_cast<size_t>(a.gw) * 16 * (a.tx.kmax + 2)) * 4 +
-                        static_cast<size_t>(a.gh) * 16 * ((a.ty.kmax + 1) / 2 + 1) * 4;
-    if (smem > 227 * 1024) return 0;
-    CUtensorMap tmap;
-    int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows_tile);
-    if (rc) return rc;
-    CRE_SMEM_ATTR_ONCE(preprocess_tma_kernel, smem);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -531,6 +766,37 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
     if (tiles64 > 0x7fffffff) return 0;
     const int tiles = static_cast<int>(tiles64);
     const int grid = tiles < sms ? tiles : sms;
+    CUtensorMap tmap;
+    if (g_pre_tma >= 2 && (a.gh * 16) % 2 == 0) {
+        // second form: row-pair intermediate (float2 per byte column), union-window weight table
+        const int upairs = (a.ty.kmax + static_cast<int>(ceil(sy)) + 2) / 2;
+        const int oh = a.gh * 16, ow = a.gw * 16;
+        // input rows 16 output rows depend on: windows [int(c - sup + .5), int(c + sup + .5)), c = sy (i + .5)  ->  <= 15 sy + 2 sup + 2
+        int rows2 = static_cast<int>(15 * sy + 2 * supy + 1) + 1;
+        if (rows2 > a.h) rows2 = a.h;
+        const size_t fixed = 2 * static_cast<size_t>(8) * p.sstride * 8 + kP2ParamSlots * kP2ParamInts * 4 + 128 + 128 + 128 +
+                             (static_cast<size_t>(ow) * a.tx.kmax + oh + oh + 2 * ow + oh / 2 + 2) * 4 + static_cast<size_t>(oh / 2) * upairs * 8 + 16;
+        const size_t raw1 = static_cast<size_t>(nbox) * rows2 * 256;
+        const int nst = fixed + 3 * raw1 <= 227 * 1024 ? 3 : 2;
+        const size_t smem2 = fixed + nst * raw1;
+        if (smem2 <= 227 * 1024) {
+            int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows2);
+            if (rc) return rc;
+            CRE_SMEM_ATTR_ONCE(preprocess_tma2_kernel, smem2);
+            LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
+            preprocess_tma2_kernel<<<grid, kP2Threads, smem2, stream>>>(tmap, p, rows2, nbox, tiles, upairs, nst);
+            CRE_CUDA_OK(cudaGetLastError());
+            return 1;
+        }
+    }
+    const size_t smem = 2 * static_cast<size_t>(nbox) * rows_tile * 256 + 2 * static_cast<size_t>(16) * p.sstride * 4 +
+                        4 * kPtParamInts * 4 + 64 + 128 +
+                        (static_cast<size_t>(a.gh) * 16 * (a.ty.kmax + 2) + static_cast<size_t>(a.gw) * 16 * (a.tx.kmax + 2)) * 4 +
+                        static_cast<size_t>(a.gh) * 16 * ((a.ty.kmax + 1) / 2 + 1) * 4;
+    if (smem > 227 * 1024) return 0;
+    int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows_tile);
+    if (rc) return rc;
+    CRE_SMEM_ATTR_ONCE(preprocess_tma_kernel, smem);
     LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
     preprocess_tma_kernel<<<grid, kPtThreads, smem, stream>>>(tmap, p, rows_tile, nbox, tiles);
     CRE_CUDA_OK(cudaGetLastError());
