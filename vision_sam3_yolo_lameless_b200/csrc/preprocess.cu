@@ -509,25 +509,27 @@ preprocess_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams 
 //   * the two row-warp octets / column-warp quartets each own every other tile (= one buffer of each ring) and run concurrently.
 // =====================================================================================================================
 constexpr int kP2ParamInts = 8, kP2ParamSlots = 8;
-// 16 row warps = 8 output-row pairs x 2 column halves of the tile; 4 column warps = 8 row pairs x 16 output columns
+// 16 row warps = 8 output-row pairs x 2 column halves of the tile; 4 column warps = 8 row pairs x 16 output columns (a second quartet
+// on alternate tiles was slower, 1.95 vs 1.87 us per 1080p frame: the kernel is bound by issue slots, which extra pollers take)
 constexpr int kP2RowWarps = 16, kP2ColWarps = 4;
 constexpr int kP2Threads = (kP2RowWarps + kP2ColWarps + 1) * 32;
 constexpr int kP2ColWarp0 = 1, kP2RowWarp0 = 1 + kP2ColWarps;
 __device__ __forceinline__ uint32_t lds32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 __global__ void __launch_bounds__(kP2Threads, 1)
-preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles, int upairs, int nst) {
+preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams p, int rows_tile, int nbox, int tiles, int upairs, int nst, int nvb) {
     extern __shared__ uint8_t smem_raw_[];
     const uint32_t base_u32 = (smem_u32(smem_raw_) + 127u) & ~127u;
     uint8_t* base = smem_raw_ + (base_u32 - smem_u32(smem_raw_));
     const int raw_bytes = nbox * rows_tile * 256;
     const int vb_bytes = 8 * p.sstride * 8;                       // 8 row pairs x sstride float2 columns
-    // raw ring: nst (2 or 3) tiles deep -- with pass 1 at ~0.8 us per tile a two-deep ring exposes the TMA latency; intermediate ring: 2
+    // raw ring: nst (2 or 3) tiles deep; intermediate ring: nvb (2 or 3) -- with the two passes at comparable ~0.6 us per tile and a
+    // hand-off latency of a few hundred cycles, a two-deep intermediate ring made BOTH sides wait for each other (ncu r02d)
     uint8_t* vb0 = base + nst * raw_bytes;
-    int* params = reinterpret_cast<int*>(base + nst * raw_bytes + 2 * vb_bytes);             // [kP2ParamSlots][kP2ParamInts]
-    const uint32_t bar0 = base_u32 + nst * raw_bytes + 2 * vb_bytes + kP2ParamSlots * kP2ParamInts * 4;
+    int* params = reinterpret_cast<int*>(base + nst * raw_bytes + nvb * vb_bytes);             // [kP2ParamSlots][kP2ParamInts]
+    const uint32_t bar0 = base_u32 + nst * raw_bytes + nvb * vb_bytes + kP2ParamSlots * kP2ParamInts * 4;
     const int oh = p.gh * 16, ow = p.gw * 16;
-    float* s_xw = reinterpret_cast<float*>(base + nst * raw_bytes + 2 * vb_bytes + kP2ParamSlots * kP2ParamInts * 4 + 128);
+    float* s_xw = reinterpret_cast<float*>(base + nst * raw_bytes + nvb * vb_bytes + kP2ParamSlots * kP2ParamInts * 4 + 128);
     float* s_yinv = s_xw + ow * p.xkmax;
     int* s_ylo = reinterpret_cast<int*>(s_yinv + oh);
     int* s_xlo = s_ylo + oh;
@@ -567,8 +569,8 @@ preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams
     for (int i = threadIdx.x; i < ow; i += kP2Threads) { s_xlo[i] = __ldg(p.xlo + i); s_xcnt[i] = __ldg(p.xcnt + i); }
     auto raw_full = [&](int b) { return bar0 + 8u * b; };                // b < nst <= 4
     auto raw_empty = [&](int b) { return bar0 + 32u + 8u * b; };
-    auto vb_full = [&](int b) { return bar0 + 64u + 8u * b; };
-    auto vb_empty = [&](int b) { return bar0 + 80u + 8u * b; };
+    auto vb_full = [&](int b) { return bar0 + 64u + 8u * b; };                 // b < nvb <= 4
+    auto vb_empty = [&](int b) { return bar0 + 96u + 8u * b; };
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
     const int per_frame = p.gh * p.gw;
     const int step = gridDim.x;
@@ -579,7 +581,7 @@ preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams
             mbar_init(raw_full(b), 1);
             mbar_init(raw_empty(b), kP2RowWarps);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < nvb; ++b) {
             mbar_init(vb_full(b), kP2RowWarps);
             mbar_init(vb_empty(b), kP2ColWarps);
         }
@@ -612,14 +614,12 @@ preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams
         // =============================== pass 1: vertical filter, warp = one output-row pair x one column half ===============================
         const int rp = (warp - kP2RowWarp0) & 7, half = (warp - kP2RowWarp0) >> 3;
         const int sel = (lane >> 2) & 1;               // lanes whose two 16-byte stores go out in swapped order
-        int it = 0, buf = 0, use = 0;
+        int it = 0, buf = 0, use = 0, vbuf = 0, vuse = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
-            const int vbuf = it & 1;
-            const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
             mbar_wait_backoff(raw_full(buf), static_cast<uint32_t>(use) & 1u, 20);
             const int* pr = params + (it & (kP2ParamSlots - 1)) * kP2ParamInts;
             const int py = pr[1], y_first = pr[4], ncol4 = pr[5] * 4;
-            if (it >= 2) mbar_wait_backoff(vb_empty(vbuf), ph ^ 1u, 20);
+            if (vuse >= 1) mbar_wait_backoff(vb_empty(vbuf), static_cast<uint32_t>(vuse - 1) & 1u, 100);
             const uint8_t* raw = base + buf * raw_bytes;
             float* vrow = reinterpret_cast<float*>(vb0 + vbuf * vb_bytes) + static_cast<size_t>(rp) * p.sstride * 2;
             const int P = py * 8 + rp;
@@ -697,15 +697,15 @@ preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams
                 mbar_arrive(vb_full(vbuf));
             }
             if (++buf == nst) { buf = 0; ++use; }
+            if (++vbuf == nvb) { vbuf = 0; ++vuse; }
         }
     } else {
         // =============================== pass 2: horizontal filter + normalise + patchify, thread = output column of a row pair ===============================
         const int wq = warp - kP2ColWarp0;
         const int kx = lane & 15, rp = 2 * wq + (lane >> 4);
-        int it = 0;
+        int it = 0, grp = 0, vuse = 0;                    // grp = ring slot of tile `it`
         for (int tile = blockIdx.x; tile < tiles; tile += step, ++it) {
-            const int grp = it & 1;                       // ring slot
-            mbar_wait_backoff(vb_full(grp), static_cast<uint32_t>(it >> 1) & 1u, 40);
+            mbar_wait_backoff(vb_full(grp), static_cast<uint32_t>(vuse) & 1u, 40);
             const int* pr = params + (it & (kP2ParamSlots - 1)) * kP2ParamInts;
             const int frame = pr[0], py = pr[1], px = pr[2], b0 = pr[3];
             const size_t patch = (static_cast<size_t>(frame) * p.gh + py) * p.gw + px;
@@ -734,6 +734,7 @@ preprocess_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const PreParams
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(vb_empty(grp));
+            if (++grp == nvb) { grp = 0; ++vuse; }
         }
     }
 }
@@ -774,17 +775,21 @@ static int try_launch_preprocess_tma(const PreprocArgs& a, PreParams p, cudaStre
         // input rows 16 output rows depend on: windows [int(c - sup + .5), int(c + sup + .5)), c = sy (i + .5)  ->  <= 15 sy + 2 sup + 2
         int rows2 = static_cast<int>(15 * sy + 2 * supy + 1) + 1;
         if (rows2 > a.h) rows2 = a.h;
-        const size_t fixed = 2 * static_cast<size_t>(8) * p.sstride * 8 + kP2ParamSlots * kP2ParamInts * 4 + 128 + 128 + 128 +
+        const size_t vb1 = static_cast<size_t>(8) * p.sstride * 8;
+        const size_t fixed = kP2ParamSlots * kP2ParamInts * 4 + 128 + 128 + 128 +
                              (static_cast<size_t>(ow) * a.tx.kmax + oh + oh + 2 * ow + oh / 2 + 2) * 4 + static_cast<size_t>(oh / 2) * upairs * 8 + 16;
         const size_t raw1 = static_cast<size_t>(nbox) * rows2 * 256;
-        const int nst = fixed + 3 * raw1 <= 227 * 1024 ? 3 : 2;
-        const size_t smem2 = fixed + nst * raw1;
+        // ring depths: the raw ring first (measured at 1080p, where only one of the two fits three deep: 1.87 vs 1.96 us per frame)
+        const size_t cap = 227 * 1024;
+        const int nst = fixed + 3 * raw1 + 2 * vb1 <= cap ? 3 : 2;
+        const int nvb = fixed + nst * raw1 + 3 * vb1 <= cap ? 3 : 2;
+        const size_t smem2 = fixed + nst * raw1 + nvb * vb1;
         if (smem2 <= 227 * 1024) {
             int rc = make_tmap_u8_3d(&tmap, a.frames, 3LL * a.w, a.h, a.n, a.row_pitch, a.frame_pitch, 256, rows2);
             if (rc) return rc;
             CRE_SMEM_ATTR_ONCE(preprocess_tma2_kernel, smem2);
             LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
-            preprocess_tma2_kernel<<<grid, kP2Threads, smem2, stream>>>(tmap, p, rows2, nbox, tiles, upairs, nst);
+            preprocess_tma2_kernel<<<grid, kP2Threads, smem2, stream>>>(tmap, p, rows2, nbox, tiles, upairs, nst, nvb);
             CRE_CUDA_OK(cudaGetLastError());
             return 1;
         }
