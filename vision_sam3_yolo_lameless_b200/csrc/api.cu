@@ -910,6 +910,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
         set_attention_poly(value);
         return 0;
     }
+    if (strcmp(key, "attention_long") == 0) {
+        set_attention_long(value);
+        return 0;
+    }
     if (strcmp(key, "attention_split_mode") == 0) {
         set_attention_split_mode(value);
         return 0;

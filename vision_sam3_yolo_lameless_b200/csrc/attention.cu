@@ -1110,6 +1110,302 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid
 }
 
 // =====================================================================================================================
+// Long-sequence kernel (T > 256: the 518 x 518 / 592 x 592 inputs, T = 1 029 / 1 374): the split-S kernel's machinery with a
+// key-block loop.  Persistent, warp-specialised, two INDEPENDENT query-tile streams ("groups") per SM:
+//
+//   unit = (frame, head, 128-row query tile); group g of CTA b walks units 2 (b + i * gridDim) + g  (the tiles of a head are
+//          neighbours in that order: its K / V blocks are re-read from L2)
+//   warps 0 / 2      TMA producer of group 0 / 1: Q of the unit (one buffer: refilled when the unit's last S has retired, two key
+//                    blocks before the unit ends) and the 96-key K and V blocks through two three-deep rings
+//   warps 1 / 3      MMA issuer of group 0 / 1 (whole warp, elected lane):  S(kb) = Q K(kb)^T into one of two S buffers,
+//                    O += P(kb) V(kb) with P read from TMEM; S(kb + 2) is queued right behind P V(kb), whose P it overwrites
+//   warps 4-7 / 8-11 softmax of group 0 / 1, one thread per query row: single pass with the fixed 32-key stabiliser, bf16 P written
+//                    back into the S buffer behind the read pointer, O read once per unit -> 1 / l -> bf16 -> staging -> TMA store
+//
+//   TMEM columns of group g (base 256 g):  [0, 96) S buffer 0 (P in [0, 48)),  [96, 192) S buffer 1 (P in [96, 144)),  [192, 256) O
+//
+// With m fixed nothing is rescaled, so O simply accumulates across the key blocks; rows whose later keys outrun the stabiliser show
+// in the row sum and their (frame, head) is recomputed by attention_exact_kernel ("Exactness" above).  Compared with
+// attention_kernel (one CTA per query tile, every warp alternating between exponentials and waiting for the MMAs it issued):
+// S(kb + 1) is computed while block kb is exponentiated, P V(kb) while block kb + 1 is, P never touches shared memory, and the
+// second stream fills the remaining bubbles.
+// =====================================================================================================================
+constexpr int kLgThreads = 384;
+constexpr int kLgKeys = 96;                                  // keys per block
+constexpr int kLgStages = 3;                                 // K and V ring depth per group
+constexpr int kLgQBytes = 128 * 128, kLgKvBytes = kLgKeys * 128;
+constexpr int kLgGroupBytes = kLgQBytes + 2 * kLgStages * kLgKvBytes;      // 88 KB
+constexpr int kLgOutOff = 2 * kLgGroupBytes;                 // eight 32-row x 128-byte O staging tiles (one per softmax warp)
+constexpr int kLgBarOff = kLgOutOff + 8 * 4096;
+constexpr int kLgSmemBytes = kLgBarOff + 512 + 1024;
+
+struct LgParams {
+    int t, heads, mtiles, units, nblocks;
+    int k_col0, v_col0;
+    int* any_flag;
+    int* unit_flags;
+};
+
+template <uint32_t POLY>
+__global__ void __launch_bounds__(kLgThreads, 1)
+attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      const __grid_constant__ CUtensorMap tmap_out, const LgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto s_q = [&](int g) { return smem_base + g * kLgGroupBytes; };
+    auto s_k = [&](int g, int st) { return smem_base + g * kLgGroupBytes + kLgQBytes + st * kLgKvBytes; };
+    auto s_v = [&](int g, int st) { return smem_base + g * kLgGroupBytes + kLgQBytes + (kLgStages + st) * kLgKvBytes; };
+    const uint32_t bar_base = smem_base + kLgBarOff;
+    // per group (24 slots): 0 q_full, 1 q_empty, 2..4 k_full, 5..7 k_empty, 8..10 v_full, 11..13 v_empty, 14..15 s_full, 16..17 p_full,
+    // 18 o_full, 19 tmem_free
+    auto bar = [&](int g, int i) { return bar_base + 8u * (24 * g + i); };
+    const uint32_t tmem_slot = bar_base + 8u * 48;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
+    const int T = p.t, NB = p.nblocks;
+    const int last_valid = T - (NB - 1) * kLgKeys;         // keys of the frame inside its last block (1 .. 96)
+    const int last_steps = (last_valid + 15) >> 4;         // 16-key MMA steps of the last block that hold a valid key
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(bar(g, 0), 1);
+            mbar_init(bar(g, 1), 1);
+            for (int st = 0; st < kLgStages; ++st) {
+                mbar_init(bar(g, 2 + st), 1);
+                mbar_init(bar(g, 5 + st), 1);
+                mbar_init(bar(g, 8 + st), 1);
+                mbar_init(bar(g, 11 + st), 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar(g, 14 + b), 1);
+                mbar_init(bar(g, 16 + b), 4);              // the four softmax warps of the group
+            }
+            mbar_init(bar(g, 18), 1);
+            mbar_init(bar(g, 19), 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int per_head = p.mtiles, per_frame = p.heads * p.mtiles;
+    const int u_step = 2 * static_cast<int>(gridDim.x);
+
+    if (warp == 0 || warp == 2) {
+        // =============================== TMA producer of group g ===============================
+        const int g = warp >> 1;
+        int kcount = 0;                                   // K / V blocks issued so far: stage = kcount % 3
+        int i = 0;
+        for (int u = 2 * static_cast<int>(blockIdx.x) + g; u < p.units; u += u_step, ++i) {
+            const int frame = u / per_frame, rem = u - frame * per_frame;
+            const int head = rem / per_head, mtile = rem - head * per_head;
+            mbar_wait(bar(g, 1), (i & 1) ^ 1u);           // every S of the previous unit has retired: Q may be replaced
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar(g, 0), kLgQBytes);
+                tma_load_2d<1>(&tmap_q, bar(g, 0), s_q(g), head * 64, frame * T + mtile * 128, kEvictFirst);
+            }
+            __syncwarp();
+            for (int kb = 0; kb < NB; ++kb, ++kcount) {
+                const int st = kcount % kLgStages;
+                const uint32_t ph = static_cast<uint32_t>(kcount / kLgStages) & 1u;
+                mbar_wait(bar(g, 5 + st), ph ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar(g, 2 + st), kLgKvBytes);
+                    tma_load_2d<1>(&tmap_kv, bar(g, 2 + st), s_k(g, st), p.k_col0 + head * 64, frame * T + kb * kLgKeys, kEvictNormal);
+                }
+                __syncwarp();
+                mbar_wait(bar(g, 11 + st), ph ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar(g, 8 + st), kLgKvBytes);
+                    tma_load_2d<1>(&tmap_kv, bar(g, 8 + st), s_v(g, st), p.v_col0 + head * 64, frame * T + kb * kLgKeys, kEvictNormal);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // =============================== MMA issuer of group g ===============================
+        const int g = warp >> 1;
+        const uint32_t gb = __shfl_sync(0xffffffffu, tmem_base, 0) + g * 256;
+        const uint32_t idesc_s = umma_idesc_bf16(128, kLgKeys);
+        const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+        const uint32_t o_col = gb + 192u;
+        int kcount = 0;                                   // blocks whose S has been issued (ring stage of K)
+        int vcount = 0;                                   // blocks whose P V has been issued (ring stage of V, S / P buffer = vcount & 1)
+        auto issue_s = [&](int kb_last) {                 // S of block number kcount of the stream into S buffer kcount & 1
+            const int st = kcount % kLgStages;
+            mbar_wait(bar(g, 2 + st), static_cast<uint32_t>(kcount / kLgStages) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dq = umma_desc_k_sw128(s_q(g));
+                const uint64_t dk = umma_desc_k_sw128(s_k(g, st));
+                const uint32_t d = gb + (kcount & 1) * kLgKeys;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16<1>(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit<1>(bar(g, 14 + (kcount & 1)));        // s_full of that buffer
+                umma_commit<1>(bar(g, 5 + st));                   // K stage free
+                if (kb_last) umma_commit<1>(bar(g, 1));           // the unit's last S: Q may be replaced
+            }
+            __syncwarp();
+            ++kcount;
+        };
+        int i = 0;
+        for (int u = 2 * static_cast<int>(blockIdx.x) + g; u < p.units; u += u_step, ++i) {
+            mbar_wait(bar(g, 0), i & 1);                  // Q of this unit
+            issue_s(NB == 1);
+            if (NB > 1) issue_s(NB == 2);
+            for (int kb = 0; kb < NB; ++kb, ++vcount) {
+                const int b = vcount & 1;
+                const int st = vcount % kLgStages;
+                mbar_wait(bar(g, 8 + st), static_cast<uint32_t>(vcount / kLgStages) & 1u);          // V block
+                if (kb == 0) mbar_wait(bar(g, 19), (i & 1) ^ 1u);                                   // O of the previous unit has been read
+                mbar_wait(bar(g, 16 + b), static_cast<uint32_t>(vcount >> 1) & 1u);                 // P(kb) published
+                tc_fence_after();
+                if (elect_one()) {
+                    const int steps = kb == NB - 1 ? last_steps : kLgKeys / 16;
+                    for (int ks = 0; ks < steps; ++ks)
+                        umma_bf16_ts(o_col, gb + b * kLgKeys + 8 * ks, umma_desc_mn_sw128(s_v(g, st) + ks * 2048), idesc_o, (kb | ks) != 0);
+                    umma_commit<1>(bar(g, 11 + st));              // V stage free
+                    if (kb == NB - 1) umma_commit<1>(bar(g, 18)); // o_full
+                }
+                __syncwarp();
+                if (kb + 2 < NB) issue_s(kb + 3 == NB);           // S(kb + 2) overwrites P(kb): in order behind the MMAs above
+            }
+        }
+    } else {
+        // =============================== softmax of group g ===============================
+        const int g = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 256;
+        constexpr float kLog2e = 1.4426950408889634f;
+        const uint64_t l2e2 = pack2(kLog2e, kLog2e);
+        const uint32_t stage_u32 = smem_base + kLgOutOff + (warp - 4) * 4096;
+        uint8_t* stage_row = smem_raw + (stage_u32 - smem_u32(smem_raw)) + lane * 128;
+        const uint32_t r7 = lane & 7;
+        auto publish = [&](int b) {                         // P of the block in S buffer b: every tcgen05.st of this warp has completed
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(g, 16 + b));
+        };
+        int vcount = 0;
+        int i = 0;
+        for (int u = 2 * static_cast<int>(blockIdx.x) + g; u < p.units; u += u_step, ++i) {
+            const int frame = u / per_frame, rem = u - frame * per_frame;
+            const int head = rem / per_head, mtile = rem - head * per_head;
+            const int row = mtile * 128 + quarter * 32 + lane;          // query token inside the frame
+            uint64_t l2 = pack2(0.0f, 0.0f);
+            uint64_t neg_m2 = pack2(0.0f, 0.0f);
+#pragma unroll 1
+            for (int kb = 0; kb < NB; ++kb, ++vcount) {
+                const int b = vcount & 1;
+                const uint32_t sb = t_row + b * kLgKeys;
+                mbar_wait(bar(g, 14 + b), static_cast<uint32_t>(vcount >> 1) & 1u);
+                __syncwarp();
+                tc_fence_after();
+                uint32_t va[32], vb[32];
+                uint32_t pk[16];
+                tmem_ld32(sb, va);
+                tmem_ld_wait();
+                if (kb == 0) {
+                    // stabiliser from the first 32 keys of the frame (CLS, registers, first patches); + log2(1 + 2^-9): see softmax_block
+                    float m = __uint_as_float(va[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+                    const float nm = fmaf(-m, kLog2e, 2.8150654e-3f);
+                    neg_m2 = pack2(nm, nm);
+                }
+                tmem_ld32(sb + 32, vb);
+                if (kb < NB - 1) {
+                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                    tmem_st16(sb, pk);
+                    tmem_ld_wait();
+                    tmem_ld32(sb + 64, va);
+                    softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                    tmem_st16(sb + 16, pk);
+                    tmem_ld_wait();
+                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                    tmem_st16(sb + 32, pk);
+                } else {
+                    // last block of the frame: keys >= last_valid belong to the next frame (P = 0); chunks past last_steps are not read
+                    softmax_block<32, POLY, true>(va, pk, last_valid, l2e2, neg_m2, l2);
+                    tmem_st16(sb, pk);
+                    tmem_ld_wait();
+                    tmem_ld32(sb + 64, va);
+                    softmax_block<32, POLY, true>(vb, pk, last_valid - 32, l2e2, neg_m2, l2);
+                    tmem_st16(sb + 16, pk);
+                    tmem_ld_wait();
+                    softmax_block<32, POLY, true>(va, pk, last_valid - 64, l2e2, neg_m2, l2);
+                    tmem_st16(sb + 32, pk);
+                }
+                publish(b);
+            }
+            // ---- O / l -> bf16 ----
+            mbar_wait(bar(g, 18), i & 1);
+            __syncwarp();
+            tc_fence_after();
+            {
+                uint32_t oa[32], ob[32];
+                tmem_ld32(t_row + 192, oa);
+                tmem_ld32(t_row + 224, ob);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(g, 19));            // O is in registers: the next unit's first P V may overwrite it
+                    bulk_wait_read0();                  // the previous unit's bulk store has drained the staging tile
+                }
+                __syncwarp();
+                float l_lo, l_hi;
+                unpack2(l2, l_lo, l_hi);
+                const float l_sum = l_lo + l_hi;
+                if (row < T && !(l_sum < kRowSumLimit)) raise_unit_flag(p.any_flag, p.unit_flags, frame * p.heads + head);
+                const float inv = __fdividef(1.001953125f, l_sum);   // the row sum carries the (1 + 2^-9) bias of the exponentials, P does not
+                const uint64_t inv2 = pack2(inv, inv);
+                auto scaled = [&](const uint32_t (&o)[32], int j) {       // columns 8 j .. 8 j + 7 of this half -> four bf16 pairs
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a, c;
+                        unpack2(mul2(pack2(__uint_as_float(o[8 * j + 2 * e]), __uint_as_float(o[8 * j + 2 * e + 1])), inv2), a, c);
+                        w[e] = pack_bf16x2(a, c);
+                    }
+                    return make_uint4(w[0], w[1], w[2], w[3]);
+                };
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(j) ^ r7) << 4)) = scaled(oa, j);
+                    *reinterpret_cast<uint4*>(stage_row + ((static_cast<uint32_t>(4 + j) ^ r7) << 4)) = scaled(ob, j);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    // rows >= T of the box (the tail of the frame's last query tile) fall outside the map's row dimension: clipped
+                    tma_store_3d(&tmap_out, stage_u32, head * 64, mtile * 128 + quarter * 32, frame);
+                    bulk_commit();
+                }
+            }
+        }
+        if (lane == 0) bulk_wait0();   // every bulk store of this warp has completed before the CTA may exit
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+// =====================================================================================================================
 // Exact recomputation of the units the tensor-core kernels flagged ("Exactness" above): fp32 on the CUDA cores, true row maximum
 // (two passes over the keys), fp32 probabilities, nothing approximated -- HF:modeling_dinov3_vit.py:210-235 on the bf16 q / k / v
 // the fast kernels read.  One CTA per flagged unit, one thread per query row, key tiles of 128 in shared memory.  With no flag up
@@ -1212,6 +1508,8 @@ attention_exact_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int k_col0
 }
 
 static int g_attn_fast = 1;     // 0: general kernel for every T; 1: persistent kernels for T <= 256
+static int g_attn_long = 1;     // 1: persistent long-sequence kernel for T > 256; 0: one CTA per query tile (attention_kernel)
+void set_attention_long(int on) { g_attn_long = on; }
 static int g_attn_split = 1;    // 1: split-S kernel for 160 < T <= 208; 0: the single-S fast kernel
 static int g_attn_poly = 1;     // split-S kernel: share of the exponentials on the FMA pipe (0: none, 1: 25 %, 2: 50 %)
 static int g_attn_mode = 0;     // split-S kernel tuning bits (FsParams::mode)
@@ -1310,6 +1608,37 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         {
             LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
             attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
+            CRE_CUDA_OK(cudaGetLastError());
+        }
+        return launch_exact(a, stream);
+    }
+    if (g_attn_long) {
+        // persistent long-sequence kernel: 96-key blocks, two query-tile streams per SM
+        int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 128);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kLgKeys);
+        if (rc) return rc;
+        CUtensorMap tout;   // out as [frames][T][heads * 64]: a 32-row store box is clipped at the frame's last token
+        rc = make_tmap_bf16_3d(&tout, a.out, a.heads * 64, a.t, a.n, a.heads * 64, static_cast<int64_t>(a.t) * a.heads * 64, 32);
+        if (rc) return rc;
+        LgParams lp;
+        lp.t = a.t;
+        lp.heads = a.heads;
+        lp.mtiles = (a.t + 127) / 128;
+        lp.nblocks = (a.t + kLgKeys - 1) / kLgKeys;
+        const int64_t units64 = static_cast<int64_t>(a.n) * a.heads * lp.mtiles;
+        CRE_REQUIRE(units64 < (1LL << 30), "attention: too many query tiles (%lld)", (long long)units64);
+        lp.units = static_cast<int>(units64);
+        lp.k_col0 = a.k_col0;
+        lp.v_col0 = a.v_col0;
+        lp.any_flag = a.any_flag;
+        lp.unit_flags = a.unit_flags;
+        const int pairs = (lp.units + 1) / 2;
+        const int grid = pairs < sms ? pairs : sms;
+        {
+            LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+            CRE_SMEM_ATTR_ONCE(attention_long_kernel<0x44u>, kLgSmemBytes);
+            attention_long_kernel<0x44u><<<grid, kLgThreads, kLgSmemBytes, stream>>>(tq, tkv, tout, lp);
             CRE_CUDA_OK(cudaGetLastError());
         }
         return launch_exact(a, stream);

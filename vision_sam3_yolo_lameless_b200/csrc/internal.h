@@ -19,6 +19,7 @@ void set_gemm_debug(int mode);
 #endif
 void set_attention_fast(int on);
 void set_attention_split(int on);
+void set_attention_long(int on);
 void set_attention_poly(int v);
 void set_attention_split_mode(int v);
 void set_attention_split_delay(int cycles);
