@@ -19,6 +19,7 @@ VARIANTS = {
     "split_poly0": {"attention_poly": 0},
     "split_poly50": {"attention_poly": 2},
     "split_pv1": {"attention_split_mode": 2},
+    "long_kernel": {"attention_fast": 0},        # the T > 256 persistent kernel on T = 201 (three 96-key blocks, two 128-row tiles)
 }
 
 

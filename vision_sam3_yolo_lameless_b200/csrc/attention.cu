@@ -1304,6 +1304,20 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const int row = mtile * 128 + quarter * 32 + lane;          // query token inside the frame
             uint64_t l2 = pack2(0.0f, 0.0f);
             uint64_t neg_m2 = pack2(0.0f, 0.0f);
+            if (mtile * 128 + quarter * 32 >= T) {
+                // no query row of this warp exists (tail of the frame's last tile): keep the barrier protocol, skip the arithmetic --
+                // the rows' P and O are never defined and never stored (the store box is clipped at the frame's last token)
+                for (int kb = 0; kb < NB; ++kb, ++vcount) {
+                    const int b = vcount & 1;
+                    mbar_wait(bar(g, 14 + b), static_cast<uint32_t>(vcount >> 1) & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(g, 16 + b));
+                }
+                mbar_wait(bar(g, 18), i & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(g, 19));
+                continue;
+            }
 #pragma unroll 1
             for (int kb = 0; kb < NB; ++kb, ++vcount) {
                 const int b = vcount & 1;
@@ -1323,29 +1337,36 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     const float nm = fmaf(-m, kLog2e, 2.8150654e-3f);
                     neg_m2 = pack2(nm, nm);
                 }
-                tmem_ld32(sb + 32, vb);
-                if (kb < NB - 1) {
-                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                    tmem_st16(sb, pk);
-                    tmem_ld_wait();
-                    tmem_ld32(sb + 64, va);
-                    softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
-                    tmem_st16(sb + 16, pk);
-                    tmem_ld_wait();
-                    softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
-                    tmem_st16(sb + 32, pk);
-                } else {
-                    // last block of the frame: keys >= last_valid belong to the next frame (P = 0); chunks past last_steps are not read
+                if (kb == NB - 1) {
+                    // last block of the frame: keys >= last_valid belong to the next frame (P = 0); 32-key chunks without a valid key are
+                    // neither read nor written (P V stops after last_steps 16-key steps)
+                    if (last_valid > 32) tmem_ld32(sb + 32, vb);
                     softmax_block<32, POLY, true>(va, pk, last_valid, l2e2, neg_m2, l2);
                     tmem_st16(sb, pk);
-                    tmem_ld_wait();
-                    tmem_ld32(sb + 64, va);
-                    softmax_block<32, POLY, true>(vb, pk, last_valid - 32, l2e2, neg_m2, l2);
-                    tmem_st16(sb + 16, pk);
-                    tmem_ld_wait();
-                    softmax_block<32, POLY, true>(va, pk, last_valid - 64, l2e2, neg_m2, l2);
-                    tmem_st16(sb + 32, pk);
+                    if (last_valid > 32) {
+                        tmem_ld_wait();
+                        if (last_valid > 64) tmem_ld32(sb + 64, va);
+                        softmax_block<32, POLY, true>(vb, pk, last_valid - 32, l2e2, neg_m2, l2);
+                        tmem_st16(sb + 16, pk);
+                        if (last_valid > 64) {
+                            tmem_ld_wait();
+                            softmax_block<32, POLY, true>(va, pk, last_valid - 64, l2e2, neg_m2, l2);
+                            tmem_st16(sb + 32, pk);
+                        }
+                    }
+                    publish(b);
+                    continue;
                 }
+                tmem_ld32(sb + 32, vb);
+                softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                tmem_st16(sb, pk);
+                tmem_ld_wait();
+                tmem_ld32(sb + 64, va);
+                softmax_block<32, POLY, false>(vb, pk, 32, l2e2, neg_m2, l2);
+                tmem_st16(sb + 16, pk);
+                tmem_ld_wait();
+                softmax_block<32, POLY, false>(va, pk, 32, l2e2, neg_m2, l2);
+                tmem_st16(sb + 32, pk);
                 publish(b);
             }
             // ---- O / l -> bf16 ----
