@@ -231,10 +231,14 @@ def _attention_case(engine, t, n, heads, q_scale=0.125, plant=None, seed=None):
 @pytest.mark.parametrize("t,n,heads", [(201, 3, 12), (1029, 1, 12), (1374, 1, 12), (37, 2, 16), (256, 2, 12), (257, 1, 12),
                                        (9, 2, 12), (16, 1, 12), (31, 2, 12), (48, 1, 12), (185, 2, 12), (129, 5, 12), (240, 2, 16),
                                        (161, 2, 12), (176, 3, 12), (177, 2, 12), (192, 2, 16), (200, 1, 12), (208, 2, 12), (209, 2, 12),
-                                       (201, 70, 12), (193, 40, 16)])
+                                       (201, 70, 12), (193, 40, 16),
+                                       (300, 3, 12), (288, 2, 16), (289, 3, 12), (385, 1, 12), (1029, 2, 16), (640, 7, 12)])
 def test_attention(engine_small, t, n, heads):
-    """All three tensor-core kernels (general: T > 256; single-S persistent: T <= 160 and 208 < T <= 256; split-S: 160 < T <= 208)
-    incl. launches with several units per CTA ((201, 70, 12) = 840 units: both halves-first orders of the split-S kernel)."""
+    """All three tensor-core kernels (long-sequence persistent: T > 256; single-S persistent: T <= 160 and 208 < T <= 256; split-S:
+    160 < T <= 208) incl. launches with several units per CTA ((201, 70, 12) = 840 units: both halves-first orders of the split-S
+    kernel) and the long kernel's edges: a full last key block (288 = 3 x 96), a last block with ONE valid key (289, 385), an odd
+    number of units, query tiles without a live row in some warps (300: rows 256..299 of the third tile), more units than streams
+    (640 x 7 x 12 = 420 units)."""
     out, ref = _attention_case(engine_small, t, n, heads)
     assert rel_err(out, ref) < 8e-3                                                             # bf16 P and bf16 output
 
