@@ -1658,8 +1658,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         const int grid = pairs < sms ? pairs : sms;
         {
             LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
-            CRE_SMEM_ATTR_ONCE(attention_long_kernel<0x44u>, kLgSmemBytes);
-            attention_long_kernel<0x44u><<<grid, kLgThreads, kLgSmemBytes, stream>>>(tq, tkv, tout, lp);
+#define CRE_LG_LAUNCH(POLY_)                                                                                                     \
+    do {                                                                                                                         \
+        CRE_SMEM_ATTR_ONCE(attention_long_kernel<POLY_>, kLgSmemBytes);                                                          \
+        attention_long_kernel<POLY_><<<grid, kLgThreads, kLgSmemBytes, stream>>>(tq, tkv, tout, lp);                              \
+    } while (0)
+            if (g_attn_poly == 0) CRE_LG_LAUNCH(0x00u);
+            else if (g_attn_poly == 2) CRE_LG_LAUNCH(0x55u);
+            else CRE_LG_LAUNCH(0x44u);
+#undef CRE_LG_LAUNCH
             CRE_CUDA_OK(cudaGetLastError());
         }
         return launch_exact(a, stream);
