@@ -26,6 +26,12 @@ timeout 300 python tools/topk_profile.py > gpurun_out/plain4.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k regex:"pool_clips|topk_prepare|merge_topk|gallery_scan_small|gemm_tn_kernel<6" -s 5 -c 5 -f -o gpurun_out/prof_reid python tools/topk_profile.py > gpurun_out/ncu_reid.log 2>&1
 echo "ncu reid rc=$?"
-for r in prof_layer0 prof_tail prof_reid; do
+# the long-sequence attention kernel at 518 x 518 (configs[2]), first launch of a small run
+LONG="python bench.py --resize 518 --height 518 --width 518 --clips 2 --frames-per-clip 111 --batch-frames 222 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-baseline"
+timeout 300 $LONG > gpurun_out/plain5.log 2>&1 && \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"attention_long" -s 1 -c 1 -f -o gpurun_out/prof_attn_long2 $LONG > gpurun_out/ncu_attn_long2.log 2>&1
+echo "ncu long rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+for r in prof_layer0 prof_tail prof_reid prof_attn_long2; do
   [ -f gpurun_out/$r.ncu-rep ] && ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null
 done
