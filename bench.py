@@ -525,11 +525,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                "api": "DINOv3Pipeline.embed_clips(list of pinned host clips, sharded=ShardedReID) -> numpy clip embeddings + top-5",
                "host_affinity": numa,
                "h2d_only_gbs": h2d_only,
-               "h2d_only_frames_per_s": sum(h2d_only) * 1e9 / per,
+               # every rank copies the same bytes and the step ends with the slowest rank (max-over-ranks timing): N x the slowest rate
+               "h2d_only_frames_per_s": len(h2d_only) * min(h2d_only) * 1e9 / per,
                "note": f"{distinct} distinct pinned clips cycled to form the {clips}-clip batch (all bytes are copied every step); re-ID "
                        "runs against the row-sharded gallery (query all-gather, per-shard scan, candidate all-gather + merge inside the "
                        "timed call).  h2d_only_gbs = per-rank rate of the same copies with no kernels launched (all ranks copying at "
-                       "once); h2d_only_frames_per_s = the e2e ceiling those rates imply"}
+                       "once); h2d_only_frames_per_s = the e2e ceiling those rates imply = N x the SLOWEST rank's rate (weak scaling, the step ends with the slowest rank)"}
         del host
 
     # ---- GPU comparison point (N = 1): the stock HF path on this GPU, bounded sample --------------------------------
