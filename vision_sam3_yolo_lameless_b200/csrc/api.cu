@@ -675,6 +675,7 @@ int32_t cre_pool_clips(const float* frame_emb_dev, const int32_t* clip_offsets_d
 
 static const int kMaxSlots = 512;
 static int g_scan_small = 1;   // tuning: 0 routes every query count through the tile GEMM
+static int g_topk_stacked = 1; // tuning: 0 keeps two MMAs per k-step (hi and lo query tiles) also for <= 64 queries
 
 int64_t cre_gallery_scratch_bytes(int32_t q, int32_t dim, int32_t k) {
     if (q <= 0 || dim <= 0 || k <= 0 || k > CRE_TOPK_LIMIT) {
@@ -722,6 +723,7 @@ static int gallery_topk_pass(cre_ctx* ctx, const float* queries_dev, int q, int 
     p.part_scores = part_s;
     p.part_idx = part_i;
     p.part_slots = slots;
+    p.topk_stacked = (g_topk_stacked && q <= 64) ? 1 : 0;   // hi / lo halves as rows of ONE M = 128 tile: one MMA per k-step
     p.dump_scores = dump_scores_dev;
     p.cut_scores = cut_s;
     p.cut_idx = cut_i;
@@ -941,6 +943,10 @@ int32_t cre_set_tuning(const char* key, int32_t value) {
     }
     if (strcmp(key, "ln_fold") == 0) {
         g_ln_fold = value != 0;
+        return 0;
+    }
+    if (strcmp(key, "topk_stacked") == 0) {
+        g_topk_stacked = value != 0;
         return 0;
     }
     if (strcmp(key, "resid_split") == 0) {

@@ -252,7 +252,8 @@ int launch_gemm(int epi, int cg, const void* a, int64_t lda, const void* b, int6
         return launch_gemm(epi, cg, a, lda, b, ldb, q, num_sms, stream);
     }
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16(&ta, a, p.M, p.K, lda, kBlockM);
+    CRE_REQUIRE(!p.topk_stacked || (epi == EPI_TOPK && p.M <= 64), "gemm: the stacked hi / lo form needs EPI_TOPK and M <= 64 (M=%d)", p.M);
+    int rc = make_tmap_bf16(&ta, a, p.M, p.K, lda, p.topk_stacked ? 64 : kBlockM);   // stacked: two 64-row boxes fill one A tile
     if (rc) return rc;
     rc = make_tmap_bf16(&tb, b, p.N, p.b_k_extent, ldb, kBlockN / cg);
     if (rc) return rc;

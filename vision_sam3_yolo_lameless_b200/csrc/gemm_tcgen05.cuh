@@ -77,6 +77,7 @@ struct GemmParams {
     int patches_per_frame;
     // EPI_TOPK
     int topk;            // k <= kTopKMax
+    int topk_stacked;    // EPI_TOPK, M <= 64 queries: ONE A tile = rows [0, 64) hi halves, rows [64, 128) lo halves (see the epilogue)
     int col_base;        // global gallery index of column 0
     float* part_scores;  // [M, slots, k]
     int* part_idx;       // [M, slots, k]
@@ -130,7 +131,9 @@ struct GemmCfg {
     static constexpr int kSmemA = kBlockM * kBlockK * 2 * (EPI == EPI_TOPK ? 2 : 1);   // 16 KB
     static constexpr int kSmemB = (kBlockN / CG) * kBlockK * 2;   // 32 KB / 16 KB
     static constexpr int kEpiOff = kStages * (kSmemA + kSmemB);
-    static constexpr int kEpiBytes = epi_resid_x(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes : 0;
+    // EPI_TOPK: four 4 KB exchange tiles (stacked form: the lo-row warps hand their partial scores to the hi-row warps)
+    static constexpr int kEpiBytes = epi_resid_x(EPI) ? kEpiWarps * ln_warp_bytes(EPI) : epi_tma_store(EPI) ? kEpiWarps * kEpiStageBytes
+                                     : EPI == EPI_TOPK ? 4 * kEpiStageBytes : 0;
     static constexpr int kTableOff = kEpiOff + kEpiBytes;
     static constexpr int kTableBytes = EPI == EPI_QKV ? kRopeTableBytes : 0;
     static constexpr int kBarOff = kTableOff + kTableBytes;
@@ -347,7 +350,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (elect_one()) {
                     const uint32_t fb = full_bar(stage);
                     if constexpr (CG == 1) {
-                        mbar_arrive_expect_tx(fb, Cfg::kSmemA + Cfg::kSmemB);
+                        mbar_arrive_expect_tx(fb, (EPI == EPI_TOPK && p.topk_stacked ? kBlockM * kBlockK * 2 : Cfg::kSmemA) + Cfg::kSmemB);
                     } else {
                         // the leader's barrier tracks both halves of the stage: 2 arrivals + the bytes of both CTAs
                         if (is_leader) mbar_arrive_expect_tx(fb, 2 * (Cfg::kSmemA + Cfg::kSmemB));
@@ -366,8 +369,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         if (prow >= 0) tma_prefetch_2d(&tmap_a, pkb * kBlockK, prow);
                     }
                     tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA, ka, row0, kEvictNormal);
-                    if constexpr (EPI == EPI_TOPK)
-                        tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2, ka + p.b_k_extent, row0, kEvictNormal);
+                    if constexpr (EPI == EPI_TOPK) {
+                        // stacked form: 64-row boxes, hi halves of the queries into tile rows [0, 64), lo halves into rows [64, 128)
+                        const int lo_off = p.topk_stacked ? 64 * kBlockK * 2 : kBlockM * kBlockK * 2;
+                        tma_load_2d<CG>(&tmap_a, fb, smem_a + stage * Cfg::kSmemA + lo_off, ka + p.b_k_extent, row0, kEvictNormal);
+                    }
                     tma_load_2d<CG>(&tmap_b, fb, smem_b + stage * Cfg::kSmemB, kbb, col0, EPI == EPI_TOPK ? kEvictNormal : kEvictLast);
                 }
                 __syncwarp();
@@ -398,7 +404,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // +32 B per K=16 step inside the 128 B swizzle atom (descriptor address unit = 16 B)
                             umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                            if constexpr (EPI == EPI_TOPK) {   // + lo(query) . gallery into the same accumulator
+                            if constexpr (EPI == EPI_TOPK) if (!p.topk_stacked) {   // + lo(query) . gallery into the same accumulator
                                 const uint64_t da_lo = umma_desc_k_sw128(smem_a + stage * Cfg::kSmemA + kBlockM * kBlockK * 2);
                                 umma_bf16<CG>(tmem_d, da_lo + 2 * k, db + 2 * k, idesc, 1u);
                             }
@@ -509,6 +515,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float tk_s[kTopKMax];
         int tk_i[kTopKMax];
         int tk_mt = -1;
+        [[maybe_unused]] int tk_xc = 0;      // stacked form: chunks this (lo-row) warp has handed over so far
         auto topk_reset = [&]() {
 #pragma unroll
             for (int j = 0; j < kTopKMax; ++j) { tk_s[j] = -INFINITY; tk_i[j] = 0x7fffffff; }
@@ -984,6 +991,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     float x[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(a[j]);
+                    if constexpr (EPI == EPI_TOPK) {
+                        if (p.topk_stacked) {
+                            // Stacked form (M <= 64): accumulator rows [0, 64) hold hi(q) . g, rows [64, 128) lo(q) . g -- ONE MMA per
+                            // k-step instead of two (and half the query bytes per k-block from L2, which is what bounds this kernel at
+                            // small M).  The warps of lane quarters 2 / 3 hand their 32 x 32 partial scores to quarters 0 / 1 through a
+                            // swizzled shared-memory tile; named barriers (64 threads) pace the pair, one chunk at a time.
+                            const int pair = half * 2 + (quarter & 1);
+                            uint8_t* xt = smem_raw + (smem_base + Cfg::kEpiOff + pair * kEpiStageBytes - smem_u32(smem_raw)) + lane * 128;
+                            if (quarter >= 2) {
+                                if (tk_xc > 0) asm volatile("bar.sync %0, 64;" ::"r"(5 + pair) : "memory");     // tile drained by the partner
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    *reinterpret_cast<float4*>(xt + ((static_cast<uint32_t>(u) ^ r7) << 4)) =
+                                        make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+                                asm volatile("bar.arrive %0, 64;" ::"r"(1 + pair) : "memory");
+                                ++tk_xc;
+                                continue;
+                            }
+                            asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const float4 v = *reinterpret_cast<const float4*>(xt + ((static_cast<uint32_t>(u) ^ r7) << 4));
+                                x[4 * u] += v.x; x[4 * u + 1] += v.y; x[4 * u + 2] += v.z; x[4 * u + 3] += v.w;
+                            }
+                            asm volatile("bar.arrive %0, 64;" ::"r"(5 + pair) : "memory");
+                        }
+                    }
 
                     if constexpr (EPI == EPI_TOPK) {
                         if (row_ok) {
