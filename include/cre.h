@@ -235,8 +235,8 @@ int32_t cre_set_cta_group(int32_t cta_group);
  * "resid_split" (1 = residual stream as two bf16 halves, CRE_EPI_RESID_SP, default; 0 = fp32 stream + bf16 copy, CRE_EPI_RESID_LN), "attention_split" (1 = split-S
  * kernel for 160 < T <= 208, default), "attention_poly" (0 | 1 | 2: share of that kernel's exponentials on the FMA pipe),
  * "attention_split_mode" (bit 0: direct global stores of O, bit 1: PV of the second key half in one piece), "attention_split_delay"
- * (SM cycles by which the second query-tile group of that kernel trails the first), "attention_long" (1 = persistent long-sequence
- * kernel for T > 256, default; 0 = one CTA per query tile), "preprocess_tma" (2 = TMA-staged K1, row pairs, default; 1 = TMA-staged,
+ * (SM cycles by which the second query-tile group of that kernel trails the first), "attention_long" (1 = persistent key-block
+ * kernel for every T outside the split-S range, default; 0 = the round-1 kernels), "preprocess_tma" (2 = TMA-staged K1, row pairs, default; 1 = TMA-staged,
  * one row per warp; 0 = direct-load kernel), "preprocess_identity", "scan_small".  Every setting gives results inside the parity
  * tolerances (the three K1 settings: identical bits).  Unknown keys return -1. */
 int32_t cre_set_tuning(const char* key, int32_t value);

@@ -1331,9 +1331,11 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 tmem_ld_wait();
                 if (kb == 0) {
                     // stabiliser from the first 32 keys of the frame (CLS, registers, first patches); + log2(1 + 2^-9): see softmax_block
+                    // (frames shorter than 32 tokens: only their own keys -- the columns behind them hold the next frame's scores)
+                    const int npre = NB == 1 && last_valid < 32 ? last_valid : 32;
                     float m = __uint_as_float(va[0]);
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+                    for (int j = 1; j < 32; ++j) m = j < npre ? fmaxf(m, __uint_as_float(va[j])) : m;
                     const float nm = fmaf(-m, kLog2e, 2.8150654e-3f);
                     neg_m2 = pack2(nm, nm);
                 }
@@ -1529,7 +1531,8 @@ attention_exact_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int k_col0
 }
 
 static int g_attn_fast = 1;     // 0: general kernel for every T; 1: persistent kernels for T <= 256
-static int g_attn_long = 1;     // 1: persistent long-sequence kernel for T > 256; 0: one CTA per query tile (attention_kernel)
+static int g_attn_long = 1;     // 1: persistent key-block kernel for every T outside the split-S range; 0: the round-1 kernels (single-S
+                                // persistent for T <= 256, one CTA per query tile above)
 void set_attention_long(int on) { g_attn_long = on; }
 static int g_attn_split = 1;    // 1: split-S kernel for 160 < T <= 208; 0: the single-S fast kernel
 static int g_attn_poly = 1;     // split-S kernel: share of the exponentials on the FMA pipe (0: none, 1: 25 %, 2: 50 %)
@@ -1608,33 +1611,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
         }
         return launch_exact(a, stream);
     }
-    if (fast) {
-        int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 256);
-        if (rc) return rc;
-        rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
-        if (rc) return rc;
-        CRE_SMEM_ATTR_ONCE(attention_fast_kernel, kFaSmemBytes);
-        FaParams fp;
-        fp.t = a.t;
-        fp.heads = a.heads;
-        fp.kb = kb;
-        fp.units = a.n * a.heads;
-        fp.out = static_cast<__nv_bfloat16*>(a.out);
-        fp.ld_out = a.heads * 64;
-        fp.k_col0 = a.k_col0;
-        fp.v_col0 = a.v_col0;
-        fp.any_flag = a.any_flag;
-        fp.unit_flags = a.unit_flags;
-        const int grid = fp.units < sms ? fp.units : sms;
-        {
-            LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
-            attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
-            CRE_CUDA_OK(cudaGetLastError());
-        }
-        return launch_exact(a, stream);
-    }
     if (g_attn_long) {
-        // persistent long-sequence kernel: 96-key blocks, two query-tile streams per SM
+        // persistent long-sequence kernel: 96-key blocks, two query-tile streams per SM.  Also the kernel for every T outside the
+        // split-S range: measured against the single-S persistent kernel it wins at every T (tools/attn_t_sweep.py: T = 65 131 vs 88,
+        // T = 129 228 vs 196, T = 230 419 vs 384, T = 256 503 vs 464 TFLOP/s), which stays behind attention_long = 0
         int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 128);
         if (rc) return rc;
         rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kLgKeys);
@@ -1667,6 +1647,31 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
             else if (g_attn_poly == 2) CRE_LG_LAUNCH(0x55u);
             else CRE_LG_LAUNCH(0x44u);
 #undef CRE_LG_LAUNCH
+            CRE_CUDA_OK(cudaGetLastError());
+        }
+        return launch_exact(a, stream);
+    }
+    if (fast) {
+        int rc = make_tmap_bf16(&tq, a.qkv, rows, a.ld, a.ld, 256);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tkv, a.qkv, rows, a.ld, a.ld, kb);
+        if (rc) return rc;
+        CRE_SMEM_ATTR_ONCE(attention_fast_kernel, kFaSmemBytes);
+        FaParams fp;
+        fp.t = a.t;
+        fp.heads = a.heads;
+        fp.kb = kb;
+        fp.units = a.n * a.heads;
+        fp.out = static_cast<__nv_bfloat16*>(a.out);
+        fp.ld_out = a.heads * 64;
+        fp.k_col0 = a.k_col0;
+        fp.v_col0 = a.v_col0;
+        fp.any_flag = a.any_flag;
+        fp.unit_flags = a.unit_flags;
+        const int grid = fp.units < sms ? fp.units : sms;
+        {
+            LaunchScope scope(CRE_K_ATTENTION, 4.0 * a.t * static_cast<double>(a.t) * 64.0 * a.heads * a.n, stream);
+            attention_fast_kernel<<<grid, kFaThreads, kFaSmemBytes, stream>>>(tq, tkv, fp);
             CRE_CUDA_OK(cudaGetLastError());
         }
         return launch_exact(a, stream);
