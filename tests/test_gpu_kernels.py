@@ -290,6 +290,13 @@ def test_preprocess_no_resize_kernel_bit_identical(engine_small, bgr):
         _lib.set_tuning("preprocess_identity", 1)
     assert torch.equal(fast.view(torch.int16), slow.view(torch.int16))
     assert torch.equal(fast_p.view(torch.int16), slow.view(torch.int16))
+    # rows that are not 16-byte aligned (pitch 690 B, odd base offsets): the shifted-load path of the same kernel, same bits; the last
+    # frame ends exactly at the end of its allocation slice (no bytes to spare behind the last row)
+    for off in (0, 2, 5, 13):
+        flat = torch.zeros(5 * 224 * 230 * 3 + 16, dtype=torch.uint8, device=dev)
+        odd = flat[off:off + 5 * 224 * 230 * 3].view(5, 224, 230, 3)[:, :, :224, :]
+        odd.copy_(dense)
+        assert torch.equal(eng.preprocess(odd, bgr=bgr).view(torch.int16), slow.view(torch.int16)), off
     ref = preprocess_ref.patchify(preprocess_ref.preprocess(fr, bgr=bgr))
     assert (fast.float().cpu() - torch.from_numpy(ref)).abs().max().item() < 1.2e-2
 

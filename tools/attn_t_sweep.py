@@ -14,7 +14,7 @@ from vision_sam3_yolo_lameless_b200.synthetic import random_init_vit
 model = random_init_vit(layers=1)
 eng = ClipEmbedEngine(VitConfig.from_hf(model.config), model.state_dict(), max_frames=8)
 heads, d = 12, 768
-for t in (65, 129, 149, 160, 201, 230, 256, 261, 401, 785):
+for t in [int(x) for x in sys.argv[1:]] or (65, 129, 149, 160, 201, 230, 256, 261, 401, 785, 1029):
     n = max(8, 230000 // t)
     qkv = (torch.randn(n * t, 3 * d, device=eng.device) * 0.5).to(torch.bfloat16)
     row = []

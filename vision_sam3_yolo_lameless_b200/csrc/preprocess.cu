@@ -25,6 +25,7 @@ constexpr int kPreThreads = 448;   // x3 CTAs per SM (<= 48 registers)
 
 struct PreParams {
     const uint8_t* frames;
+    const uint8_t* frames_end;   // one past the last byte of the last frame's last row (the unaligned identity path never reads beyond it)
     int h, w;
     int64_t row_pitch, frame_pitch;
     int bgr, gh, gw;
@@ -198,10 +199,47 @@ __global__ void __launch_bounds__(256) preprocess_identity_kernel(const PreParam
     const int64_t frame = t / p.gh;
     const uint8_t* src = p.frames + frame * p.frame_pitch + static_cast<int64_t>(py * 16 + ky) * p.row_pitch + px * 48;
     uint32_t wds[12];
+    if (p.vec) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
-        wds[4 * i] = q.x; wds[4 * i + 1] = q.y; wds[4 * i + 2] = q.z; wds[4 * i + 3] = q.w;
+        for (int i = 0; i < 3; ++i) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            wds[4 * i] = q.x; wds[4 * i + 1] = q.y; wds[4 * i + 2] = q.z; wds[4 * i + 3] = q.w;
+        }
+    } else {
+        // rows that are not 16-byte aligned (e.g. 518-pixel rows: pitch 1 554 bytes): the four aligned vectors that cover the 48 bytes,
+        // shifted into place in registers (two select stages for the word offset, a funnel shift for the byte offset).  The fourth vector
+        // is only touched when the row really reaches into it, and never beyond the end of the frame buffer.
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+        const uint32_t sh = static_cast<uint32_t>(addr & 15);
+        const uint4* base = reinterpret_cast<const uint4*>(addr - sh);
+        uint32_t w[17];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint4 q = __ldg(base + i);
+            w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+        }
+        uint4 q3 = make_uint4(0u, 0u, 0u, 0u);
+        if (sh != 0) {                           // bytes [48 - sh, 48) of the row live in the fourth vector
+            const uint8_t* v3 = reinterpret_cast<const uint8_t*>(base + 3);
+            if (v3 + 16 <= p.frames_end) {
+                q3 = __ldg(base + 3);
+            } else {                             // the very last rows of the buffer: only the bytes that exist
+                uint32_t t[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 16 && v3 + j < p.frames_end; ++j) t[j >> 2] |= static_cast<uint32_t>(__ldg(v3 + j)) << (8 * (j & 3));
+                q3 = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        w[12] = q3.x; w[13] = q3.y; w[14] = q3.z; w[15] = q3.w; w[16] = 0u;
+        const bool b0 = (sh & 4) != 0, b1 = (sh & 8) != 0;
+        uint32_t v1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v1[i] = b0 ? w[i + 1] : w[i];
+        uint32_t v2[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) v2[i] = b1 ? v1[i + 2] : v1[i];
+        const uint32_t bits = (sh & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) wds[i] = __funnelshift_r(v2[i], v2[i + 1], bits);
     }
     float v[48];   // byte 3 i + j = pixel i, memory channel j
 #pragma unroll
@@ -814,6 +852,7 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     CRE_REQUIRE(a.row_pitch >= 3LL * a.w, "preprocess: row_pitch %lld < 3*w", (long long)a.row_pitch);
     PreParams p;
     p.frames = a.frames;
+    p.frames_end = a.frames + static_cast<int64_t>(a.n - 1) * a.frame_pitch + static_cast<int64_t>(a.h - 1) * a.row_pitch + 3LL * a.w;
     p.h = a.h;
     p.w = a.w;
     p.row_pitch = a.row_pitch;
@@ -836,7 +875,7 @@ int launch_preprocess(const PreprocArgs& a, cudaStream_t stream) {
     p.xkmax = a.tx.kmax;
     p.vec = ((reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && a.row_pitch % 16 == 0 && a.frame_pitch % 16 == 0) ? 1 : 0;
     p.rois = a.rois;
-    if (a.rois == nullptr && g_pre_identity && p.vec && a.ty.in == a.ty.out && a.tx.in == a.tx.out) {
+    if (a.rois == nullptr && g_pre_identity && a.ty.in == a.ty.out && a.tx.in == a.tx.out) {
         // no resize: normalise + patchify only
         const int64_t total = static_cast<int64_t>(a.n) * a.gh * a.gw * 16;
         LaunchScope scope(CRE_K_PREPROCESS, static_cast<double>(a.n) * (3.0 * a.h * a.w + 1536.0 * a.gh * a.gw), stream);
